@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- DCT-II + DCT-III round-trip throughput (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one forward (REDFT10 x REDFT10) plus one inverse (REDFT01 x REDFT01, fused 1/(4wh) store scale)
+2-D transform of every plane of the rank's batch, device resident, through the C ABI's dsp_dct_execute_dev.
+Default workload: 8192x8192 float32 single-channel planes (the size BASELINE.json's target is quoted on), `--planes`
+of them per GPU (weak scaling: per-GPU work is fixed).  Other workloads: --workload batch1024 (C4), spec512 (C1).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...   # CPU arm: the oracle port (scipy pocketfft, all host threads)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dct2+dct3 round-trip throughput"
+UNIT = "Gpixel/s"
+
+WORKLOADS = {
+    # name: (h, w, d, default planes per GPU, prec)
+    "plane8192": (8192, 8192, 1, 2, "f"),
+    "plane8192_f64": (8192, 8192, 1, 1, "d"),
+    "batch1024": (1024, 1024, 3, 64, "f"),
+    "spec512": (512, 512, 3, 64, "f"),
+    "plane4096x3": (4096, 4096, 3, 2, "f"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_roundtrip(h, w, d, prec, reps, nplanes=1):
+    """The oracle port timed on the host cores: scipy pocketfft dctn type 2 then type 3 over (h, w) of an
+    interleaved [h][w][d] buffer, all threads.  Returns (Gpixel/s, cores, seconds per round trip)."""
+    import numpy as np
+    from oracle import dct as od
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    x = rng.random((nplanes, h, w, d)).astype(np.float32 if prec == "f" else np.float64)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores)
+        z = od.dctn_fast(y, [od.REDFT01] * 2, axes=(1, 2), workers=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    del z
+    return nplanes * h * w * d / best / 1e9, cores, best
+
+
+def run_reference(args):
+    h, w, d, planes, prec = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: one plane / a few images of the workload per step
+    nplanes = 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
+    import numpy as np
+    from oracle import dct as od
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    x = rng.random((nplanes, h, w, d)).astype(np.float32 if prec == "f" else np.float64)
+    steps = min(args.steps, 5)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        od.dctn_fast(od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores), [od.REDFT01] * 2, axes=(1, 2), workers=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores)
+        od.dctn_fast(y, [od.REDFT01] * 2, axes=(1, 2), workers=cores)
+    dt = (time.perf_counter() - t0) / steps
+    val = nplanes * h * w * d / dt / 1e9
+    sample = "%d x %dx%dx%d %s per step, forward+inverse, scipy pocketfft workers=%d" % (nplanes, h, w, d, "f32" if prec == "f" else "f64", cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": [h, w, d], "note": "FFTW is not in the image: oracle port (pocketfft stand-in, not FFTW) on the host cores"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="plane8192", choices=sorted(WORKLOADS))
+    ap.add_argument("--planes", type=int, default=0, help="planes/images per GPU (0 = workload default)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dspfun_b200 import REDFT01, REDFT10, Plan, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.load()
+
+    h, w, d, planes, prec = WORKLOADS[args.workload]
+    if args.planes:
+        planes = args.planes
+    tdt = torch.float32 if prec == "f" else torch.float64
+    es = 4 if prec == "f" else 8
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    x = torch.rand((planes, h, w, d), device="cuda", dtype=tdt, generator=g)
+    x0 = x[0].clone()
+    fwd = Plan.interleaved_2d(prec, h, w, d, REDFT10, nbatch=planes)
+    inv = Plan.interleaved_2d(prec, h, w, d, REDFT01, nbatch=planes).fuse_scale(1.0, 1.0 / (4.0 * h * w))
+    stream = torch.cuda.current_stream().cuda_stream
+    ptr = x.data_ptr()
+
+    def step():
+        fwd.execute_dev(ptr, ptr, stream)
+        inv.execute_dev(ptr, ptr, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    fwd.profile(True); inv.profile(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.dsp_dct_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.dsp_dct_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    fwd.profile(False); inv.profile(False)
+    stats = [("fwd", s) for s in fwd.pass_stats()] + [("inv", s) for s in inv.pass_stats()]
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # round trip must be the identity (parity is the tests' job; this guards against a broken timed region)
+    err = (torch.linalg.norm((x[0] - x0).double()) / torch.linalg.norm(x0.double())).item()
+    samples_per_step = planes * h * w * d
+    value = world * samples_per_step * args.steps / (ms * 1e-3) / 1e9
+    ms_per_step = ms / args.steps
+
+    # roofline of the dominant kernel (largest share of the step)
+    peak, peak_src = peaks()
+    kern = []
+    for which, s in stats:
+        if s["launches"]:
+            avg_ms = s["ms_total"] / s["launches"]
+            kern.append({"plan": which, "kernel": s["kernel"], "axis": s["axis"], "n": s["n"], "grid": s["grid"],
+                         "smem_bytes": s["smem_bytes"], "avg_ms": avg_ms,
+                         "achieved_gbs": 2 * es * s["samples"] / (avg_ms * 1e-3) / 1e9})
+    dom = max(kern, key=lambda k: k["avg_ms"]) if kern else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": "%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]),
+                    "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["achieved_gbs"] / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": 2 * es * samples_per_step,
+                    "round_trip_frac": (4 * es * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak}
+
+    # end to end through the C ABI with pinned HOST buffers: H2D + passes + D2H for forward, then for inverse
+    e2e = None
+    if not args.no_e2e:
+        nbytes = samples_per_step * es
+        hp = lib.dsp_dct_alloc(nbytes)
+        if not hp:
+            raise SystemExit("dsp_dct_alloc failed: " + capi.last_error(lib))
+        ctype = ctypes.c_float if prec == "f" else ctypes.c_double
+        hbuf = np.ctypeslib.as_array((ctype * samples_per_step).from_address(hp))
+        hbuf[:] = np.random.default_rng(5 + rank).random(samples_per_step, dtype=np.float32 if prec == "f" else np.float64)
+        ksteps = max(2, min(args.steps, 5))
+        fwd.execute_host(hbuf); inv.execute_host(hbuf)      # warm (allocates the plan's staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            fwd.execute_host(hbuf)
+            inv.execute_host(hbuf)
+        barrier()
+        dt = (time.perf_counter() - t0) / ksteps
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * samples_per_step / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
+               "d2h_bytes_per_step": 2 * nbytes, "steps": ksteps, "ms_per_step": dt * 1e3,
+               "path": "dsp_dct_execute_host (pinned host buffers, forward then inverse)"}
+        lib.dsp_dct_free(hp)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nplanes = 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
+        v, cores, secs = cpu_roundtrip(h, w, d, prec, 3, nplanes)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d x %dx%dx%d round trip, best of 3 (%.0f ms), scipy pocketfft workers=%d (FFTW not in image)" % (nplanes, h, w, d, secs * 1e3, cores)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "shape": [h, w, d], "planes_per_gpu": planes,
+                       "bytes_per_gpu": samples_per_step * es, "l2_policy": "inputs larger than L2 (%.0f MB per GPU per pass)" % (samples_per_step * es / 1e6),
+                       "parallelism": "independent planes per GPU, no collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "kernels": kern, "roundtrip_rel_l2": err,
+        }
+        print(json.dumps(out))
+    fwd.destroy(); inv.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

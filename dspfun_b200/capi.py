@@ -1,0 +1,109 @@
+"""ctypes binding of include/dsp_dct.h.
+
+``load()`` binds the product library (dspfun_b200/libdspdct.so) and raises loudly if it has not been built.
+``bind(path)`` attaches the same prototypes to any build of the library sources; the test-suite uses it for the
+host SIMT emulation under tests/emu (a test harness, never used by this package).
+"""
+import ctypes
+import os
+
+REDFT01 = 4
+REDFT10 = 5
+
+SCALE_LOG, SCALE_LINEAR = 0, 1
+SIGN_ABS, SIGN_SHIFT, SIGN_SATURATE, SIGN_RETAIN = 0, 1, 2, 3
+RANGE_ONE, RANGE_DC, RANGE_DCS = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdspdct.so")
+
+# every symbol include/dsp_dct.h declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "dsp_dct_plan_many", "dsp_dct_plan_many_batched", "dsp_dct_plan_2d", "dsp_dct_execute", "dsp_dct_execute_host",
+    "dsp_dct_execute_dev", "dsp_dct_destroy", "dsp_dct_alloc", "dsp_dct_free", "dsp_dct_cleanup",
+    "dsp_dct_last_error", "dsp_dct_launch_count", "dsp_dct_fuse_scale", "dsp_dct_fuse_spec", "dsp_dct_spec_dc",
+    "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
+]
+
+
+class DspDctError(RuntimeError):
+    pass
+
+
+class SpecParams(ctypes.Structure):
+    _fields_ = [("scaletype", ctypes.c_int), ("signtype", ctypes.c_int), ("rangetype", ctypes.c_int),
+                ("gain", ctypes.c_double)]
+
+
+class PassStat(ctypes.Structure):
+    _fields_ = [("is_row", ctypes.c_int), ("axis", ctypes.c_int), ("n", ctypes.c_int), ("grid", ctypes.c_int),
+                ("block", ctypes.c_int), ("smem_bytes", ctypes.c_size_t), ("launches", ctypes.c_int),
+                ("ms_total", ctypes.c_double), ("samples", ctypes.c_double)]
+
+
+class IspecParams(ctypes.Structure):
+    _fields_ = [("scaletype", ctypes.c_int), ("signtype", ctypes.c_int), ("gain", ctypes.c_double),
+                ("max", ctypes.c_double * 4), ("preserve_dc", ctypes.c_int), ("dc", ctypes.c_double * 4),
+                ("signmap", ctypes.c_void_p)]
+
+
+def bind(path):
+    lib = ctypes.CDLL(path)
+    vp, ci, cu, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_double
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.dsp_dct_plan_many.restype = vp
+    lib.dsp_dct_plan_many.argtypes = [ctypes.c_char, ci, ip, ci, vp, ip, ci, ci, vp, ip, ci, ci, ip, cu]
+    lib.dsp_dct_plan_many_batched.restype = vp
+    lib.dsp_dct_plan_many_batched.argtypes = [ctypes.c_char, ci, ip, ci, vp, ip, ci, ci, vp, ip, ci, ci, ip, cu,
+                                              ci, ctypes.c_ssize_t, ctypes.c_ssize_t]
+    lib.dsp_dct_plan_2d.restype = vp
+    lib.dsp_dct_plan_2d.argtypes = [ctypes.c_char, ci, ci, vp, vp, ci, ci, cu]
+    lib.dsp_dct_execute.restype = None
+    lib.dsp_dct_execute.argtypes = [vp]
+    lib.dsp_dct_execute_host.restype = ci
+    lib.dsp_dct_execute_host.argtypes = [vp, vp, vp]
+    lib.dsp_dct_execute_dev.restype = ci
+    lib.dsp_dct_execute_dev.argtypes = [vp, vp, vp, vp]
+    lib.dsp_dct_destroy.restype = None
+    lib.dsp_dct_destroy.argtypes = [vp]
+    lib.dsp_dct_alloc.restype = vp
+    lib.dsp_dct_alloc.argtypes = [ctypes.c_size_t]
+    lib.dsp_dct_free.restype = None
+    lib.dsp_dct_free.argtypes = [vp]
+    lib.dsp_dct_cleanup.restype = None
+    lib.dsp_dct_last_error.restype = ctypes.c_char_p
+    lib.dsp_dct_launch_count.restype = ctypes.c_ulonglong
+    lib.dsp_dct_fuse_scale.restype = ci
+    lib.dsp_dct_fuse_scale.argtypes = [vp, cd, cd]
+    lib.dsp_dct_fuse_spec.restype = ci
+    lib.dsp_dct_fuse_spec.argtypes = [vp, ctypes.POINTER(SpecParams)]
+    lib.dsp_dct_spec_dc.restype = ci
+    lib.dsp_dct_spec_dc.argtypes = [vp, ctypes.POINTER(cd), ci]
+    lib.dsp_dct_fuse_ispec.restype = ci
+    lib.dsp_dct_fuse_ispec.argtypes = [vp, ctypes.POINTER(IspecParams)]
+    lib.dsp_dct_profile.restype = ci
+    lib.dsp_dct_profile.argtypes = [vp, ci]
+    lib.dsp_dct_num_passes.restype = ci
+    lib.dsp_dct_num_passes.argtypes = [vp]
+    lib.dsp_dct_pass_stat_get.restype = ci
+    lib.dsp_dct_pass_stat_get.argtypes = [vp, ci, ctypes.POINTER(PassStat)]
+    return lib
+
+
+_LIB = None
+
+
+def load():
+    """The product library.  Raises if the CUDA extension has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise DspDctError(
+                "dspfun_b200/libdspdct.so is missing: build it with `make -C dspfun_b200/csrc` "
+                "(or python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+        _LIB = bind(LIB_PATH)
+    return _LIB
+
+
+def last_error(lib):
+    return lib.dsp_dct_last_error().decode("utf-8", "replace")

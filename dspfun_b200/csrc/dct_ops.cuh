@@ -1,0 +1,135 @@
+// dct_ops.cuh -- pointwise stages fused into the first (load side) or last (store side) pass of a plan.
+//
+// OpNone is the zero-cost default.  OpAny is one POD that carries any of the tool-level stages and dispatches on
+// a CTA-uniform `kind`; kernels are instantiated for <OpNone, OpNone> and <OpAny, OpAny> only.
+//
+// Reference formulas (all /root/reference): spec/spec.c:66-139 (OP_SPEC), spec/ispec.c:84-163 (OP_ISPEC),
+// scan/scan.c:296-298 (OP_SCALE), scan/scan.c:429-459 (OP_SCAN_MASK / OP_SCAN_ACCUM).
+// The reference rounds to `coeff` after every loop; the stages below round to T at the same points and do the
+// transcendental steps in double ("intermediate" = D, the reference default for COEFF_PRECISION=F).
+#pragma once
+#include "dct_core.cuh"
+#include <math.h>
+
+namespace dsp {
+
+enum {
+	OP_NONE = 0,
+	OP_SCALE,        // v * p[0]
+	OP_ACCUM_DC,     // store side of spec's row pass: sum the k = 0 outputs per channel into aux (double[4])
+	OP_SPEC,         // store side of spec's column pass
+	OP_ISPEC,        // load side of ispec's first pass
+	OP_SCAN_MASK,    // load side: keep coefficient iff lo <= index[y][x] < hi, zero DC   (scan/scan.c:429-445)
+	OP_SCAN_ACCUM,   // store side: sum[i] += v ; out = sum[i]                             (scan/scan.c:451-456)
+};
+
+struct OpAny {
+	int kind;
+	int scaletype, signtype, rangetype;
+	int d, w, h, flag;
+	int lo, hi;
+	double p[4];             // OP_SCALE: p[0] = factor.  OP_SPEC/ISPEC: p[0] = gain, p[1] = norm (2wh)
+	double q[4];             // OP_ISPEC: log1p(max[z]) or max[z] per channel; OP_SPEC (range one): the same
+	double dc[4];            // OP_ISPEC preserve_dc values
+	const void *aux_c;       // OP_SPEC: double[8] device scalars {scale_z[4], -, -, -, -};  OP_ISPEC: u8 signmap;  OP_SCAN_MASK: int32 index map
+	void *aux;               // OP_ACCUM_DC: double[4] accumulators;  OP_SPEC: double[4] DC out;  OP_SCAN_ACCUM: T sum buffer
+
+	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+		typedef double I;
+		const I SQRT2 = 1.41421356237309504880168872420969808;
+		switch (kind) {
+		default:
+		case OP_NONE: return v;
+		case OP_SCALE: return (T)(v * (T)p[0]);
+		case OP_ACCUM_DC: {
+			if (c.c[2] == 0) {
+#if DSP_GPU
+				atomicAdd((double *)aux + c.c[3], (double)v);
+#else
+				((double *)aux)[c.c[3]] += (double)v;
+#endif
+			}
+			return v;
+		}
+		case OP_SPEC: {
+			const int y = c.c[1], x = c.c[2], ch = c.c[3];
+			T f = v;
+			if (y == 0 && x == 0) ((double *)aux)[ch] = (double)f / ((double)w * (double)h * 4.0);   // spec.c:66-68
+			if (y == 0) f = (T)((I)f / SQRT2);                                                       // :70-71
+			if (x == 0) f = (T)((I)f / SQRT2);                                                       // :72-74
+			f = (T)((I)f / p[1]);                                                                    // :76-78
+			f = (T)((I)f * p[0]);                                                                    // :89-90
+			const I sc = DSP_LDG((const double *)aux_c + ch);     // log1p(max[z]) or max[z], resolved on device
+			if (scaletype == 0) f = (T)(copysign(log1p(fabs((I)f)), (I)f) / sc);                     // :110-117
+			else                f = (T)(f / (T)sc);                                                  // :118-121
+			if (signtype == 0) f = (T)fabs((I)f);                                                    // :126-128
+			else if (signtype == 1) f = (T)(((I)f / 2.0 + 0.5) * 254 / 255);                         // :130-132
+			else if (signtype == 2) { if (y != 0 || x != 0) f = signbit((I)f) ? (T)0 : (T)1; }        // :134-136
+			return f;
+		}
+		case OP_ISPEC: {
+			const int y = c.c[1], x = c.c[2], ch = c.c[3];
+			const bool pix0 = (y == 0 && x == 0);
+			T f = v;
+			if (signtype == 0) {                                                                     // ispec.c:87-98
+				if (aux_c && !pix0) {
+					const int sm = (int)DSP_LDG((const unsigned char *)aux_c + ((size_t)y * w + x) * d + ch) - 128;
+					f = (T)copysign((I)f, (I)sm);
+				}
+			} else if (signtype == 1) f = (T)(((I)f * 255.0 / 254 - 0.5) * 2);                       // :100-103
+			else if (signtype == 2) { if (!pix0) f = f * 2 - 1; }                                     // :104-107
+			if (scaletype == 0) {                                                                    // :136-143
+				const T prod = f * (T)q[ch];
+				f = (T)copysign(expm1(fabs((I)prod)), (I)f);
+			} else f = f * (T)q[ch];                                                                 // :144-147
+			f = (T)((I)f / p[0]);                                                                    // :150-151
+			if (y == 0) f = (T)((I)f * SQRT2);                                                       // :153-154
+			if (x == 0) f = (T)((I)f * SQRT2);                                                       // :155-157
+			f = f / 2;                                                                               // :158-159
+			if (flag && pix0) f = (T)dc[ch];                                                         // :161-163
+			return f;
+		}
+		case OP_SCAN_MASK: {
+			const int y = c.c[1], x = c.c[2];
+			if (y == 0 && x == 0) return (T)0;                                                       // scan.c:445
+			const int idx = DSP_LDG((const int *)aux_c + (size_t)y * w + x);
+			return (idx >= lo && idx < hi) ? v : (T)0;                                               // scan.c:429-432
+		}
+		case OP_SCAN_ACCUM: {
+			T *sum = (T *)aux + (((size_t)c.c[1] * w + c.c[2]) * d + c.c[3]);
+			const T s = *sum + v;                                                                    // scan.c:454
+			*sum = s;
+			return s;
+		}
+		}
+	}
+};
+
+// Resolves spec's data-dependent range (spec/spec.c:92-117) once the row pass has accumulated the per-channel
+// sums S[z] of its k = 0 outputs: Y[0,0,z] = 2 S[z].  Writes scale_z[ch] = log1p(max[ch]) or max[ch].
+template <class T>
+DSP_DEV void spec_resolve_range(const OpAny &op, const double *acc, double *scale_z) {
+	typedef double I;
+	const I SQRT2 = 1.41421356237309504880168872420969808;
+	T mx[4];
+	for (int z = 0; z < op.d && z < 4; z++) {
+		T f = (T)(2.0 * acc[z]);
+		f = (T)((I)f / SQRT2); f = (T)((I)f / SQRT2);
+		f = (T)((I)f / op.p[1]);
+		f = (T)((I)f * op.p[0]);
+		mx[z] = f;
+	}
+	if (op.rangetype == 0) for (int z = 0; z < op.d && z < 4; z++) mx[z] = (T)op.p[0];
+	else if (op.rangetype == 1) {
+		T m = mx[0];
+		for (int z = 1; z < op.d && z < 4; z++) if (mx[z] > m) m = mx[z];
+		for (int z = 0; z < op.d && z < 4; z++) mx[z] = m;
+	}
+	for (int z = 0; z < op.d && z < 4; z++) {
+		T m = mx[z];
+		if (op.scaletype == 0) m = (T)log1p((I)m);     // mc(log1p): rounded to coeff
+		scale_z[z] = (double)m;
+	}
+}
+
+}  // namespace dsp

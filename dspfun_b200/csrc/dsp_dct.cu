@@ -1,0 +1,732 @@
+// dsp_dct.cu -- planner, table cache, kernel launches and the C ABI of libdspdct (include/dsp_dct.h).
+//
+// A plan is a list of passes, one per transformed axis.  The pass over the contiguous axis uses the row
+// kernel (a line of n*d elements per sequence group), every other axis uses the column kernel (a tile of
+// adjacent columns over the whole axis).  Forward plans run the contiguous axis first, inverse plans run it
+// last, so a forward+inverse round trip meets in the middle on the same column tiles (L2 reuse).
+#include "../../include/dsp_dct.h"
+#include "dct_core.cuh"
+#include "dct_ops.cuh"
+#include "dsp_rt.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#if !DSP_GPU
+#include <thread>
+#endif
+
+namespace dsp {
+
+static thread_local std::string g_err;
+static std::mutex g_mu;
+static std::atomic<unsigned long long> g_launches(0);
+
+static const size_t kMaxSmem = 227 * 1024;
+static const int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------ kernels
+#if DSP_GPU
+template <class T, class L, class S>
+__global__ void __launch_bounds__(kThreads) k_row(const __grid_constant__ RowArgs a, const __grid_constant__ L l,
+                                                  const __grid_constant__ S s) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	cta_row_pass<T, L, S>(a, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<T> *)smem);
+}
+template <class T, class L, class S>
+__global__ void __launch_bounds__(kThreads) k_col(const __grid_constant__ ColArgs a, const __grid_constant__ L l,
+                                                  const __grid_constant__ S s) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	cta_col_pass<T, L, S>(a, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<T> *)smem);
+}
+template <class T> __global__ void k_spec_resolve(OpAny op, const double *acc, double *scale_z) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) spec_resolve_range<T>(op, acc, scale_z);
+}
+#endif
+
+template <class T, class L, class S>
+static bool launch_row(const RowArgs &a, const L &l, const S &s, int grid, size_t smem, rt_stream st) {
+#if DSP_GPU
+	static size_t attr_set = 0;
+	if (smem > 48 * 1024 && smem > attr_set) {
+		if (!rt_ok(cudaFuncSetAttribute(k_row<T, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), g_err, "smem attr"))
+			return false;
+		attr_set = kMaxSmem;
+	}
+	k_row<T, L, S><<<grid, kThreads, smem, st>>>(a, l, s);
+	if (!rt_ok(cudaGetLastError(), g_err, "row kernel launch")) return false;
+#else
+	(void)st;
+	std::vector<unsigned char> buf(smem + 64);
+	for (int cta = 0; cta < grid; cta++) cta_row_pass<T, L, S>(a, l, s, cta, 0, kThreads, kThreads, (C2<T> *)buf.data());
+#endif
+	g_launches++;
+	return true;
+}
+
+template <class T, class L, class S>
+static bool launch_col(const ColArgs &a, const L &l, const S &s, int grid, size_t smem, rt_stream st) {
+#if DSP_GPU
+	static size_t attr_set = 0;
+	if (smem > 48 * 1024 && smem > attr_set) {
+		if (!rt_ok(cudaFuncSetAttribute(k_col<T, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), g_err, "smem attr"))
+			return false;
+		attr_set = kMaxSmem;
+	}
+	k_col<T, L, S><<<grid, kThreads, smem, st>>>(a, l, s);
+	if (!rt_ok(cudaGetLastError(), g_err, "column kernel launch")) return false;
+#else
+	(void)st;
+	std::vector<unsigned char> buf(smem + 64);
+	for (int cta = 0; cta < grid; cta++) cta_col_pass<T, L, S>(a, l, s, cta, 0, kThreads, kThreads, (C2<T> *)buf.data());
+#endif
+	g_launches++;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+static FastDiv mk_fd(uint32_t d) {
+	FastDiv f;
+	f.d = d ? d : 1;
+	if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
+	uint32_t k = 0;
+	while ((1ull << k) < f.d) k++;
+	const uint32_t p = 31 + k;
+	f.mul = (uint32_t)(((1ull << p) + f.d - 1) / f.d);
+	f.shr = p - 32;
+	return f;
+}
+
+// radices for the DIF passes: odd primes first (largest sub-stride), powers of two last with 16s at the end,
+// which keeps every pass's smem access pattern a power-of-two stride under the bank-skew padding.
+static bool factorize(int n, std::vector<int> &fac) {
+	fac.clear();
+	static const int odd[] = {13, 11, 7, 5, 3};
+	for (int r : odd)
+		while (n % r == 0) { fac.push_back(r); n /= r; }
+	int e = 0;
+	while (n % 2 == 0) { e++; n /= 2; }
+	if (n != 1) return false;
+	if (e % 4) fac.push_back(1 << (e % 4));
+	for (int i = 0; i < e / 4; i++) fac.push_back(16);
+	return (int)fac.size() <= DSP_MAX_FAC;
+}
+
+struct Tables {
+	int n;
+	char prec;
+	std::vector<int> fac;
+	int npad;
+	void *tw, *om;
+	uint16_t *pos2, *pos3;
+};
+static std::map<std::pair<int, std::pair<int, char>>, Tables *> g_tables;
+
+template <class T> static int pad_of(int e) { return Pad<T>::of(e); }
+
+template <class T> static Tables *build_tables(int n) {
+	Tables *t = new Tables();
+	t->n = n;
+	t->prec = sizeof(T) == 4 ? 'f' : 'd';
+	t->tw = t->om = nullptr;
+	t->pos2 = t->pos3 = nullptr;
+	if (!factorize(n, t->fac)) {
+		g_err = "transform length " + std::to_string(n) + " has a prime factor > 13 (not supported by the on-chip FFT path yet)";
+		delete t;
+		return nullptr;
+	}
+	t->npad = pad_of<T>(n - 1) + 1;
+	const long double pi = 3.141592653589793238462643383279502884L;
+	std::vector<C2<T>> tw(n), om(n / 2 + 1);
+	for (int k = 0; k < n; k++) {
+		const long double a = 2 * pi * (long double)k / (long double)n;
+		tw[k].x = (T)cosl(a);
+		tw[k].y = (T)(-sinl(a));
+	}
+	for (int k = 0; k <= n / 2; k++) {
+		const long double a = pi * (long double)k / (2 * (long double)n);
+		om[k].x = (T)cosl(a);
+		om[k].y = (T)sinl(a);
+	}
+	std::vector<uint16_t> pos2(n), pos3(n);
+	for (int k = 0; k < n; k++) {
+		int kk = k, P = 0, stride = n;
+		for (int r : t->fac) { stride /= r; P += (kk % r) * stride; kk /= r; }
+		pos2[k] = (uint16_t)P;
+	}
+	for (int j = 0; j < n; j++) pos3[j] = pos2[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)];
+	std::string err;
+	bool ok = rt_malloc(&t->tw, sizeof(C2<T>) * n, err) && rt_malloc(&t->om, sizeof(C2<T>) * (n / 2 + 1), err) &&
+	          rt_malloc((void **)&t->pos2, sizeof(uint16_t) * n, err) && rt_malloc((void **)&t->pos3, sizeof(uint16_t) * n, err) &&
+	          rt_h2d(t->tw, tw.data(), sizeof(C2<T>) * n, 0, err) && rt_h2d(t->om, om.data(), sizeof(C2<T>) * (n / 2 + 1), 0, err) &&
+	          rt_h2d(t->pos2, pos2.data(), sizeof(uint16_t) * n, 0, err) && rt_h2d(t->pos3, pos3.data(), sizeof(uint16_t) * n, 0, err) &&
+	          rt_sync(0, err);
+	if (!ok) {
+		g_err = err;
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3);
+		delete t;
+		return nullptr;
+	}
+	return t;
+}
+
+static Tables *get_tables(int n, char prec) {
+	if (n > 65535) { g_err = "transform length " + std::to_string(n) + " too large"; return nullptr; }
+	auto key = std::make_pair(rt_device(), std::make_pair(n, prec));
+	auto it = g_tables.find(key);
+	if (it != g_tables.end()) return it->second;
+	Tables *t = prec == 'f' ? build_tables<float>(n) : build_tables<double>(n);
+	if (t) g_tables[key] = t;
+	return t;
+}
+
+static void fill_fft(FftDesc &f, const Tables *t) {
+	memset(&f, 0, sizeof(f));
+	f.n = t->n;
+	f.nfac = (int)t->fac.size();
+	int L = t->n;
+	for (int p = 0; p < f.nfac; p++) {
+		f.fac[p] = t->fac[p];
+		f.dM[p] = mk_fd((uint32_t)(L / f.fac[p]));
+		f.dNb[p] = mk_fd((uint32_t)(t->n / f.fac[p]));
+		L /= f.fac[p];
+	}
+	f.npad = t->npad;
+	f.tw = t->tw; f.om = t->om; f.pos2 = t->pos2; f.pos3 = t->pos3;
+	f.dHalf = mk_fd((uint32_t)(t->n / 2 + 1));
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct Level { long long cnt, is, os; int slot; };
+
+struct PassPlan {
+	bool row;
+	int axis;
+	RowArgs ra;
+	ColArgs ca;
+	int grid;
+	size_t smem;
+	bool vec_in_layout, vec_out_layout;
+	OpAny lop, sop;
+	bool fused;
+};
+
+}  // namespace dsp
+
+using namespace dsp;
+
+struct dsp_dct_plan_s {
+	char prec;
+	int es;                                  // element size
+	int rank, n[3], kind[3];
+	int d;                                   // interleave (1 = planar)
+	int device;
+	void *in, *out;                          // pointers captured at plan time
+	size_t in_span, out_span;                // elements covered by the layouts
+	bool out_has_gaps;
+	std::vector<PassPlan> passes;
+	// host-pointer staging
+	void *d_in, *d_out;
+	size_t d_in_bytes, d_out_bytes;
+	// fusion state
+	int fuse_kind;                           // 0 none, 1 spec, 2 ispec
+	double *d_scalars;                       // acc[4] | scale_z[4] | dc_out[4]
+	unsigned char *d_signmap;
+	bool need_acc;
+	rt_stream last_stream;
+	// per-pass profiling
+	bool profiling;
+	double samples_per_launch;
+#if DSP_GPU
+	std::vector<cudaEvent_t> ev;             // 2 events per pass per recorded execute
+#endif
+	std::vector<int> ev_pass;
+};
+
+namespace dsp {
+
+static bool set_outer(Outer &o, std::vector<Level> lv) {
+	std::vector<Level> keep;
+	for (auto &l : lv) if (l.cnt > 1) keep.push_back(l);
+	if (keep.size() > 4) { g_err = "layout needs more than four outer loop levels"; return false; }
+	for (int i = 0; i < 4; i++) {
+		if (i < (int)keep.size()) { o.cnt[i] = (int)keep[i].cnt; o.is[i] = keep[i].is; o.os[i] = keep[i].os; o.slot[i] = keep[i].slot; }
+		else { o.cnt[i] = 1; o.is[i] = 0; o.os[i] = 0; o.slot[i] = -1; }
+	}
+	o.d0 = mk_fd((uint32_t)o.cnt[0]);
+	o.d01 = mk_fd((uint32_t)((long long)o.cnt[0] * o.cnt[1]));
+	o.d012 = mk_fd((uint32_t)((long long)o.cnt[0] * o.cnt[1] * o.cnt[2]));
+	return true;
+}
+
+static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int istride, int idist, const int *onembed,
+                       int ostride, int odist, int nbatch, long long ibdist, long long obdist) {
+	const int r = P->rank;
+	const int VN = 16 / P->es;
+	// ---- layout
+	int d;
+	if (istride == 1 && ostride == 1) d = 1;
+	else if (istride == howmany && ostride == howmany && idist == 1 && odist == 1 && howmany > 1) d = howmany;
+	else {
+		g_err = "unsupported layout: need planar (stride 1) or channel-interleaved (stride == howmany, dist == 1) buffers";
+		return false;
+	}
+	P->d = d;
+	long long sI[3], sO[3];
+	const int *ie = inembed ? inembed : P->n, *oe = onembed ? onembed : P->n;
+	for (int i = 0; i < r; i++)
+		if (ie[i] < P->n[i] || oe[i] < P->n[i]) {
+			if (i > 0) { g_err = "embed smaller than the logical size"; return false; }
+		}
+	sI[r - 1] = d; sO[r - 1] = d;
+	for (int i = r - 2; i >= 0; i--) { sI[i] = sI[i + 1] * ie[i + 1]; sO[i] = sO[i + 1] * oe[i + 1]; }
+	std::vector<Level> batch;
+	if (d == 1 && howmany > 1) batch.push_back(Level{howmany, idist, odist, 3});
+	if (nbatch > 1) batch.push_back(Level{nbatch, ibdist, obdist, 4});
+	// spans (elements) for host staging
+	long long ispan = 1, ospan = 1, dense = (long long)d;
+	for (int i = 0; i < r; i++) { ispan += (long long)(P->n[i] - 1) * sI[i]; ospan += (long long)(P->n[i] - 1) * sO[i]; dense *= P->n[i]; }
+	ispan += d - 1; ospan += d - 1;
+	for (auto &b : batch) { ispan += (b.cnt - 1) * b.is; ospan += (b.cnt - 1) * b.os; dense *= b.cnt; }
+	P->in_span = (size_t)ispan; P->out_span = (size_t)ospan;
+	P->out_has_gaps = ospan != dense;
+	P->samples_per_launch = (double)dense;
+
+	// ---- pass order
+	std::vector<int> order;
+	if (P->kind[0] == DSP_DCT_REDFT10) for (int a = r - 1; a >= 0; a--) order.push_back(a);
+	else for (int a = 0; a < r; a++) order.push_back(a);
+
+	const size_t cbytes = 2 * (size_t)P->es;
+	for (size_t pi = 0; pi < order.size(); pi++) {
+		const int ax = order[pi];
+		const bool first = pi == 0;
+		const long long *sIn = first ? sI : sO;
+		Tables *t = get_tables(P->n[ax], P->prec);
+		if (!t) return false;
+		PassPlan pp;
+		memset(&pp.ra, 0, sizeof(pp.ra)); memset(&pp.ca, 0, sizeof(pp.ca));
+		memset(&pp.lop, 0, sizeof(pp.lop)); memset(&pp.sop, 0, sizeof(pp.sop));
+		pp.fused = false;
+		pp.axis = ax;
+		pp.row = ax == r - 1;
+		const size_t seqb = (size_t)t->npad * cbytes;
+		std::vector<Level> lv;
+		bool vin = true, vout = true;
+		if (pp.row) {
+			for (int a = r - 2; a >= 0; a--) lv.push_back(Level{P->n[a], sIn[a], sO[a], a + 3 - r});
+			for (auto &b : batch) lv.push_back(Level{b.cnt, first ? b.is : b.os, b.os, b.slot});
+			RowArgs &A = pp.ra;
+			fill_fft(A.f, t);
+			A.kind = P->kind[ax];
+			A.d = d; A.dd = mk_fd((uint32_t)d);
+			long long nl = 1;
+			for (auto &l : lv) { nl *= l.cnt; if (l.cnt > 1 && (l.is % VN)) vin = false; if (l.cnt > 1 && (l.os % VN)) vout = false; }
+			if (nl >= (1ll << 31)) { g_err = "too many lines"; return false; }
+			A.nlines = (int)nl;
+			if (!set_outer(A.o, lv)) return false;
+			A.ax_slot = 2;
+			const size_t pairb = seqb * (size_t)d;
+			if (pairb > kMaxSmem) { g_err = "transform length " + std::to_string(P->n[ax]) + " does not fit on chip"; return false; }
+			long long pairs = (long long)((48 * 1024) / pairb);
+			if (pairs < 1) pairs = 1;
+			const long long total_pairs = (nl + 1) / 2;
+			// keep at least ~4 CTAs per SM worth of work when the problem allows it
+			while (pairs > 1 && total_pairs / pairs < 4 * 148) pairs--;
+			if (pairs > total_pairs) pairs = total_pairs;
+			A.lines_per_cta = (int)(2 * pairs);
+			pp.grid = (int)((nl + A.lines_per_cta - 1) / A.lines_per_cta);
+			pp.smem = (size_t)pairs * pairb;
+		} else {
+			for (int a = r - 2; a >= 0; a--) if (a != ax) lv.push_back(Level{P->n[a], sIn[a], sO[a], a + 3 - r});
+			for (auto &b : batch) lv.push_back(Level{b.cnt, first ? b.is : b.os, b.os, b.slot});
+			ColArgs &A = pp.ca;
+			fill_fft(A.f, t);
+			A.kind = P->kind[ax];
+			A.ncols = P->n[r - 1] * d;
+			A.d = d; A.dd = mk_fd((uint32_t)d);
+			A.ax_is = sIn[ax]; A.ax_os = sO[ax];
+			if (A.ax_is % VN) vin = false;
+			if (A.ax_os % VN) vout = false;
+			long long no = 1;
+			for (auto &l : lv) { no *= l.cnt; if (l.cnt > 1 && (l.is % VN)) vin = false; if (l.cnt > 1 && (l.os % VN)) vout = false; }
+			if (!set_outer(A.o, lv)) return false;
+			A.ax_slot = ax + 3 - r; A.col_slot = 2;
+			// columns per CTA: as wide as fits ~64 KB (wider rows of the tile = longer contiguous global segments)
+			const int cand[] = {8 * VN, 4 * VN, 2 * VN, VN};
+			int tc = 0;
+			for (int c : cand) if ((size_t)(c / 2) * seqb <= 64 * 1024) { tc = c; break; }
+			if (!tc) {
+				tc = (VN >= 4 && 2 * seqb <= kMaxSmem) ? VN : 2;
+				if ((size_t)(tc / 2) * seqb > kMaxSmem) { g_err = "transform length " + std::to_string(P->n[ax]) + " does not fit on chip"; return false; }
+			}
+			while (tc > VN && tc / 2 >= A.ncols) tc /= 2;
+			// enough CTAs to fill the machine
+			while (tc > 2 * VN && ((A.ncols + tc - 1) / tc) * no < 2 * 148) tc /= 2;
+			A.tc = tc;
+			A.ntiles = (A.ncols + tc - 1) / tc;
+			A.dtiles = mk_fd((uint32_t)A.ntiles);
+			const long long g = (long long)A.ntiles * no;
+			if (g >= (1ll << 31)) { g_err = "too many column tiles"; return false; }
+			pp.grid = (int)g;
+			pp.smem = (size_t)((tc + 1) / 2) * seqb;
+		}
+		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
+		P->passes.push_back(pp);
+	}
+	return true;
+}
+
+template <class T>
+static bool run_pass_t(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st) {
+	const bool ain = ((uintptr_t)in % 16) == 0, aout = ((uintptr_t)out % 16) == 0;
+	if (pp.row) {
+		RowArgs a = pp.ra;
+		a.in = in; a.out = out;
+		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
+		if (pp.fused) return launch_row<T, OpAny, OpAny>(a, pp.lop, pp.sop, pp.grid, pp.smem, st);
+		return launch_row<T, OpNone, OpNone>(a, OpNone(), OpNone(), pp.grid, pp.smem, st);
+	}
+	ColArgs a = pp.ca;
+	a.in = in; a.out = out;
+	a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
+	if (pp.fused) return launch_col<T, OpAny, OpAny>(a, pp.lop, pp.sop, pp.grid, pp.smem, st);
+	return launch_col<T, OpNone, OpNone>(a, OpNone(), OpNone(), pp.grid, pp.smem, st);
+}
+
+static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st) {
+	if (P->need_acc && !rt_zero(P->d_scalars, sizeof(double) * 4, st, g_err)) return false;
+	for (size_t i = 0; i < P->passes.size(); i++) {
+		PassPlan &pp = P->passes[i];
+		const void *in = i == 0 ? d_in : d_out;
+#if DSP_GPU
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		if (P->profiling) {
+			cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, st);
+		}
+#endif
+		const bool ok = P->prec == 'f' ? run_pass_t<float>(P, pp, in, d_out, st) : run_pass_t<double>(P, pp, in, d_out, st);
+		if (!ok) return false;
+#if DSP_GPU
+		if (P->profiling) {
+			cudaEventRecord(e1, st);
+			P->ev.push_back(e0); P->ev.push_back(e1);
+			P->ev_pass.push_back((int)i);
+		}
+#endif
+		if (P->fuse_kind == 1 && i == 0) {
+			const OpAny &op = P->passes.back().sop;
+#if DSP_GPU
+			if (P->prec == 'f') k_spec_resolve<float><<<1, 32, 0, st>>>(op, P->d_scalars, P->d_scalars + 4);
+			else k_spec_resolve<double><<<1, 32, 0, st>>>(op, P->d_scalars, P->d_scalars + 4);
+			if (!rt_ok(cudaGetLastError(), g_err, "spec resolve launch")) return false;
+#else
+			if (P->prec == 'f') spec_resolve_range<float>(op, P->d_scalars, P->d_scalars + 4);
+			else spec_resolve_range<double>(op, P->d_scalars, P->d_scalars + 4);
+#endif
+			g_launches++;
+		}
+	}
+	P->last_stream = st;
+	return true;
+}
+
+static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, void *in, const int *inembed, int istride,
+                              int idist, void *out, const int *onembed, int ostride, int odist, const int *kind,
+                              int nbatch, long long ibdist, long long obdist) {
+	g_err.clear();
+	if (prec != 'f' && prec != 'd') { g_err = "precision must be 'f' or 'd' (long double has no GPU equivalent)"; return nullptr; }
+	if (rank < 1 || rank > 3) { g_err = "rank must be 1..3"; return nullptr; }
+	if (!n || !kind) { g_err = "null n/kind"; return nullptr; }
+	if (howmany < 1 || nbatch < 1) { g_err = "howmany/nbatch must be >= 1"; return nullptr; }
+	for (int i = 0; i < rank; i++) {
+		if (n[i] < 1) { g_err = "transform sizes must be >= 1"; return nullptr; }
+		if (kind[i] != DSP_DCT_REDFT10 && kind[i] != DSP_DCT_REDFT01) {
+			g_err = "only REDFT10 (DCT-II) and REDFT01 (DCT-III) are supported";
+			return nullptr;
+		}
+	}
+	std::lock_guard<std::mutex> lock(g_mu);
+	if (!rt_init(g_err)) return nullptr;
+	dsp_dct_plan_s *P = new dsp_dct_plan_s();
+	P->prec = prec;
+	P->es = prec == 'f' ? 4 : 8;
+	P->rank = rank;
+	for (int i = 0; i < 3; i++) { P->n[i] = i < rank ? n[i] : 1; P->kind[i] = i < rank ? kind[i] : 0; }
+	P->device = rt_device();
+	P->in = in; P->out = out;
+	P->d_in = P->d_out = nullptr;
+	P->d_in_bytes = P->d_out_bytes = 0;
+	P->fuse_kind = 0;
+	P->d_scalars = nullptr;
+	P->d_signmap = nullptr;
+	P->need_acc = false;
+	P->last_stream = 0;
+	P->profiling = false;
+	P->samples_per_launch = 0;
+	if (!build_plan(P, howmany, inembed, istride, idist, onembed, ostride, odist, nbatch, ibdist, obdist)) {
+		delete P;
+		return nullptr;
+	}
+	return P;
+}
+
+static bool ensure_staging(dsp_dct_plan_s *P, bool inplace) {
+	const size_t ib = P->in_span * (size_t)P->es, ob = P->out_span * (size_t)P->es;
+	if (inplace) {
+		const size_t need = ib > ob ? ib : ob;
+		if (P->d_in_bytes < need) {
+			rt_free(P->d_in);
+			P->d_in = nullptr; P->d_in_bytes = 0;
+			if (!rt_malloc(&P->d_in, need, g_err)) return false;
+			P->d_in_bytes = need;
+		}
+		return true;
+	}
+	if (P->d_in_bytes < ib) {
+		rt_free(P->d_in);
+		P->d_in = nullptr; P->d_in_bytes = 0;
+		if (!rt_malloc(&P->d_in, ib, g_err)) return false;
+		P->d_in_bytes = ib;
+	}
+	if (P->d_out_bytes < ob) {
+		rt_free(P->d_out);
+		P->d_out = nullptr; P->d_out_bytes = 0;
+		if (!rt_malloc(&P->d_out, ob, g_err)) return false;
+		P->d_out_bytes = ob;
+	}
+	return true;
+}
+
+static bool execute_host(dsp_dct_plan_s *P, void *in, void *out) {
+	const bool inplace = in == out;
+	if (!ensure_staging(P, inplace)) return false;
+	void *din = P->d_in, *dout = inplace ? P->d_in : P->d_out;
+	rt_stream st = 0;
+	if (!rt_h2d(din, in, P->in_span * (size_t)P->es, st, g_err)) return false;
+	if (!inplace && P->out_has_gaps && !rt_h2d(dout, out, P->out_span * (size_t)P->es, st, g_err)) return false;
+	if (!run_passes(P, din, dout, st)) return false;
+	if (!rt_d2h(out, dout, P->out_span * (size_t)P->es, st, g_err)) return false;
+	return rt_sync(st, g_err);
+}
+
+static bool ensure_scalars(dsp_dct_plan_s *P) {
+	if (P->d_scalars) return true;
+	if (!rt_malloc((void **)&P->d_scalars, sizeof(double) * 16, g_err)) return false;
+	return rt_zero(P->d_scalars, sizeof(double) * 16, 0, g_err) && rt_sync(0, g_err);
+}
+
+}  // namespace dsp
+
+// ================================================================================================ C ABI
+extern "C" {
+
+dsp_dct_plan dsp_dct_plan_many(char prec, int rank, const int *n, int howmany, void *in, const int *inembed, int istride,
+                               int idist, void *out, const int *onembed, int ostride, int odist, const int *kind,
+                               unsigned flags) {
+	(void)flags;
+	return make_plan(prec, rank, n, howmany, in, inembed, istride, idist, out, onembed, ostride, odist, kind, 1, 0, 0);
+}
+
+dsp_dct_plan dsp_dct_plan_many_batched(char prec, int rank, const int *n, int howmany, void *in, const int *inembed,
+                                       int istride, int idist, void *out, const int *onembed, int ostride, int odist,
+                                       const int *kind, unsigned flags, int nbatch, ptrdiff_t ibdist, ptrdiff_t obdist) {
+	(void)flags;
+	return make_plan(prec, rank, n, howmany, in, inembed, istride, idist, out, onembed, ostride, odist, kind, nbatch,
+	                 (long long)ibdist, (long long)obdist);
+}
+
+dsp_dct_plan dsp_dct_plan_2d(char prec, int n0, int n1, void *in, void *out, int kind0, int kind1, unsigned flags) {
+	const int n[2] = {n0, n1}, kind[2] = {kind0, kind1};
+	(void)flags;
+	return make_plan(prec, 2, n, 1, in, nullptr, 1, 0, out, nullptr, 1, 0, kind, 1, 0, 0);
+}
+
+int dsp_dct_execute_host(dsp_dct_plan p, void *in, void *out) {
+	g_err.clear();
+	if (!p || !in || !out) { g_err = "null plan or buffer"; return 1; }
+	return execute_host(p, in, out) ? 0 : 1;
+}
+
+int dsp_dct_execute_dev(dsp_dct_plan p, void *d_in, void *d_out, void *stream) {
+	g_err.clear();
+	if (!p || !d_in || !d_out) { g_err = "null plan or buffer"; return 1; }
+	return run_passes(p, d_in, d_out, (rt_stream)stream) ? 0 : 1;
+}
+
+void dsp_dct_execute(dsp_dct_plan p) {
+	g_err.clear();
+	if (!p) { g_err = "null plan"; return; }
+	bool ok;
+	if (rt_is_device_ptr(p->in)) ok = run_passes(p, p->in, p->out, 0) && rt_sync(0, g_err);
+	else ok = execute_host(p, p->in, p->out);
+	if (!ok) fprintf(stderr, "dsp_dct_execute: %s\n", g_err.c_str());
+}
+
+void dsp_dct_destroy(dsp_dct_plan p) {
+	if (!p) return;
+	rt_free(p->d_in);
+	rt_free(p->d_out);
+	rt_free(p->d_scalars);
+	rt_free(p->d_signmap);
+#if DSP_GPU
+	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+#endif
+	delete p;
+}
+
+void *dsp_dct_alloc(size_t bytes) {
+	g_err.clear();
+	std::string e;
+	if (!rt_init(e)) { g_err = e; return nullptr; }
+	void *p = rt_host_alloc(bytes);
+	if (!p) g_err = "pinned host allocation failed";
+	return p;
+}
+
+void dsp_dct_free(void *p) { rt_host_free(p); }
+
+void dsp_dct_cleanup(void) {
+	std::lock_guard<std::mutex> lock(g_mu);
+	for (auto &kv : g_tables) {
+		Tables *t = kv.second;
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3);
+		delete t;
+	}
+	g_tables.clear();
+}
+
+const char *dsp_dct_last_error(void) { return g_err.c_str(); }
+
+unsigned long long dsp_dct_launch_count(void) { return g_launches.load(); }
+
+int dsp_dct_profile(dsp_dct_plan p, int enable) {
+	if (!p) return 1;
+	p->profiling = enable != 0;
+	return 0;
+}
+
+int dsp_dct_num_passes(dsp_dct_plan p) { return p ? (int)p->passes.size() : 0; }
+
+int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out) {
+	g_err.clear();
+	if (!p || !out || i < 0 || i >= (int)p->passes.size()) { g_err = "pass index out of range"; return 1; }
+	const PassPlan &pp = p->passes[(size_t)i];
+	memset(out, 0, sizeof(*out));
+	out->is_row = pp.row ? 1 : 0;
+	out->axis = pp.axis;
+	out->n = p->n[pp.axis];
+	out->grid = pp.grid;
+	out->block = kThreads;
+	out->smem_bytes = pp.smem;
+	out->samples = p->samples_per_launch;
+#if DSP_GPU
+	std::vector<cudaEvent_t> keep;
+	std::vector<int> keep_pass;
+	for (size_t k = 0; k < p->ev_pass.size(); k++) {
+		cudaEvent_t e0 = p->ev[2 * k], e1 = p->ev[2 * k + 1];
+		if (p->ev_pass[k] != i) { keep.push_back(e0); keep.push_back(e1); keep_pass.push_back(p->ev_pass[k]); continue; }
+		float ms = 0;
+		if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
+			out->ms_total += ms;
+			out->launches++;
+		}
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
+	}
+	p->ev.swap(keep);
+	p->ev_pass.swap(keep_pass);
+#endif
+	return 0;
+}
+
+int dsp_dct_fuse_scale(dsp_dct_plan p, double load_scale, double store_scale) {
+	g_err.clear();
+	if (!p) { g_err = "null plan"; return 1; }
+	if (p->fuse_kind) { g_err = "plan already carries a fused stage"; return 1; }
+	PassPlan &f = p->passes.front(), &l = p->passes.back();
+	if (load_scale != 1.0) { f.lop.kind = OP_SCALE; f.lop.p[0] = load_scale; f.fused = true; }
+	if (store_scale != 1.0) { l.sop.kind = OP_SCALE; l.sop.p[0] = store_scale; l.fused = true; }
+	return 0;
+}
+
+int dsp_dct_fuse_spec(dsp_dct_plan p, const dsp_spec_params *sp) {
+	g_err.clear();
+	if (!p || !sp) { g_err = "null plan or params"; return 1; }
+	if (p->rank != 2 || p->kind[0] != DSP_DCT_REDFT10 || p->kind[1] != DSP_DCT_REDFT10) { g_err = "spec fusion needs a rank-2 REDFT10 plan"; return 1; }
+	if (p->d > 4) { g_err = "spec fusion supports at most 4 channels"; return 1; }
+	if (p->fuse_kind) { g_err = "plan already carries a fused stage"; return 1; }
+	if (!ensure_scalars(p)) return 1;
+	const int h = p->n[0], w = p->n[1];
+	PassPlan &rowp = p->passes.front(), &colp = p->passes.back();
+	OpAny op;
+	memset(&op, 0, sizeof(op));
+	op.kind = OP_SPEC;
+	op.scaletype = sp->scaletype; op.signtype = sp->signtype; op.rangetype = sp->rangetype;
+	op.d = p->d; op.w = w; op.h = h;
+	op.p[0] = sp->gain; op.p[1] = 2.0 * (double)w * (double)h;
+	op.aux_c = p->d_scalars + 4;
+	op.aux = p->d_scalars + 8;
+	colp.sop = op; colp.fused = true;
+	if (sp->rangetype != DSP_SPEC_RANGE_ONE) {
+		memset(&rowp.sop, 0, sizeof(OpAny));
+		rowp.sop.kind = OP_ACCUM_DC;
+		rowp.sop.aux = p->d_scalars;
+		rowp.fused = true;
+		p->need_acc = true;
+	}
+	p->fuse_kind = 1;
+	return 0;
+}
+
+int dsp_dct_spec_dc(dsp_dct_plan p, double *dc, int d) {
+	g_err.clear();
+	if (!p || p->fuse_kind != 1 || !dc || d < 1 || d > 4) { g_err = "plan has no spec stage"; return 1; }
+	if (!rt_sync(p->last_stream, g_err)) return 1;
+	if (!rt_d2h(dc, p->d_scalars + 8, sizeof(double) * (size_t)d, 0, g_err)) return 1;
+	return rt_sync(0, g_err) ? 0 : 1;
+}
+
+int dsp_dct_fuse_ispec(dsp_dct_plan p, const dsp_ispec_params *ip) {
+	g_err.clear();
+	if (!p || !ip) { g_err = "null plan or params"; return 1; }
+	if (p->rank != 2 || p->kind[0] != DSP_DCT_REDFT01 || p->kind[1] != DSP_DCT_REDFT01) { g_err = "ispec fusion needs a rank-2 REDFT01 plan"; return 1; }
+	if (p->d > 4) { g_err = "ispec fusion supports at most 4 channels"; return 1; }
+	if (p->fuse_kind) { g_err = "plan already carries a fused stage"; return 1; }
+	const int h = p->n[0], w = p->n[1];
+	OpAny op;
+	memset(&op, 0, sizeof(op));
+	op.kind = OP_ISPEC;
+	op.scaletype = ip->scaletype; op.signtype = ip->signtype;
+	op.d = p->d; op.w = w; op.h = h;
+	op.p[0] = ip->gain;
+	op.flag = ip->preserve_dc;
+	for (int z = 0; z < 4; z++) {
+		// spec/ispec.c:138: max[z] = log1p(max[z]) stored back into coeff precision
+		double m = ip->max[z];
+		if (p->prec == 'f') m = (double)(float)m;
+		if (ip->scaletype == DSP_SPEC_SCALE_LOG) { m = log1p(m); if (p->prec == 'f') m = (double)(float)m; }
+		op.q[z] = m;
+		op.dc[z] = ip->dc[z];
+	}
+	if (ip->signmap) {
+		const size_t bytes = (size_t)h * w * p->d;
+		if (rt_is_device_ptr(ip->signmap)) op.aux_c = ip->signmap;
+		else {
+			if (!rt_malloc((void **)&p->d_signmap, bytes, g_err)) return 1;
+			if (!rt_h2d(p->d_signmap, ip->signmap, bytes, 0, g_err) || !rt_sync(0, g_err)) return 1;
+			op.aux_c = p->d_signmap;
+		}
+	}
+	PassPlan &f = p->passes.front();
+	f.lop = op; f.fused = true;
+	p->fuse_kind = 2;
+	return 0;
+}
+
+}  // extern "C"

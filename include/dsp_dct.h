@@ -1,0 +1,146 @@
+/*
+ * dsp_dct.h -- C ABI of libdspdct: B200 (sm_100a) DCT-II / DCT-III plans behind dspfun's FFTW call sites.
+ *
+ * This is the drop-in boundary.  dspfun's tools reach their transform through FFTW's r2r planner interface,
+ * spelled fftw(call) -> fftwf_call / fftw_call by /root/reference/include/precision.h:115.  Each entry point
+ * below cites the reference call site(s) it replaces.  shim/fftw3.h maps the FFTW names the tools use onto
+ * these functions so spec.c / ispec.c / zoom.c / scan.c / motion.c / draw.c compile unchanged.
+ *
+ * Conventions
+ *   prec      'f' (COEFF_PRECISION=F, float buffers) or 'd' (COEFF_PRECISION=D, double buffers).
+ *             'l' (long double) has no GPU equivalent and is rejected.
+ *   kinds     DSP_DCT_REDFT10 (unnormalised DCT-II,  Y_k = 2 sum_j X_j cos(pi (j+1/2) k / n)) and
+ *             DSP_DCT_REDFT01 (unnormalised DCT-III, Y_k = X_0 + 2 sum_{j>=1} X_j cos(pi j (k+1/2) / n)),
+ *             the only two kinds the reference ever plans.  Same numeric values as FFTW's fftw_r2r_kind.
+ *   pointers  `in`/`out` given at plan time may be host or device pointers (detected).  Host buffers are
+ *             staged through plan-owned device memory inside dsp_dct_execute; device buffers are transformed
+ *             where they are.  dsp_dct_execute_dev is the device-resident, stream-ordered entry.
+ *   errors    a failing call returns NULL / non-zero and leaves a message in dsp_dct_last_error().  There is
+ *             no CPU fallback: without a usable CUDA device every plan call fails.
+ */
+#ifndef DSP_DCT_H
+#define DSP_DCT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSP_DCT_REDFT01 4
+#define DSP_DCT_REDFT10 5
+
+/* planner-effort flags are accepted and ignored (values match fftw3.h) */
+#define DSP_DCT_MEASURE    (0U)
+#define DSP_DCT_EXHAUSTIVE (1U << 3)
+#define DSP_DCT_PATIENT    (1U << 5)
+#define DSP_DCT_ESTIMATE   (1U << 6)
+
+typedef struct dsp_dct_plan_s *dsp_dct_plan;
+
+/* Replaces fftw(plan_many_r2r): spec/spec.c:63, spec/ispec.c:165, zoom/zoom.c:263, scan/scan.c:292,359,
+ * motion/motion.c:535-538,549-552.  Same argument meaning as FFTW's advanced interface.  Supported layouts:
+ * planar (istride == ostride == 1, any howmany/dist/embed) and channel-interleaved (stride == howmany,
+ * dist == 1, the layout of every image tool).  rank 1..3.  Never touches the user buffers at plan time. */
+dsp_dct_plan dsp_dct_plan_many(char prec, int rank, const int *n, int howmany,
+                               void *in, const int *inembed, int istride, int idist,
+                               void *out, const int *onembed, int ostride, int odist,
+                               const int *kind, unsigned flags);
+
+/* Same, with one more outermost batch level (nbatch independent copies of the whole plan_many problem,
+ * ibdist / obdist elements apart): the batched-images configuration, one launch per pass for all images. */
+dsp_dct_plan dsp_dct_plan_many_batched(char prec, int rank, const int *n, int howmany,
+                                       void *in, const int *inembed, int istride, int idist,
+                                       void *out, const int *onembed, int ostride, int odist,
+                                       const int *kind, unsigned flags,
+                                       int nbatch, ptrdiff_t ibdist, ptrdiff_t obdist);
+
+/* Replaces fftw(plan_r2r_2d): applybasis/draw.c:74. */
+dsp_dct_plan dsp_dct_plan_2d(char prec, int n0, int n1, void *in, void *out, int kind0, int kind1, unsigned flags);
+
+/* Replaces fftw(execute): spec/spec.c:64, spec/ispec.c:166, zoom/zoom.c:264, scan/scan.c:293,407,447,
+ * motion/motion.c:641,753, applybasis/draw.c:75.  Transforms the buffers given at plan time; returns when
+ * the result is visible to the host (host buffers) or the work is complete (device buffers). */
+void dsp_dct_execute(dsp_dct_plan p);
+
+/* New-array execute on host buffers with the plan's layout (fftw_execute_r2r analogue).  0 on success. */
+int dsp_dct_execute_host(dsp_dct_plan p, void *in, void *out);
+
+/* Device-resident execute: d_in / d_out are device pointers with the plan's layout; kernels are enqueued on
+ * `stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising.  0 on success. */
+int dsp_dct_execute_dev(dsp_dct_plan p, void *d_in, void *d_out, void *stream);
+
+/* Replaces fftw(destroy_plan): spec/spec.c:65, spec/ispec.c:167, zoom/zoom.c:265, scan/scan.c:294,
+ * motion/motion.c:834, applybasis/draw.c:76. */
+void dsp_dct_destroy(dsp_dct_plan p);
+
+/* Replace fftw(alloc_real) / fftw(free) (spec/spec.c:59,143, motion/motion.c:500,826): pinned host memory, so
+ * dsp_dct_execute's staging copies run at full PCIe rate. */
+void *dsp_dct_alloc(size_t bytes);
+void dsp_dct_free(void *p);
+
+/* Replace fftw(cleanup) (zoom/zoom.c:266, motion/motion.c:836): releases cached twiddle tables. */
+void dsp_dct_cleanup(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *dsp_dct_last_error(void);
+
+/* Number of this library's kernels launched so far by this process (bench.py's gpu_launches). */
+unsigned long long dsp_dct_launch_count(void);
+
+/* Per-pass device timing (CUDA events on the launching stream around every pass of every execute while enabled).
+ * dsp_dct_pass_stat blocks until the recorded executes finished, returns the statistics accumulated since the
+ * last call for pass `i` and resets them.  Returns non-zero when `i` is out of range. */
+typedef struct {
+	int is_row;          /* 1: contiguous-axis (row) kernel, 0: strided-axis (column) kernel */
+	int axis, n;         /* transformed axis and its length */
+	int grid, block;     /* launch geometry */
+	size_t smem_bytes;   /* dynamic shared memory per CTA */
+	int launches;        /* launches accumulated */
+	double ms_total;     /* their summed device time */
+	double samples;      /* scalar samples one launch reads and writes */
+} dsp_dct_pass_stat;
+int dsp_dct_profile(dsp_dct_plan p, int enable);
+int dsp_dct_num_passes(dsp_dct_plan p);
+int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out);
+
+/* ---- fused pointwise stages (run inside the first / last pass; no extra trip through HBM) ---------------- */
+
+/* Multiply every element by load_scale as it is read and by store_scale as it is written.
+ * scan/scan.c:296-298 (coeffs /= w*h*4) is store_scale = 1/(4wh) on the forward plan. */
+int dsp_dct_fuse_scale(dsp_dct_plan p, double load_scale, double store_scale);
+
+enum { DSP_SPEC_SCALE_LOG = 0, DSP_SPEC_SCALE_LINEAR = 1 };
+enum { DSP_SPEC_SIGN_ABS = 0, DSP_SPEC_SIGN_SHIFT = 1, DSP_SPEC_SIGN_SATURATE = 2, DSP_SPEC_SIGN_RETAIN = 3 };
+enum { DSP_SPEC_RANGE_ONE = 0, DSP_SPEC_RANGE_DC = 1, DSP_SPEC_RANGE_DCS = 2 };
+
+/* spec's post-transform loops (spec/spec.c:66-139) fused into the last pass of a rank-2 REDFT10 plan:
+ * DC capture, row0/col0 /sqrt2, /(2wh), *gain, range (one|dc|dcs), scale (log|linear), sign (abs|shift|
+ * saturate|retain).  `gain` is the already-resolved multiplier (spec/spec.c:81-87).  After execute the DC
+ * property values (spec/spec.c:66-68) are available from dsp_dct_spec_dc(). */
+typedef struct {
+	int scaletype, signtype, rangetype;
+	double gain;
+} dsp_spec_params;
+int dsp_dct_fuse_spec(dsp_dct_plan p, const dsp_spec_params *sp);
+/* copies the d DC values of the last execute (blocks until that execute finished).  0 on success. */
+int dsp_dct_spec_dc(dsp_dct_plan p, double *dc, int d);
+
+/* ispec's pre-transform loops (spec/ispec.c:84-163) fused into the first pass of a rank-2 REDFT01 plan.
+ * max[z] is the already-resolved range (spec/ispec.c:119-134, before the log1p of :138); dc[] is only read
+ * when preserve_dc is set.  signmap (device or host pointer to u8 [h][w][d], or NULL) is spec/ispec.c:87-98. */
+typedef struct {
+	int scaletype, signtype;
+	double gain;
+	double max[4];
+	int preserve_dc;
+	double dc[4];
+	const unsigned char *signmap;
+} dsp_ispec_params;
+int dsp_dct_fuse_ispec(dsp_dct_plan p, const dsp_ispec_params *ip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+"""CPU suite: the kernel sources compiled as a host SIMT emulation (tests/emu) vs the oracle.  Checks the host
+logic (planner, tables, layouts) and the kernels' index arithmetic; the GPU suite repeats these on the device."""
+import numpy as np
+import pytest
+
+from dspfun_b200 import REDFT01, REDFT10, Plan, capi
+from tests import cases
+from tests.emu import emu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu.load()
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", cases.SHAPES_2D)
+def test_interleaved_2d(lib, prec, kind, shape):
+    cases.check_interleaved_2d(lib, prec, *shape, kind, definition=max(shape[:2]) <= 64)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_out_of_place_preserves_input(lib, prec):
+    cases.check_interleaved_2d(lib, prec, 24, 40, 3, REDFT01, inplace=False)
+    cases.check_interleaved_2d(lib, prec, 24, 40, 1, REDFT10, inplace=False)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_rank1_batches(lib, prec, kind):
+    cases.check_rank1_batch(lib, prec, 64, 5, kind)
+    cases.check_rank1_batch(lib, prec, 60, 7, kind, dist=67)
+    cases.check_rank1_batch(lib, prec, 2048, 3, kind)
+    cases.check_rank1_batch(lib, prec, 1, 4, kind)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_planar_3d_embed(lib, prec, kind):
+    cases.check_planar_3d_embed(lib, prec, (8, 8, 8), (8, 8, 8), kind)
+    cases.check_planar_3d_embed(lib, prec, (4, 6, 10), (7, 9, 12), kind)
+    cases.check_planar_3d_embed(lib, prec, (1, 16, 24), (1, 16, 24), kind)      # motion's default depth-1 blocks
+    cases.check_planar_3d_embed(lib, prec, (16, 15, 20), (16, 27, 36), kind)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_batched_images_roundtrip(lib, prec):
+    cases.check_batched_images(lib, prec, 5, 16, 24, 3)
+    cases.check_batched_images(lib, prec, 3, 32, 32, 1)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("typ", [2, 3])
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 32, 64, 128, 256, 512, 1024])
+def test_fftw_golden_vectors(lib, golden, prec, typ, n):
+    cases.check_golden_1d(lib, golden, prec, n, typ)
+
+
+def test_plan_2d_matches_plan_many(lib):
+    rng = np.random.default_rng(4)
+    x = rng.random((12, 16))
+    h = lib.dsp_dct_plan_2d(b"d", 12, 16, None, None, REDFT01, REDFT01, 0)
+    assert h
+    y = x.copy()
+    assert lib.dsp_dct_execute_host(h, y.ctypes.data, y.ctypes.data) == 0
+    lib.dsp_dct_destroy(h)
+    from oracle import dct as od
+    np.testing.assert_allclose(y, od.dctn_def(x, [od.REDFT01] * 2), rtol=0, atol=1e-11)
+
+
+def test_rejects_loudly(lib):
+    for args in [dict(prec="l", n=[8], kinds=[REDFT10]), dict(prec="f", n=[8], kinds=[3]),
+                 dict(prec="f", n=[0], kinds=[REDFT10]), dict(prec="f", n=[8, 8], kinds=[REDFT10] * 2, howmany=2, istride=5, idist=1, ostride=5, odist=1)]:
+        with pytest.raises(capi.DspDctError) as e:
+            Plan(lib=lib, **args)
+        assert str(e.value)

@@ -1,0 +1,150 @@
+"""GPU suite (-m gpu): the product CUDA library, through its C ABI, vs the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from dspfun_b200 import REDFT01, REDFT10, Plan, capi
+from oracle import dct as od
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the gpu suite needs a CUDA device"
+    return torch
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", cases.SHAPES_2D)
+def test_interleaved_2d(lib, prec, kind, shape):
+    cases.check_interleaved_2d(lib, prec, *shape, kind, definition=max(shape[:2]) <= 64)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("shape", [(512, 512, 3), (1024, 1024, 3), (1080, 1920, 1), (540, 960, 3), (2048, 4096, 1),
+                                   (4096, 2048, 3), (8192, 512, 1), (512, 8192, 1)])
+def test_reference_config_shapes(lib, prec, shape):
+    cases.check_interleaved_2d(lib, prec, *shape, REDFT10)
+    cases.check_interleaved_2d(lib, prec, *shape, REDFT01, seed=9)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_out_of_place_preserves_input(lib, prec):
+    cases.check_interleaved_2d(lib, prec, 24, 40, 3, REDFT01, inplace=False)
+    cases.check_interleaved_2d(lib, prec, 256, 320, 1, REDFT10, inplace=False)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_rank1_batches(lib, prec, kind):
+    cases.check_rank1_batch(lib, prec, 64, 5, kind)
+    cases.check_rank1_batch(lib, prec, 60, 7, kind, dist=67)
+    cases.check_rank1_batch(lib, prec, 2048, 3, kind)
+    cases.check_rank1_batch(lib, prec, 8192, 33, kind)
+    cases.check_rank1_batch(lib, prec, 1, 4, kind)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_planar_3d_embed(lib, prec, kind):
+    cases.check_planar_3d_embed(lib, prec, (8, 8, 8), (8, 8, 8), kind)
+    cases.check_planar_3d_embed(lib, prec, (4, 6, 10), (7, 9, 12), kind)
+    cases.check_planar_3d_embed(lib, prec, (1, 16, 24), (1, 16, 24), kind)
+    cases.check_planar_3d_embed(lib, prec, (16, 15, 20), (16, 27, 36), kind)
+    cases.check_planar_3d_embed(lib, prec, (32, 135, 240), (32, 135, 240), kind)   # 1/8-scale motion volume
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_batched_images_roundtrip(lib, prec):
+    cases.check_batched_images(lib, prec, 5, 16, 24, 3)
+    cases.check_batched_images(lib, prec, 16, 256, 256, 3)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("typ", [2, 3])
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 32, 64, 128, 256, 512, 1024])
+def test_fftw_golden_vectors(lib, golden, prec, typ, n):
+    cases.check_golden_1d(lib, golden, prec, n, typ)
+
+
+def test_device_resident_roundtrip_8192(lib, torch_cuda):
+    """Full BASELINE size, size-independent properties: REDFT01(REDFT10(x)) = 4wh x, and 64 random rows/columns of
+    the forward result against the separable definition."""
+    torch = torch_cuda
+    n = 8192
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand((n, n), device="cuda", dtype=torch.float32, generator=g)
+    y = x.clone()
+    fwd = Plan.interleaved_2d("f", n, n, 1, REDFT10)
+    inv = Plan.interleaved_2d("f", n, n, 1, REDFT01).fuse_scale(1.0, 1.0 / (4.0 * n * n))
+    st = torch.cuda.current_stream().cuda_stream
+    fwd.execute_dev(y.data_ptr(), y.data_ptr(), st)
+    torch.cuda.synchronize()
+    # rows of the 2-D result: Y[k1, :] = REDFT10_x( sum_y 2 cos(pi (y+1/2) k1 / n) x[y, :] )
+    xh = x.double()
+    rng = np.random.default_rng(0)
+    ks = rng.integers(0, n, 8)
+    yy = torch.arange(n, device="cuda", dtype=torch.float64)
+    for k1 in ks:
+        wv = 2 * torch.cos(torch.pi * (yy + 0.5) * float(k1) / n)
+        row = (wv[:, None] * xh).sum(0).cpu().numpy()
+        ref = od.dctn_fast(row, [od.REDFT10])
+        assert od.rel_l2(y[int(k1)].cpu().numpy(), ref) < 1e-5
+    inv.execute_dev(y.data_ptr(), y.data_ptr(), st)
+    torch.cuda.synchronize()
+    err = (torch.linalg.norm((y - x).double()) / torch.linalg.norm(xh)).item()
+    assert err < 1e-5, err
+    fwd.destroy(); inv.destroy()
+
+
+def test_device_resident_double_4096(lib, torch_cuda):
+    torch = torch_cuda
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand((n, n), device="cuda", dtype=torch.float64, generator=g)
+    y = x.clone()
+    fwd = Plan.interleaved_2d("d", n, n, 1, REDFT10)
+    inv = Plan.interleaved_2d("d", n, n, 1, REDFT01).fuse_scale(1.0, 1.0 / (4.0 * n * n))
+    st = torch.cuda.current_stream().cuda_stream
+    fwd.execute_dev(y.data_ptr(), y.data_ptr(), st)
+    torch.cuda.synchronize()
+    ref = od.dctn_fast(x.cpu().numpy(), [od.REDFT10] * 2)
+    assert od.rel_l2(y.cpu().numpy(), ref) < 1e-12
+    inv.execute_dev(y.data_ptr(), y.data_ptr(), st)
+    torch.cuda.synchronize()
+    err = (torch.linalg.norm(y - x) / torch.linalg.norm(x)).item()
+    assert err < 1e-12, err
+    fwd.destroy(); inv.destroy()
+
+
+def test_linearity_and_pinned_alloc(lib):
+    n = 256
+    nbytes = n * n * 4
+    pa = lib.dsp_dct_alloc(nbytes)
+    assert pa
+    a = np.ctypeslib.as_array((ctypes.c_float * (n * n)).from_address(pa))
+    rng = np.random.default_rng(11)
+    u, v = rng.random(n * n).astype(np.float32), rng.random(n * n).astype(np.float32)
+    p = Plan.interleaved_2d("f", n, n, 1, REDFT10)
+    a[:] = u; yu = p.execute_host(a).copy()
+    a[:] = v; yv = p.execute_host(a).copy()
+    a[:] = u + 2 * v; ys = p.execute_host(a).copy()
+    assert od.rel_l2(ys, yu + 2 * yv) < 1e-6
+    p.destroy()
+    lib.dsp_dct_free(pa)
+
+
+def test_launch_counter_counts_our_kernels(lib):
+    before = lib.dsp_dct_launch_count()
+    cases.check_interleaved_2d(lib, "f", 64, 64, 1, REDFT10)
+    assert lib.dsp_dct_launch_count() - before == 2
