@@ -22,12 +22,14 @@
 #define DSP_GPU 1
 #define DSP_DEV __device__ __forceinline__
 #define DSP_DEVM __device__ __forceinline__
+#define DSP_HDM __host__ __device__ __forceinline__
 #define DSP_SYNC() __syncthreads()
 #define DSP_LDG(p) __ldg(p)
 #else
 #define DSP_GPU 0
 #define DSP_DEV static inline
 #define DSP_DEVM inline
+#define DSP_HDM inline
 #define DSP_SYNC() ((void)0)
 #define DSP_LDG(p) (*(p))
 #endif
@@ -58,8 +60,8 @@ DSP_DEV uint32_t fd_div(uint32_t n, const FastDiv &f) {
 // Bank-skew padding of a complex index: every hex (f32) / octal (f64) digit of the index is added into the low
 // digit, so any access pattern whose lanes differ by a power-of-two stride lands in distinct banks.
 template <class T> struct Pad;
-template <> struct Pad<float>  { DSP_DEVM static int of(int e) { return e + (e >> 4) + (e >> 8) + (e >> 12); } };
-template <> struct Pad<double> { DSP_DEVM static int of(int e) { return e + (e >> 3) + (e >> 6) + (e >> 9) + (e >> 12); } };
+template <> struct Pad<float>  { DSP_HDM static int of(int e) { return e + (e >> 4) + (e >> 8) + (e >> 12); } };
+template <> struct Pad<double> { DSP_HDM static int of(int e) { return e + (e >> 3) + (e >> 6) + (e >> 9) + (e >> 12); } };
 
 // ------------------------------------------------------------------------------------------------ descriptors
 struct FftDesc {

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -26,6 +27,10 @@ namespace dsp {
 static thread_local std::string g_err;
 static std::mutex g_mu;
 static std::atomic<unsigned long long> g_launches(0);
+
+// DSP_DCT_TRACE=1 prints planner / launch steps to stderr
+static bool trace_on() { static int t = -1; if (t < 0) { const char *e = getenv("DSP_DCT_TRACE"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
+#define DSP_TRACE(...) do { if (trace_on()) { fprintf(stderr, "[dsp_dct] " __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
 
 static const size_t kMaxSmem = 227 * 1024;
 static const int kThreads = 256;
@@ -161,6 +166,7 @@ template <class T> static Tables *build_tables(int n) {
 	}
 	for (int j = 0; j < n; j++) pos3[j] = pos2[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)];
 	std::string err;
+	DSP_TRACE("tables: host side done (nfac=%d npad=%d), allocating", (int)t->fac.size(), t->npad);
 	bool ok = rt_malloc(&t->tw, sizeof(C2<T>) * n, err) && rt_malloc(&t->om, sizeof(C2<T>) * (n / 2 + 1), err) &&
 	          rt_malloc((void **)&t->pos2, sizeof(uint16_t) * n, err) && rt_malloc((void **)&t->pos3, sizeof(uint16_t) * n, err) &&
 	          rt_h2d(t->tw, tw.data(), sizeof(C2<T>) * n, 0, err) && rt_h2d(t->om, om.data(), sizeof(C2<T>) * (n / 2 + 1), 0, err) &&
@@ -180,7 +186,9 @@ static Tables *get_tables(int n, char prec) {
 	auto key = std::make_pair(rt_device(), std::make_pair(n, prec));
 	auto it = g_tables.find(key);
 	if (it != g_tables.end()) return it->second;
+	DSP_TRACE("building tables n=%d prec=%c", n, prec);
 	Tables *t = prec == 'f' ? build_tables<float>(n) : build_tables<double>(n);
+	DSP_TRACE("tables %s", t ? "ok" : g_err.c_str());
 	if (t) g_tables[key] = t;
 	return t;
 }
@@ -377,6 +385,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			pp.smem = (size_t)((tc + 1) / 2) * seqb;
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
+		DSP_TRACE("pass %zu: %s axis=%d n=%d grid=%d smem=%zu vec=%d/%d", pi, pp.row ? "row" : "col", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout);
 		P->passes.push_back(pp);
 	}
 	return true;
@@ -404,6 +413,7 @@ static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st)
 	for (size_t i = 0; i < P->passes.size(); i++) {
 		PassPlan &pp = P->passes[i];
 		const void *in = i == 0 ? d_in : d_out;
+		DSP_TRACE("launch pass %zu in=%p out=%p", i, in, d_out);
 #if DSP_GPU
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
 		if (P->profiling) {
@@ -453,7 +463,9 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 		}
 	}
 	std::lock_guard<std::mutex> lock(g_mu);
+	DSP_TRACE("plan: prec=%c rank=%d n=%d,%d,%d howmany=%d istride=%d idist=%d nbatch=%d", prec, rank, n[0], rank > 1 ? n[1] : 1, rank > 2 ? n[2] : 1, howmany, istride, idist, nbatch);
 	if (!rt_init(g_err)) return nullptr;
+	DSP_TRACE("runtime ok, device %d", rt_device());
 	dsp_dct_plan_s *P = new dsp_dct_plan_s();
 	P->prec = prec;
 	P->es = prec == 'f' ? 4 : 8;

@@ -7,6 +7,8 @@
 
 #if defined(__CUDACC__) && !defined(DSP_EMULATE)
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
 namespace dsp {
 typedef cudaStream_t rt_stream;
 inline bool rt_ok(cudaError_t e, std::string &err, const char *what) {
@@ -25,7 +27,12 @@ inline bool rt_init(std::string &err) {
 	return true;
 }
 inline int rt_device() { int d = 0; cudaGetDevice(&d); return d; }
-inline bool rt_malloc(void **p, size_t bytes, std::string &err) { return rt_ok(cudaMalloc(p, bytes ? bytes : 1), err, "cudaMalloc"); }
+inline bool rt_malloc(void **p, size_t bytes, std::string &err) {
+	if (getenv("DSP_DCT_TRACE")) { fprintf(stderr, "[dsp_dct] cudaMalloc %zu\n", bytes); fflush(stderr); }
+	cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+	if (getenv("DSP_DCT_TRACE")) { fprintf(stderr, "[dsp_dct] cudaMalloc -> %d\n", (int)e); fflush(stderr); }
+	return rt_ok(e, err, "cudaMalloc");
+}
 inline void rt_free(void *p) { if (p) cudaFree(p); }
 inline bool rt_h2d(void *d, const void *h, size_t n, rt_stream s, std::string &err) { return rt_ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), err, "H2D copy"); }
 inline bool rt_d2h(void *h, const void *d, size_t n, rt_stream s, std::string &err) { return rt_ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), err, "D2H copy"); }
