@@ -87,7 +87,15 @@ struct Outer {
 	FastDiv d0, d01, d012;       // divide by cnt[0], cnt[0]*cnt[1], cnt[0]*cnt[1]*cnt[2]
 };
 
-struct Coord { int c[5]; };     // i0, i1, i2, channel, batch
+// Logical coordinates of an element.  Named fields + select-based set(): a dynamically indexed array would be
+// demoted to local memory.
+struct Coord {
+	int i0, i1, i2, ch, b;
+	DSP_HDM void set(int slot, int v) {
+		i0 = slot == 0 ? v : i0; i1 = slot == 1 ? v : i1; i2 = slot == 2 ? v : i2;
+		ch = slot == 3 ? v : ch; b = slot == 4 ? v : b;
+	}
+};
 
 // ------------------------------------------------------------------------------------------------ complex helpers
 template <class T> DSP_DEV C2<T> cadd(C2<T> a, C2<T> b) { return C2<T>{a.x + b.x, a.y + b.y}; }
@@ -95,6 +103,22 @@ template <class T> DSP_DEV C2<T> csub(C2<T> a, C2<T> b) { return C2<T>{a.x - b.x
 template <class T> DSP_DEV C2<T> cmul(C2<T> a, C2<T> b) { return C2<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 template <class T> DSP_DEV C2<T> cmulc(C2<T> a, T br, T bi) { return C2<T>{a.x * br - a.y * bi, a.x * bi + a.y * br}; }
 template <class T> DSP_DEV C2<T> mul_mi(C2<T> a) { return C2<T>{a.y, -a.x}; }   // a * (-i)
+
+// streaming 16-byte global load that does not allocate in L1 (keeps the twiddle / slot tables resident there)
+#if DSP_GPU
+DSP_DEV VecOf<float>::type ldg_stream(const VecOf<float>::type *p) {
+	VecOf<float>::type r;
+	asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+	return r;
+}
+DSP_DEV VecOf<double>::type ldg_stream(const VecOf<double>::type *p) {
+	VecOf<double>::type r;
+	asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+	return r;
+}
+#else
+template <class V> DSP_DEV V ldg_stream(const V *p) { return *p; }
+#endif
 
 // read-only (LDG) load of a complex table entry
 #if DSP_GPU
@@ -324,6 +348,11 @@ DSP_DEV void dct2_post(C2<T> *s, int nseq, const FftDesc &f, int tid, int nthr) 
 // ------------------------------------------------------------------------------------------------ fused ops
 // A load op maps the value read from global memory to the value entering the transform; a store op maps the
 // transform output to the value written.  Both see the element's logical coordinates.
+// v * f: the lean kernels' only pointwise stage (f = 1 when nothing is fused; dsp_dct_fuse_scale sets it)
+template <class T> struct OpMul {
+	T f;
+	DSP_DEVM T operator()(T v, const Coord &) const { return v * f; }
+};
 struct OpNone {
 	template <class T> DSP_DEVM T operator()(T v, const Coord &) const { return v; }
 };
@@ -341,10 +370,7 @@ DSP_DEV void outer_decode(const Outer &o, uint32_t l, long long &ioff, long long
 	const uint32_t l0 = r - l1 * o.d0.d;
 	ioff = (long long)l0 * o.is[0] + (long long)l1 * o.is[1] + (long long)l2 * o.is[2] + (long long)l3 * o.is[3];
 	ooff = (long long)l0 * o.os[0] + (long long)l1 * o.os[1] + (long long)l2 * o.os[2] + (long long)l3 * o.os[3];
-	if (o.slot[0] >= 0) c.c[o.slot[0]] = (int)l0;
-	if (o.slot[1] >= 0) c.c[o.slot[1]] = (int)l1;
-	if (o.slot[2] >= 0) c.c[o.slot[2]] = (int)l2;
-	if (o.slot[3] >= 0) c.c[o.slot[3]] = (int)l3;
+	c.set(o.slot[0], (int)l0); c.set(o.slot[1], (int)l1); c.set(o.slot[2], (int)l2); c.set(o.slot[3], (int)l3);
 }
 
 // ------------------------------------------------------------------------------------------------ row pass
@@ -358,6 +384,8 @@ struct RowArgs {
 	int nlines, lines_per_cta;
 	Outer o;                     // line index -> offsets / coords
 	int ax_slot;                 // coordinate fed by the axis index
+	int simple;                  // line l sits at l * ls_in / l * ls_out (all outer levels collapse to one stride)
+	long long ls_in, ls_out;
 	const void *in;
 	void *out;
 	int vec_in, vec_out;         // 16-byte access legal
@@ -386,7 +414,7 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 			const uint32_t g = idx / gpl, q = idx - g * gpl;
 			const int la = line0 + 2 * (int)g;
 			const bool hasb = (2 * (int)g + 1) < nl;
-			Coord ca = {{0, 0, 0, 0, 0}}, cb = {{0, 0, 0, 0, 0}};
+			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
@@ -413,8 +441,8 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 				const int e = e0 + t;
 				if (e < llen) {
 					const int x = (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
-					ca.c[a.ax_slot] = x; ca.c[3] = ch;
-					cb.c[a.ax_slot] = x; cb.c[3] = ch;
+					ca.set(a.ax_slot, x); ca.ch = ch;
+					cb.set(a.ax_slot, x); cb.ch = ch;
 					const T pa = lop(va[t], ca);
 					const T pb = hasb ? lop(vb[t], cb) : (T)0;
 					const int slot = fwd ? ((x & 1) ? n - 1 - (x >> 1) : (x >> 1)) : x;
@@ -443,7 +471,7 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 			const uint32_t g = idx / gpl, q = idx - g * gpl;
 			const int la = line0 + 2 * (int)g;
 			const bool hasb = (2 * (int)g + 1) < nl;
-			Coord ca = {{0, 0, 0, 0, 0}}, cb = {{0, 0, 0, 0, 0}};
+			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
@@ -456,8 +484,8 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 				if (e >= llen) continue;
 				const int x = (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
 				const C2<T> z = s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + Pad<T>::of((int)DSP_LDG(pos + x))];
-				ca.c[a.ax_slot] = x; ca.c[3] = ch;
-				cb.c[a.ax_slot] = x; cb.c[3] = ch;
+				ca.set(a.ax_slot, x); ca.ch = ch;
+				cb.set(a.ax_slot, x); cb.ch = ch;
 				ra.v[t] = sop(z.x, ca);
 				rb.v[t] = sop(fwd ? z.y : -z.y, cb);
 			}
@@ -511,7 +539,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	const int nseq = (ncl + 1) / 2;
 	const uint32_t gpr = (uint32_t)((ncl + VN - 1) / VN);    // vector groups per axis position
 	const bool fwd = a.kind == DSP_KIND_REDFT10;
-	Coord cbase = {{0, 0, 0, 0, 0}};
+	Coord cbase = {0, 0, 0, 0, 0};
 	long long ibase, obase;
 	outer_decode(a.o, oidx, ibase, obase, cbase);
 
@@ -531,13 +559,13 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 				for (int t = 0; t < VN; t++) v[t] = (c0 + t < ncl) ? src[t] : (T)0;
 			}
 			Coord c = cbase;
-			c.c[a.ax_slot] = (int)r;
+			c.set(a.ax_slot, (int)r);
 #pragma unroll
 			for (int t = 0; t < VN; t++) {
 				if (c0 + t < ncl) {
 					const int col = col0 + c0 + t;
 					const int x = (int)fd_div((uint32_t)col, a.dd);
-					c.c[a.col_slot] = x; c.c[3] = col - x * a.d;
+					c.set(a.col_slot, x); c.ch = col - x * a.d;
 					v[t] = lop(v[t], c);
 				}
 			}
@@ -569,7 +597,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 			const int c0 = (int)cg * VN;
 			const int slot = Pad<T>::of((int)DSP_LDG(pos + r));
 			Coord c = cbase;
-			c.c[a.ax_slot] = (int)r;
+			c.set(a.ax_slot, (int)r);
 			Vec res;
 #pragma unroll
 			for (int p = 0; p < VN / 2; p++) {
@@ -585,7 +613,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 				if (c0 + t < ncl) {
 					const int col = col0 + c0 + t;
 					const int x = (int)fd_div((uint32_t)col, a.dd);
-					c.c[a.col_slot] = x; c.c[3] = col - x * a.d;
+					c.set(a.col_slot, x); c.ch = col - x * a.d;
 					res.v[t] = sop(res.v[t], c);
 				}
 			}

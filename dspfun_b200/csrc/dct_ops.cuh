@@ -42,17 +42,17 @@ struct OpAny {
 		case OP_NONE: return v;
 		case OP_SCALE: return (T)(v * (T)p[0]);
 		case OP_ACCUM_DC: {
-			if (c.c[2] == 0) {
+			if (c.i2 == 0) {
 #if DSP_GPU
-				atomicAdd((double *)aux + c.c[3], (double)v);
+				atomicAdd((double *)aux + c.ch, (double)v);
 #else
-				((double *)aux)[c.c[3]] += (double)v;
+				((double *)aux)[c.ch] += (double)v;
 #endif
 			}
 			return v;
 		}
 		case OP_SPEC: {
-			const int y = c.c[1], x = c.c[2], ch = c.c[3];
+			const int y = c.i1, x = c.i2, ch = c.ch;
 			T f = v;
 			if (y == 0 && x == 0) ((double *)aux)[ch] = (double)f / ((double)w * (double)h * 4.0);   // spec.c:66-68
 			if (y == 0) f = (T)((I)f / SQRT2);                                                       // :70-71
@@ -68,7 +68,7 @@ struct OpAny {
 			return f;
 		}
 		case OP_ISPEC: {
-			const int y = c.c[1], x = c.c[2], ch = c.c[3];
+			const int y = c.i1, x = c.i2, ch = c.ch;
 			const bool pix0 = (y == 0 && x == 0);
 			T f = v;
 			if (signtype == 0) {                                                                     // ispec.c:87-98
@@ -90,13 +90,13 @@ struct OpAny {
 			return f;
 		}
 		case OP_SCAN_MASK: {
-			const int y = c.c[1], x = c.c[2];
+			const int y = c.i1, x = c.i2;
 			if (y == 0 && x == 0) return (T)0;                                                       // scan.c:445
 			const int idx = DSP_LDG((const int *)aux_c + (size_t)y * w + x);
 			return (idx >= lo && idx < hi) ? v : (T)0;                                               // scan.c:429-432
 		}
 		case OP_SCAN_ACCUM: {
-			T *sum = (T *)aux + (((size_t)c.c[1] * w + c.c[2]) * d + c.c[3]);
+			T *sum = (T *)aux + (((size_t)c.i1 * w + c.i2) * d + c.ch);
 			const T s = *sum + v;                                                                    // scan.c:454
 			*sum = s;
 			return s;

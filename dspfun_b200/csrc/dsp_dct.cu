@@ -5,9 +5,7 @@
 // adjacent columns over the whole axis).  Forward plans run the contiguous axis first, inverse plans run it
 // last, so a forward+inverse round trip meets in the middle on the same column tiles (L2 reuse).
 #include "../../include/dsp_dct.h"
-#include "dct_core.cuh"
-#include "dct_ops.cuh"
-#include "dsp_rt.h"
+#include "dsp_kernels.h"
 
 #include <atomic>
 #include <cmath>
@@ -22,6 +20,12 @@
 #include <thread>
 #endif
 
+// The power-of-two fast path is instantiated for float only by default (double falls back to the generic
+// mixed-radix engine); build with -DDSP_FAST_F64=1 and the kern_*_fast_f64.cu units to enable it for double.
+#ifndef DSP_FAST_F64
+#define DSP_FAST_F64 0
+#endif
+
 namespace dsp {
 
 static thread_local std::string g_err;
@@ -32,67 +36,6 @@ static std::atomic<unsigned long long> g_launches(0);
 static bool trace_on() { static int t = -1; if (t < 0) { const char *e = getenv("DSP_DCT_TRACE"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
 #define DSP_TRACE(...) do { if (trace_on()) { fprintf(stderr, "[dsp_dct] " __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
 
-static const size_t kMaxSmem = 227 * 1024;
-static const int kThreads = 256;
-
-// ------------------------------------------------------------------------------------------------ kernels
-#if DSP_GPU
-template <class T, class L, class S>
-__global__ void __launch_bounds__(kThreads) k_row(const __grid_constant__ RowArgs a, const __grid_constant__ L l,
-                                                  const __grid_constant__ S s) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	cta_row_pass<T, L, S>(a, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<T> *)smem);
-}
-template <class T, class L, class S>
-__global__ void __launch_bounds__(kThreads) k_col(const __grid_constant__ ColArgs a, const __grid_constant__ L l,
-                                                  const __grid_constant__ S s) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	cta_col_pass<T, L, S>(a, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<T> *)smem);
-}
-template <class T> __global__ void k_spec_resolve(OpAny op, const double *acc, double *scale_z) {
-	if (threadIdx.x == 0 && blockIdx.x == 0) spec_resolve_range<T>(op, acc, scale_z);
-}
-#endif
-
-template <class T, class L, class S>
-static bool launch_row(const RowArgs &a, const L &l, const S &s, int grid, size_t smem, rt_stream st) {
-#if DSP_GPU
-	static size_t attr_set = 0;
-	if (smem > 48 * 1024 && smem > attr_set) {
-		if (!rt_ok(cudaFuncSetAttribute(k_row<T, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), g_err, "smem attr"))
-			return false;
-		attr_set = kMaxSmem;
-	}
-	k_row<T, L, S><<<grid, kThreads, smem, st>>>(a, l, s);
-	if (!rt_ok(cudaGetLastError(), g_err, "row kernel launch")) return false;
-#else
-	(void)st;
-	std::vector<unsigned char> buf(smem + 64);
-	for (int cta = 0; cta < grid; cta++) cta_row_pass<T, L, S>(a, l, s, cta, 0, kThreads, kThreads, (C2<T> *)buf.data());
-#endif
-	g_launches++;
-	return true;
-}
-
-template <class T, class L, class S>
-static bool launch_col(const ColArgs &a, const L &l, const S &s, int grid, size_t smem, rt_stream st) {
-#if DSP_GPU
-	static size_t attr_set = 0;
-	if (smem > 48 * 1024 && smem > attr_set) {
-		if (!rt_ok(cudaFuncSetAttribute(k_col<T, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), g_err, "smem attr"))
-			return false;
-		attr_set = kMaxSmem;
-	}
-	k_col<T, L, S><<<grid, kThreads, smem, st>>>(a, l, s);
-	if (!rt_ok(cudaGetLastError(), g_err, "column kernel launch")) return false;
-#else
-	(void)st;
-	std::vector<unsigned char> buf(smem + 64);
-	for (int cta = 0; cta < grid; cta++) cta_col_pass<T, L, S>(a, l, s, cta, 0, kThreads, kThreads, (C2<T> *)buf.data());
-#endif
-	g_launches++;
-	return true;
-}
 
 // ------------------------------------------------------------------------------------------------ tables
 static FastDiv mk_fd(uint32_t d) {
@@ -129,6 +72,9 @@ struct Tables {
 	int npad;
 	void *tw, *om;
 	uint16_t *pos2, *pos3;
+	// power-of-two fast path (n = r0 * 16^(nmid+1)); sig == nullptr when not applicable
+	int r0, nmid;
+	uint16_t *sig;
 };
 static std::map<std::pair<int, std::pair<int, char>>, Tables *> g_tables;
 
@@ -165,6 +111,27 @@ template <class T> static Tables *build_tables(int n) {
 		pos2[k] = (uint16_t)P;
 	}
 	for (int j = 0; j < n; j++) pos3[j] = pos2[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)];
+	// fast path: n = r0 * 16^(nmid+1), r0 in {1,2,4,8,16,32}
+	t->sig = nullptr; t->r0 = 0; t->nmid = 0;
+	std::vector<uint16_t> sig;
+	if (n >= 16 && (n & (n - 1)) == 0 && !getenv("DSP_DCT_NO_FAST") && (sizeof(T) == 4 || DSP_FAST_F64)) {
+		int a = 0;
+		while ((1 << a) < n) a++;
+		int l0 = (a - 4) % 4;                       // log2 r0 in {0,1,2,3} ...
+		int k = (a - 4 - l0) / 4;                   // ... middle passes
+		if (l0 == 0 && k > 0) { l0 = 4; k--; }      // prefer r0 = 16 over r0 = 1 with one more middle pass
+		else if (l0 == 1 && k > 0) { l0 = 5; k--; } // and r0 = 32 over r0 = 2
+		if (k <= 3) {
+			t->r0 = 1 << l0; t->nmid = k;
+			sig.resize(n);
+			for (int e = 0; e < n; e++) {
+				int x = e, stride = n, slot = 0;
+				for (int p = 0; p <= k; p++) { stride /= 16; slot += (x % 16) * stride; x /= 16; }
+				slot += x;
+				sig[e] = (uint16_t)pad_of<T>(slot);
+			}
+		}
+	}
 	std::string err;
 	DSP_TRACE("tables: host side done (nfac=%d npad=%d), allocating", (int)t->fac.size(), t->npad);
 	bool ok = rt_malloc(&t->tw, sizeof(C2<T>) * n, err) && rt_malloc(&t->om, sizeof(C2<T>) * (n / 2 + 1), err) &&
@@ -172,9 +139,11 @@ template <class T> static Tables *build_tables(int n) {
 	          rt_h2d(t->tw, tw.data(), sizeof(C2<T>) * n, 0, err) && rt_h2d(t->om, om.data(), sizeof(C2<T>) * (n / 2 + 1), 0, err) &&
 	          rt_h2d(t->pos2, pos2.data(), sizeof(uint16_t) * n, 0, err) && rt_h2d(t->pos3, pos3.data(), sizeof(uint16_t) * n, 0, err) &&
 	          rt_sync(0, err);
+	if (ok && !sig.empty())
+		ok = rt_malloc((void **)&t->sig, sizeof(uint16_t) * n, err) && rt_h2d(t->sig, sig.data(), sizeof(uint16_t) * n, 0, err) && rt_sync(0, err);
 	if (!ok) {
 		g_err = err;
-		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3);
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig);
 		delete t;
 		return nullptr;
 	}
@@ -209,12 +178,31 @@ static void fill_fft(FftDesc &f, const Tables *t) {
 	f.dHalf = mk_fd((uint32_t)(t->n / 2 + 1));
 }
 
+template <class T> static void fill_fast_t(FastDesc &f, const Tables *t) {
+	memset(&f, 0, sizeof(f));
+	f.n = t->n; f.M = t->n / 16;
+	f.r0 = t->r0; f.nmid = t->nmid;
+	f.npad = t->npad;
+	f.tw = t->tw; f.om = t->om; f.sig = t->sig;
+	int lp = t->r0;
+	for (int q = 0; q <= t->nmid; q++) {
+		for (int j = 0; j < 16; j++) f.poff[q][j] = pad_of<T>(j * lp);
+		lp *= 16;
+	}
+	f.dHalf = mk_fd((uint32_t)(f.M / 2 + 1));
+}
+static void fill_fast(FastDesc &f, const Tables *t) {
+	if (t->prec == 'f') fill_fast_t<float>(f, t); else fill_fast_t<double>(f, t);
+}
+
 // ------------------------------------------------------------------------------------------------ plan
 struct Level { long long cnt, is, os; int slot; };
 
 struct PassPlan {
 	bool row;
 	int axis;
+	bool fast;
+	FastDesc ff;
 	RowArgs ra;
 	ColArgs ca;
 	int grid;
@@ -323,6 +311,9 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		pp.fused = false;
 		pp.axis = ax;
 		pp.row = ax == r - 1;
+		pp.fast = t->sig != nullptr;
+		memset(&pp.ff, 0, sizeof(pp.ff));
+		if (pp.fast) fill_fast(pp.ff, t);
 		const size_t seqb = (size_t)t->npad * cbytes;
 		std::vector<Level> lv;
 		bool vin = true, vout = true;
@@ -339,6 +330,17 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			A.nlines = (int)nl;
 			if (!set_outer(A.o, lv)) return false;
 			A.ax_slot = 2;
+			{
+				// do all outer levels collapse to a single line stride?
+				std::vector<Level> act;
+				for (auto &l : lv) if (l.cnt > 1) act.push_back(l);
+				bool simple = true;
+				for (size_t k = 1; k < act.size(); k++)
+					if (act[k].is != act[k - 1].cnt * act[k - 1].is || act[k].os != act[k - 1].cnt * act[k - 1].os) simple = false;
+				A.simple = simple ? 1 : 0;
+				A.ls_in = act.empty() ? 0 : act[0].is;
+				A.ls_out = act.empty() ? 0 : act[0].os;
+			}
 			const size_t pairb = seqb * (size_t)d;
 			if (pairb > kMaxSmem) { g_err = "transform length " + std::to_string(P->n[ax]) + " does not fit on chip"; return false; }
 			long long pairs = (long long)((48 * 1024) / pairb);
@@ -385,27 +387,39 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			pp.smem = (size_t)((tc + 1) / 2) * seqb;
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
-		DSP_TRACE("pass %zu: %s axis=%d n=%d grid=%d smem=%zu vec=%d/%d", pi, pp.row ? "row" : "col", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout);
+		DSP_TRACE("pass %zu: %s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid);
 		P->passes.push_back(pp);
 	}
 	return true;
 }
 
-template <class T>
-static bool run_pass_t(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st) {
+static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st) {
 	const bool ain = ((uintptr_t)in % 16) == 0, aout = ((uintptr_t)out % 16) == 0;
+	const bool f32 = P->prec == 'f';
+	bool ok;
 	if (pp.row) {
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
-		if (pp.fused) return launch_row<T, OpAny, OpAny>(a, pp.lop, pp.sop, pp.grid, pp.smem, st);
-		return launch_row<T, OpNone, OpNone>(a, OpNone(), OpNone(), pp.grid, pp.smem, st);
+		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+#if DSP_FAST_F64
+		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+#endif
+		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err)
+		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+	} else {
+		ColArgs a = pp.ca;
+		a.in = in; a.out = out;
+		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
+		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+#if DSP_FAST_F64
+		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+#endif
+		else ok = f32 ? launch_col_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err)
+		              : launch_col_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
 	}
-	ColArgs a = pp.ca;
-	a.in = in; a.out = out;
-	a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
-	if (pp.fused) return launch_col<T, OpAny, OpAny>(a, pp.lop, pp.sop, pp.grid, pp.smem, st);
-	return launch_col<T, OpNone, OpNone>(a, OpNone(), OpNone(), pp.grid, pp.smem, st);
+	if (ok) g_launches++;
+	return ok;
 }
 
 static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st) {
@@ -421,7 +435,7 @@ static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st)
 			cudaEventRecord(e0, st);
 		}
 #endif
-		const bool ok = P->prec == 'f' ? run_pass_t<float>(P, pp, in, d_out, st) : run_pass_t<double>(P, pp, in, d_out, st);
+		const bool ok = run_pass(P, pp, in, d_out, st);
 		if (!ok) return false;
 #if DSP_GPU
 		if (P->profiling) {
@@ -431,15 +445,7 @@ static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st)
 		}
 #endif
 		if (P->fuse_kind == 1 && i == 0) {
-			const OpAny &op = P->passes.back().sop;
-#if DSP_GPU
-			if (P->prec == 'f') k_spec_resolve<float><<<1, 32, 0, st>>>(op, P->d_scalars, P->d_scalars + 4);
-			else k_spec_resolve<double><<<1, 32, 0, st>>>(op, P->d_scalars, P->d_scalars + 4);
-			if (!rt_ok(cudaGetLastError(), g_err, "spec resolve launch")) return false;
-#else
-			if (P->prec == 'f') spec_resolve_range<float>(op, P->d_scalars, P->d_scalars + 4);
-			else spec_resolve_range<double>(op, P->d_scalars, P->d_scalars + 4);
-#endif
+			if (!launch_spec_resolve(P->prec, P->passes.back().sop, P->d_scalars, P->d_scalars + 4, st, g_err)) return false;
 			g_launches++;
 		}
 	}
@@ -608,7 +614,7 @@ void dsp_dct_cleanup(void) {
 	std::lock_guard<std::mutex> lock(g_mu);
 	for (auto &kv : g_tables) {
 		Tables *t = kv.second;
-		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3);
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig);
 		delete t;
 	}
 	g_tables.clear();
@@ -662,8 +668,9 @@ int dsp_dct_fuse_scale(dsp_dct_plan p, double load_scale, double store_scale) {
 	if (!p) { g_err = "null plan"; return 1; }
 	if (p->fuse_kind) { g_err = "plan already carries a fused stage"; return 1; }
 	PassPlan &f = p->passes.front(), &l = p->passes.back();
-	if (load_scale != 1.0) { f.lop.kind = OP_SCALE; f.lop.p[0] = load_scale; f.fused = true; }
-	if (store_scale != 1.0) { l.sop.kind = OP_SCALE; l.sop.p[0] = store_scale; l.fused = true; }
+	// a plain multiply rides in the lean kernels (no OpAny dispatch needed)
+	if (load_scale != 1.0) { f.lop.kind = OP_SCALE; f.lop.p[0] = load_scale; }
+	if (store_scale != 1.0) { l.sop.kind = OP_SCALE; l.sop.p[0] = store_scale; }
 	return 0;
 }
 

@@ -1,0 +1,32 @@
+// dsp_kernels.h -- launch entry points of the pass kernels.  Each (element type, row/column, generic/fast)
+// combination lives in its own translation unit (kern_*.cu, all generated from kern_inst.cuh) so the library
+// builds in parallel.
+#pragma once
+#include "dct_core.cuh"
+#include "dct_ops.cuh"
+#include "dct_fast.cuh"
+#include "dsp_rt.h"
+#include <string>
+
+namespace dsp {
+
+static const size_t kMaxSmem = 227 * 1024;
+static const int kThreads = 256;
+
+// fused == false launches the lean <OpMul, OpMul> instantiation (lop / sop may only be OP_NONE or OP_SCALE)
+#define DSP_DECL_LAUNCH(NAME, ARGS)                                                                          \
+	bool NAME(const ARGS &a, const FastDesc &f, bool fused, const OpAny &lop, const OpAny &sop, int grid,    \
+	          size_t smem, rt_stream st, std::string &err);
+DSP_DECL_LAUNCH(launch_row_generic_f32, RowArgs)
+DSP_DECL_LAUNCH(launch_row_generic_f64, RowArgs)
+DSP_DECL_LAUNCH(launch_row_fast_f32, RowArgs)
+DSP_DECL_LAUNCH(launch_row_fast_f64, RowArgs)
+DSP_DECL_LAUNCH(launch_col_generic_f32, ColArgs)
+DSP_DECL_LAUNCH(launch_col_generic_f64, ColArgs)
+DSP_DECL_LAUNCH(launch_col_fast_f32, ColArgs)
+DSP_DECL_LAUNCH(launch_col_fast_f64, ColArgs)
+#undef DSP_DECL_LAUNCH
+
+bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
+
+}  // namespace dsp

@@ -1,0 +1,89 @@
+// kern_inst.cuh -- one pass-kernel family per translation unit.  The including .cu defines
+//   KERN_T (float|double), KERN_SUFFIX (f32|f64), KERN_ROW (1|0), KERN_FAST (1|0)
+#include "dsp_kernels.h"
+#include <vector>
+
+namespace dsp {
+
+#define KERN_CAT_(a, b, c, d) a##b##c##d
+#define KERN_CAT(a, b, c, d) KERN_CAT_(a, b, c, d)
+#if KERN_ROW
+#define KERN_ARGS RowArgs
+#define KERN_RC _row_
+#else
+#define KERN_ARGS ColArgs
+#define KERN_RC _col_
+#endif
+#if KERN_FAST
+#define KERN_GF fast_
+#else
+#define KERN_GF generic_
+#endif
+#define KERN_LAUNCH KERN_CAT(launch, KERN_RC, KERN_GF, KERN_SUFFIX)
+
+// NB: the element type and the row/fast flags are template parameters so that every translation unit
+// instantiates distinctly named kernels (same-signature templates in different TUs would be merged by the linker).
+template <class TT, int ROW, int FAST, class L, class S>
+DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int cta, int t0, int t1, int nthr,
+                      C2<KERN_T> *smem) {
+	const bool FWD = (FAST & 2) != 0;       // fast kernels are specialised on the transform kind (bit 1 of FAST)
+	(void)FWD;
+#if KERN_ROW && KERN_FAST
+	cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, f, l, s, cta, t0, t1, nthr, smem);
+#elif KERN_ROW
+	(void)f;
+	cta_row_pass<KERN_T, L, S>(a, l, s, cta, t0, t1, nthr, smem);
+#elif KERN_FAST
+	cta_col_fast<KERN_T, (FAST & 2) != 0, L, S>(a, f, l, s, cta, t0, t1, nthr, smem);
+#else
+	(void)f;
+	cta_col_pass<KERN_T, L, S>(a, l, s, cta, t0, t1, nthr, smem);
+#endif
+}
+
+#if DSP_GPU
+// f32: two CTAs per SM (<= 128 registers); f64: one (the paired outer pass keeps 64 complex doubles live)
+template <class TT, int ROW, int FAST, class L, class S>
+__global__ void __launch_bounds__(kThreads, sizeof(KERN_T) == 4 ? 2 : 1)
+k_pass(const __grid_constant__ KERN_ARGS a, const __grid_constant__ FastDesc f, const __grid_constant__ L l,
+       const __grid_constant__ S s) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	cta_body<TT, ROW, FAST, L, S>(a, f, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<KERN_T> *)smem);
+}
+#endif
+
+template <class TT, int ROW, int FAST, class L, class S>
+static bool launch_t(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int grid, size_t smem, rt_stream st,
+                     std::string &err) {
+#if DSP_GPU
+	static size_t attr_set = 0;
+	if (smem > 48 * 1024 && smem > attr_set) {
+		if (!rt_ok(cudaFuncSetAttribute(k_pass<TT, ROW, FAST, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute"))
+			return false;
+		attr_set = kMaxSmem;
+	}
+	k_pass<TT, ROW, FAST, L, S><<<grid, kThreads, smem, st>>>(a, f, l, s);
+	return rt_ok(cudaGetLastError(), err, "pass kernel launch");
+#else
+	(void)st; (void)err;
+	std::vector<unsigned char> buf(smem + 64);
+	for (int cta = 0; cta < grid; cta++) cta_body<TT, ROW, FAST, L, S>(a, f, l, s, cta, 0, kThreads, kThreads, (C2<KERN_T> *)buf.data());
+	return true;
+#endif
+}
+
+bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,
+                 rt_stream st, std::string &err) {
+	// lean kernels: the only pointwise stage is a multiply (1 unless dsp_dct_fuse_scale set it)
+	const OpMul<KERN_T> lm = {(KERN_T)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(KERN_T)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
+#if KERN_FAST
+	if (a.kind == DSP_KIND_REDFT10) {
+		if (fused) return launch_t<KERN_T, KERN_ROW, 3, OpAny, OpAny>(a, f, lop, sop, grid, smem, st, err);
+		return launch_t<KERN_T, KERN_ROW, 3, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, smem, st, err);
+	}
+#endif
+	if (fused) return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpAny, OpAny>(a, f, lop, sop, grid, smem, st, err);
+	return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, smem, st, err);
+}
+
+}  // namespace dsp
