@@ -15,7 +15,8 @@ SIGN_ABS, SIGN_SHIFT, SIGN_SATURATE, SIGN_RETAIN = 0, 1, 2, 3
 RANGE_ONE, RANGE_DC, RANGE_DCS = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdspdct.so")
+# DSPFUN_B200_LIB points at another build of the same CUDA library (kernel tuning experiments)
+LIB_PATH = os.environ.get("DSPFUN_B200_LIB") or os.path.join(_HERE, "libdspdct.so")
 
 # every symbol include/dsp_dct.h declares (tests check the built library exports all of them)
 SYMBOLS = [

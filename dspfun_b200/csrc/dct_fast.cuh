@@ -424,7 +424,7 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 template <class T, bool FWD, class Op>
 DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
 	typedef typename VecOf<T>::type Vec;
-	const int UNR = 4;
+	const int UNR = 8;
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
 	const int n = f.n;
@@ -566,39 +566,58 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 }
 
 // ------------------------------------------------------------------------------------------------ column pass (fast)
-// Moves the CTA's column tile between global memory and smem, `UNR` vector groups per thread in flight.
-// IN: global -> lop -> slot ; !IN: slot -> (re, +-im) -> sop -> global.  `scatter` selects sig[makhoul(r)] vs Pad(r).
-template <class T, bool IN, class Op>
-DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
+// W consecutive elements of T as one global access (W * sizeof(T) in {8, 16} bytes)
+template <class T, int W> struct alignas(W * sizeof(T)) VecW { T v[W]; };
+#if DSP_GPU
+DSP_DEV VecW<float, 4> ldg_stream(const VecW<float, 4> *p) {
+	VecW<float, 4> r;
+	asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+	return r;
+}
+DSP_DEV VecW<float, 2> ldg_stream(const VecW<float, 2> *p) {
+	VecW<float, 2> r;
+	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+	return r;
+}
+DSP_DEV VecW<double, 2> ldg_stream(const VecW<double, 2> *p) {
+	VecW<double, 2> r;
+	asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+	return r;
+}
+#endif
+
+// Moves the CTA's column tile between global memory and smem in groups of W columns, UNR groups per thread in
+// flight.  IN: global -> lop -> slot ; !IN: slot -> (re, +-im) -> sop -> global.  `scatter` selects
+// sig[makhoul(r)] vs Pad(r).  `vec`: W-wide accesses are legal (alignment + the tile is a whole number of groups).
+template <class T, int W, bool IN, class Op>
+DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, bool vec, int col0, int ncl,
                       long long gbase, const Coord &cbase, int tid, int nthr, C2<T> *s) {
-	typedef typename VecOf<T>::type Vec;
-	const int VN = VecOf<T>::N;
-	const int UNR = 4;
+	typedef VecW<T, W> Vec;
+	const int UNR = 8;
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
 	const int n = f.n;
-	const int gpr = (ncl + VN - 1) / VN;                      // vector groups per axis position
+	const int gpr = (ncl + W - 1) / W;                        // groups per axis position
 	const int total = n * gpr;
 	const long long axs = IN ? a.ax_is : a.ax_os;
-	const bool vec = (IN ? a.vec_in : a.vec_out) && (ncl % VN) == 0;
 	const int lg = (gpr & (gpr - 1)) == 0 ? ilog2(gpr) : -1;
 	for (int i0 = tid; i0 < total; i0 += nthr * UNR) {
-		T v[UNR][VecOf<T>::N];
+		T v[UNR][W];
 		if (IN) {
 #pragma unroll
 			for (int u = 0; u < UNR; u++) {
 				const int idx = i0 + u * nthr;
 				if (idx < total) {
 					const int r = lg >= 0 ? idx >> lg : idx / gpr, cg = idx - r * gpr;
-					const int c0 = cg * VN;
+					const int c0 = cg * W;
 					const T *src = gin + gbase + (long long)r * axs + col0 + c0;
 					if (vec) {
 						const Vec tv = ldg_stream((const Vec *)src);
 #pragma unroll
-						for (int t = 0; t < VN; t++) v[u][t] = tv.v[t];
+						for (int t = 0; t < W; t++) v[u][t] = tv.v[t];
 					} else {
 #pragma unroll
-						for (int t = 0; t < VN; t++) v[u][t] = (c0 + t < ncl) ? src[t] : (T)0;
+						for (int t = 0; t < W; t++) v[u][t] = (c0 + t < ncl) ? src[t] : (T)0;
 					}
 				}
 			}
@@ -608,13 +627,13 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 			const int idx = i0 + u * nthr;
 			if (idx < total) {
 				const int r = lg >= 0 ? idx >> lg : idx / gpr, cg = idx - r * gpr;
-				const int c0 = cg * VN;
+				const int c0 = cg * W;
 				const int slot = scatter ? (int)DSP_LDG(f.sig + makhoul(r, n)) : Pad<T>::of(r);
 				Coord c = cbase;
 				c.set(a.ax_slot, r);
 				if (!IN) {
 #pragma unroll
-					for (int p = 0; p < VN / 2; p++) {
+					for (int p = 0; p < W / 2; p++) {
 						v[u][2 * p] = 0; v[u][2 * p + 1] = 0;
 						if (c0 + 2 * p < ncl) {
 							const C2<T> z = s[(c0 / 2 + p) * f.npad + slot];
@@ -624,7 +643,7 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 					}
 				}
 #pragma unroll
-				for (int t = 0; t < VN; t++) {
+				for (int t = 0; t < W; t++) {
 					if (c0 + t < ncl) {
 						const int col = col0 + c0 + t;
 						int x = col, ch = 0;
@@ -635,24 +654,35 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 				}
 				if (IN) {
 #pragma unroll
-					for (int p = 0; p < VN / 2; p++)
+					for (int p = 0; p < W / 2; p++)
 						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * f.npad + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
 				} else {
 					T *dst = gout + gbase + (long long)r * axs + col0 + c0;
 					if (vec) {
 						Vec res;
 #pragma unroll
-						for (int t = 0; t < VN; t++) res.v[t] = v[u][t];
+						for (int t = 0; t < W; t++) res.v[t] = v[u][t];
 						*(Vec *)dst = res;
 					} else {
 #pragma unroll
-						for (int t = 0; t < VN; t++)
+						for (int t = 0; t < W; t++)
 							if (c0 + t < ncl) dst[t] = v[u][t];
 					}
 				}
 			}
 		}
 	}
+}
+
+// picks the access width: full 16-byte groups when the tile allows it, else 8-byte (float) pairs, else scalar
+template <class T, bool IN, class Op>
+DSP_DEV void col_move_any(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
+                          long long gbase, const Coord &cbase, int tid, int nthr, C2<T> *s) {
+	const int VN = VecOf<T>::N;
+	const bool al = IN ? a.vec_in : a.vec_out;
+	if (al && (ncl % VN) == 0) col_move<T, VecOf<T>::N, IN, Op>(a, f, op, scatter, negim, true, col0, ncl, gbase, cbase, tid, nthr, s);
+	else if (sizeof(T) == 4 && al && (ncl % 2) == 0 && (a.tc % 2) == 0) col_move<T, 2, IN, Op>(a, f, op, scatter, negim, true, col0, ncl, gbase, cbase, tid, nthr, s);
+	else col_move<T, 2, IN, Op>(a, f, op, scatter, negim, false, col0, ncl, gbase, cbase, tid, nthr, s);
 }
 
 template <class T, bool FWD, class LoadOp, class StoreOp>
@@ -670,7 +700,7 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 	outer_decode(a.o, oidx, ibase, obase, cbase);
 
 	// ---- copy-in: DCT-II scatters through sig, DCT-III keeps natural order
-	for (int tid = t0; tid < t1; tid++) col_move<T, true, LoadOp>(a, f, lop, FWD, false, col0, ncl, ibase, cbase, tid, nthr, s);
+	for (int tid = t0; tid < t1; tid++) col_move_any<T, true, LoadOp>(a, f, lop, FWD, false, col0, ncl, ibase, cbase, tid, nthr, s);
 	DSP_SYNC();
 
 	if (FWD) {
@@ -708,7 +738,7 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 	}
 
 	// ---- copy-out: DCT-II results sit in natural order, DCT-III results at their digit-reversed slots
-	for (int tid = t0; tid < t1; tid++) col_move<T, false, StoreOp>(a, f, sop, !FWD, !FWD, col0, ncl, obase, cbase, tid, nthr, s);
+	for (int tid = t0; tid < t1; tid++) col_move_any<T, false, StoreOp>(a, f, sop, !FWD, !FWD, col0, ncl, obase, cbase, tid, nthr, s);
 }
 
 }  // namespace dsp

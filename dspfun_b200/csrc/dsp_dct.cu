@@ -205,7 +205,7 @@ struct PassPlan {
 	FastDesc ff;
 	RowArgs ra;
 	ColArgs ca;
-	int grid;
+	int grid, block;
 	size_t smem;
 	bool vec_in_layout, vec_out_layout;
 	OpAny lop, sop;
@@ -375,6 +375,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 				tc = (VN >= 4 && 2 * seqb <= kMaxSmem) ? VN : 2;
 				if ((size_t)(tc / 2) * seqb > kMaxSmem) { g_err = "transform length " + std::to_string(P->n[ax]) + " does not fit on chip"; return false; }
 			}
+			if (getenv("DSP_DCT_TC")) { const int want = atoi(getenv("DSP_DCT_TC")); int t2 = 2; while (t2 * 2 <= want && t2 < 64) t2 *= 2; if ((size_t)(t2 / 2) * seqb <= kMaxSmem) tc = t2; }  /* tuning aid: power of two */
 			while (tc > VN && tc / 2 >= A.ncols) tc /= 2;
 			// enough CTAs to fill the machine
 			while (tc > 2 * VN && ((A.ncols + tc - 1) / tc) * no < 2 * 148) tc /= 2;
@@ -387,6 +388,9 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			pp.smem = (size_t)((tc + 1) / 2) * seqb;
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
+		// one CTA per SM (big tile): run it with 512 threads; otherwise 256 and rely on several CTAs per SM
+		pp.block = (pp.fast && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;
+		if (pp.fast && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
 		DSP_TRACE("pass %zu: %s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid);
 		P->passes.push_back(pp);
 	}
@@ -401,22 +405,22 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
-		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
-		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #endif
-		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err)
-		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
+		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 	} else {
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
-		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
-		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #endif
-		else ok = f32 ? launch_col_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err)
-		              : launch_col_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.smem, st, g_err);
+		else ok = f32 ? launch_col_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
+		              : launch_col_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 	}
 	if (ok) g_launches++;
 	return ok;
@@ -641,7 +645,7 @@ int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out) {
 	out->axis = pp.axis;
 	out->n = p->n[pp.axis];
 	out->grid = pp.grid;
-	out->block = kThreads;
+	out->block = pp.block;
 	out->smem_bytes = pp.smem;
 	out->samples = p->samples_per_launch;
 #if DSP_GPU

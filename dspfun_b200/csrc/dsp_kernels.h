@@ -16,7 +16,7 @@ static const int kThreads = 256;
 // fused == false launches the lean <OpMul, OpMul> instantiation (lop / sop may only be OP_NONE or OP_SCALE)
 #define DSP_DECL_LAUNCH(NAME, ARGS)                                                                          \
 	bool NAME(const ARGS &a, const FastDesc &f, bool fused, const OpAny &lop, const OpAny &sop, int grid,    \
-	          size_t smem, rt_stream st, std::string &err);
+	          int block, size_t smem, rt_stream st, std::string &err);
 DSP_DECL_LAUNCH(launch_row_generic_f32, RowArgs)
 DSP_DECL_LAUNCH(launch_row_generic_f64, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f32, RowArgs)

@@ -3,6 +3,10 @@
 #include "dsp_kernels.h"
 #include <vector>
 
+#ifndef KERN_ROW_MINB
+#define KERN_ROW_MINB 2
+#endif
+
 namespace dsp {
 
 #define KERN_CAT_(a, b, c, d) a##b##c##d
@@ -44,7 +48,7 @@ DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S
 #if DSP_GPU
 // f32: two CTAs per SM (<= 128 registers); f64: one (the paired outer pass keeps 64 complex doubles live)
 template <class TT, int ROW, int FAST, class L, class S>
-__global__ void __launch_bounds__(kThreads, sizeof(KERN_T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__((KERN_FAST && !KERN_ROW) ? 2 * kThreads : kThreads, sizeof(KERN_T) != 4 ? 1 : (KERN_FAST ? (KERN_ROW ? KERN_ROW_MINB : 1) : 2))
 k_pass(const __grid_constant__ KERN_ARGS a, const __grid_constant__ FastDesc f, const __grid_constant__ L l,
        const __grid_constant__ S s) {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -53,8 +57,8 @@ k_pass(const __grid_constant__ KERN_ARGS a, const __grid_constant__ FastDesc f, 
 #endif
 
 template <class TT, int ROW, int FAST, class L, class S>
-static bool launch_t(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int grid, size_t smem, rt_stream st,
-                     std::string &err) {
+static bool launch_t(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int grid, int block, size_t smem,
+                     rt_stream st, std::string &err) {
 #if DSP_GPU
 	static size_t attr_set = 0;
 	if (smem > 48 * 1024 && smem > attr_set) {
@@ -62,28 +66,29 @@ static bool launch_t(const KERN_ARGS &a, const FastDesc &f, const L &l, const S 
 			return false;
 		attr_set = kMaxSmem;
 	}
-	k_pass<TT, ROW, FAST, L, S><<<grid, kThreads, smem, st>>>(a, f, l, s);
+	k_pass<TT, ROW, FAST, L, S><<<grid, block, smem, st>>>(a, f, l, s);
 	return rt_ok(cudaGetLastError(), err, "pass kernel launch");
 #else
 	(void)st; (void)err;
 	std::vector<unsigned char> buf(smem + 64);
-	for (int cta = 0; cta < grid; cta++) cta_body<TT, ROW, FAST, L, S>(a, f, l, s, cta, 0, kThreads, kThreads, (C2<KERN_T> *)buf.data());
+	for (int cta = 0; cta < grid; cta++) cta_body<TT, ROW, FAST, L, S>(a, f, l, s, cta, 0, block, block, (C2<KERN_T> *)buf.data());
 	return true;
 #endif
 }
 
-bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,
-                 rt_stream st, std::string &err) {
+bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny &lop, const OpAny &sop, int grid, int block,
+                 size_t smem, rt_stream st, std::string &err) {
+	if (!KERN_FAST) block = kThreads;
 	// lean kernels: the only pointwise stage is a multiply (1 unless dsp_dct_fuse_scale set it)
 	const OpMul<KERN_T> lm = {(KERN_T)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(KERN_T)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
 #if KERN_FAST
 	if (a.kind == DSP_KIND_REDFT10) {
-		if (fused) return launch_t<KERN_T, KERN_ROW, 3, OpAny, OpAny>(a, f, lop, sop, grid, smem, st, err);
-		return launch_t<KERN_T, KERN_ROW, 3, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, smem, st, err);
+		if (fused) return launch_t<KERN_T, KERN_ROW, 3, OpAny, OpAny>(a, f, lop, sop, grid, block, smem, st, err);
+		return launch_t<KERN_T, KERN_ROW, 3, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
 	}
 #endif
-	if (fused) return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpAny, OpAny>(a, f, lop, sop, grid, smem, st, err);
-	return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, smem, st, err);
+	if (fused) return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpAny, OpAny>(a, f, lop, sop, grid, block, smem, st, err);
+	return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
 }
 
 }  // namespace dsp
