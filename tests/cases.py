@@ -101,3 +101,90 @@ SHAPES_2D = [
     (8, 8, 1), (16, 32, 3), (12, 20, 3), (30, 14, 1), (64, 48, 3), (1, 16, 1), (16, 1, 3), (1, 1, 3), (5, 7, 2),
     (2, 3, 4), (256, 256, 1), (100, 135, 3), (33, 77, 1), (26, 22, 3), (128, 512, 3), (1024, 16, 1), (49, 81, 2),
 ]
+
+
+# ---------------------------------------------------------------------------------------------- spec / ispec
+from dspfun_b200 import spec as gspec          # noqa: E402
+from oracle import pipelines as pl             # noqa: E402
+
+INTERMEDIATE = {"f": np.float64, "d": np.longdouble}   # reference default: INTERMEDIATE_PRECISION = COEFF << 1
+
+
+def _quantised_matches(ours, ref, bits, tie_tol):
+    """Quantised pixels must be identical except where the reference's own unquantised value sits within
+    `tie_tol` LSB of a rounding tie (BASELINE.json north_star); even there the difference is at most one LSB."""
+    m = (1 << bits) - 1
+    qo, qr = pl.quantize_unorm(ours, bits).astype(np.int64), pl.quantize_unorm(ref, bits).astype(np.int64)
+    diff = qo != qr
+    if diff.any():
+        assert np.abs(qo - qr).max() <= 1
+        frac = np.clip(np.asarray(ref, dtype=np.float64), 0, 1) * m
+        dist = np.abs(frac - np.floor(frac) - 0.5)
+        assert (dist[diff] < tie_tol).all(), "quantised mismatch away from a rounding tie: max dist %.3g" % dist[diff].max()
+    return float(diff.mean())
+
+
+def check_spec_presets(lib, prec, h, w, d, seed=0, fast=False):
+    """Fused spec epilogue / ispec prologue vs the restated reference loops (spec/spec.c:66-139, ispec.c:84-163)."""
+    rng = np.random.default_rng(seed)
+    px = (rng.integers(0, 256, (h, w, d)) / 255.0).astype(DT[prec])
+    I = INTERMEDIATE[prec]
+    for preset in ("abs", "shift", "flat", "sign", "copy"):
+        s1, dc1 = gspec.spec(px, preset, lib=lib)
+        s0, dc0 = pl.spec_forward(px, preset, intermediate=I, fast=fast)
+        np.testing.assert_allclose(dc1, dc0, rtol=0, atol=2e-6 if prec == "f" else 1e-13)
+        if preset == "sign":
+            # a sign map: every coefficient whose magnitude is above the float noise floor must get the same bit
+            raw = od.dctn_fast(px.astype(np.float64), [od.REDFT10] * 2, axes=(0, 1))
+            solid = np.abs(raw) > (1e-4 if prec == "f" else 1e-10) * np.abs(raw).max()
+            solid.reshape(-1)[:d] = False
+            assert np.array_equal(s1[solid], s0[solid])
+            continue
+        assert od.rel_l2(s1, s0) < OK[prec], (preset, od.rel_l2(s1, s0))
+        sm = None
+        if preset == "abs":
+            smf, _ = pl.spec_forward(px, "sign", intermediate=I, fast=fast)
+            sm = np.round(smf * 255).astype(np.uint8)
+            sm.reshape(-1)[:d] = np.round(dc0 * 255).astype(np.uint8)
+        b1 = gspec.ispec(s0, dc0, preset, signmap=sm, lib=lib)
+        b0 = pl.ispec_inverse(s0, dc0, preset, intermediate=I, signmap=sm, fast=fast)
+        assert od.rel_l2(b1, b0) < OK[prec], (preset, od.rel_l2(b1, b0))
+
+
+def check_spec_c1_roundtrip(lib, prec, h=512, w=512, d=3, preset="shift", seed=0):
+    """BASELINE config 0: spec -t <preset> -> 16-bit image -> ispec -t <preset> -> 8- and 16-bit pixels, against the
+    same chain through the oracle.  Returns the fractions of differing 16-bit spectrogram / 8-bit pixel values."""
+    rng = np.random.default_rng(seed)
+    px = (rng.integers(0, 256, (h, w, d)) / 255.0).astype(DT[prec])
+    I = INTERMEDIATE[prec]
+    s1, dc1 = gspec.spec(px, preset, lib=lib)
+    s0, dc0 = pl.spec_forward(px, preset, intermediate=I, fast=True)
+    f16 = _quantised_matches(s1, s0, 16, 0.25 if prec == "f" else 1e-6)   # f32 transform noise ~1e-6 = 0.07 LSB16
+    img = (pl.quantize_unorm(s0, 16) / 65535.0).astype(DT[prec])          # what ispec reads back from the PNG
+    b1 = gspec.ispec(img, dc0, preset, lib=lib)
+    b0 = pl.ispec_inverse(img, dc0, preset, intermediate=I, fast=True)
+    f8 = _quantised_matches(b1, b0, 8, 0.01 if prec == "f" else 1e-6)
+    _quantised_matches(b1, b0, 16, 0.5)                                    # at most one LSB anywhere
+    # and with the log-scaled template the round trip really reproduces the 8-bit source (spec/README.md:64-70)
+    if preset == "shift":
+        assert np.array_equal(pl.quantize_unorm(b1, 8), np.round(px.astype(np.float64) * 255).astype(np.uint8))
+    return f16, f8
+
+
+def check_spec_options(lib, prec):
+    """Individual -R/-T/-S/-G overrides (spec/spec.h:112-155) incl. rangetype dcs and the reference gain."""
+    rng = np.random.default_rng(3)
+    px = (rng.integers(0, 256, (24, 40, 3)) / 255.0).astype(DT[prec])
+    I = INTERMEDIATE[prec]
+    for params in [("log", "shift", "reference", "dcs"), ("linear", "abs", "native", "dc"), ("log", "retain", "custom", "one")]:
+        sc, sg, gt, rg = params
+        kw = dict(scale=sc, sign=sg, range_=rg, gain=(gt if gt != "custom" else 37.5))
+        s1, dc1 = gspec.spec(px, None, lib=lib, **kw)
+        s0, dc0 = pl.spec_forward(px, params=params, custom_gain=37.5, intermediate=I)
+        assert od.rel_l2(s1, s0) < OK[prec], (params, od.rel_l2(s1, s0))
+        if sg != "abs":
+            b1 = gspec.ispec(s0, dc0, None, lib=lib, **kw)
+            b0 = pl.ispec_inverse(s0, dc0, params=params, custom_gain=37.5, intermediate=I)
+            assert od.rel_l2(b1, b0) < OK[prec], (params, od.rel_l2(b1, b0))
+            b2 = gspec.ispec(s0, dc0, None, preserve_dc=True, lib=lib, **kw)
+            assert od.rel_l2(b2, pl.ispec_inverse(s0, dc0, params=params, custom_gain=37.5, intermediate=I, preserve_dc=True)) < OK[prec]

@@ -148,3 +148,23 @@ def test_launch_counter_counts_our_kernels(lib):
     before = lib.dsp_dct_launch_count()
     cases.check_interleaved_2d(lib, "f", 64, 64, 1, REDFT10)
     assert lib.dsp_dct_launch_count() - before == 2
+
+
+# ---------------------------------------------------------------------------------------------- spec / ispec (fused)
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("shape", [(16, 24, 3), (64, 64, 1), (33, 50, 4), (256, 384, 3)])
+def test_spec_presets(lib, prec, shape):
+    cases.check_spec_presets(lib, prec, *shape, fast=max(shape) > 64)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_spec_option_overrides(lib, prec):
+    cases.check_spec_options(lib, prec)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("preset", ["shift", "flat"])
+def test_spec_c1_roundtrip_512(lib, prec, preset):
+    """BASELINE config 0: spec + ispec round trip on a synthetic 512x512 RGB image, 16-bit spectrogram, 8/16-bit pixels."""
+    f16, f8 = cases.check_spec_c1_roundtrip(lib, prec, 512, 512, 3, preset)
+    assert f8 < 1e-3
