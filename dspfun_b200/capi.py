@@ -24,6 +24,7 @@ SYMBOLS = [
     "dsp_dct_execute_dev", "dsp_dct_destroy", "dsp_dct_alloc", "dsp_dct_free", "dsp_dct_cleanup",
     "dsp_dct_last_error", "dsp_dct_launch_count", "dsp_dct_fuse_scale", "dsp_dct_fuse_spec", "dsp_dct_spec_dc",
     "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
+    "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
 ]
 
 
@@ -82,6 +83,16 @@ def bind(path):
     lib.dsp_dct_spec_dc.argtypes = [vp, ctypes.POINTER(cd), ci]
     lib.dsp_dct_fuse_ispec.restype = ci
     lib.dsp_dct_fuse_ispec.argtypes = [vp, ctypes.POINTER(IspecParams)]
+    lib.dsp_scan_create.restype = vp
+    lib.dsp_scan_create.argtypes = [ctypes.c_char, ci, ci, ci, vp, vp]
+    lib.dsp_scan_frame.restype = ci
+    lib.dsp_scan_frame.argtypes = [vp, ci, ci, vp]
+    lib.dsp_scan_coeffs.restype = ci
+    lib.dsp_scan_coeffs.argtypes = [vp, vp]
+    lib.dsp_scan_sum.restype = ci
+    lib.dsp_scan_sum.argtypes = [vp, vp]
+    lib.dsp_scan_destroy.restype = None
+    lib.dsp_scan_destroy.argtypes = [vp]
     lib.dsp_dct_profile.restype = ci
     lib.dsp_dct_profile.argtypes = [vp, ci]
     lib.dsp_dct_num_passes.restype = ci

@@ -76,6 +76,11 @@ struct FftDesc {
 	FastDiv dM[DSP_MAX_FAC];     // divide by M_p = L_p / r_p
 	FastDiv dNb[DSP_MAX_FAC];    // divide by n / r_p (butterflies per sequence in pass p)
 	FastDiv dHalf;               // divide by n/2+1
+	// dense fallback (lengths with a prime factor > 13): direct O(n^2) evaluation of the definition
+	int dense;                   // 1: no FFT; input at [0, half), output at [half, 2*half) of each sequence
+	int half;                    // complex elements per half
+	const void *ctab;            // T[4n]  cos(pi m / 2n)
+	FastDiv dN;                  // divide by n
 };
 
 // Up to four outer loop levels around a pass (level 0 fastest).  slot: which coordinate the level feeds
@@ -345,18 +350,80 @@ DSP_DEV void dct2_post(C2<T> *s, int nseq, const FftDesc &f, int tid, int nthr) 
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ dense fallback
+// Y_k = 2 sum_j x_j cos(pi (2j+1) k / 2n)            (REDFT10)
+// Y_k = x_0 + 2 sum_{j>=1} x_j cos(pi j (2k+1) / 2n)  (REDFT01)
+// evaluated directly on the (A, B) complex pairs; the cosine comes from a 4n-periodic table.
+template <class T>
+DSP_DEV void dense_dct(C2<T> *s, int nseq, const FftDesc &f, bool fwd, int tid, int nthr) {
+	const int n = f.n, p4 = 4 * n;
+	const T *ct = (const T *)f.ctab;
+	const uint32_t total = (uint32_t)nseq * (uint32_t)n;
+	for (uint32_t g = (uint32_t)tid; g < total; g += (uint32_t)nthr) {
+		const uint32_t seq = fd_div(g, f.dN);
+		const int k = (int)(g - seq * (uint32_t)n);
+		const C2<T> *in = s + (size_t)seq * (size_t)f.npad;
+		T ar = 0, ai = 0;
+		if (fwd) {
+			int idx = k % p4;
+			const int step = (2 * k) % p4;
+			for (int j = 0; j < n; j++) {
+				const T c = DSP_LDG(ct + idx);
+				const C2<T> x = in[Pad<T>::of(j)];
+				ar += x.x * c; ai += x.y * c;
+				idx += step; if (idx >= p4) idx -= p4;
+			}
+			ar *= 2; ai *= 2;
+		} else {
+			const int step = (2 * k + 1) % p4;
+			int idx = step;
+			for (int j = 1; j < n; j++) {
+				const T c = DSP_LDG(ct + idx);
+				const C2<T> x = in[Pad<T>::of(j)];
+				ar += x.x * c; ai += x.y * c;
+				idx += step; if (idx >= p4) idx -= p4;
+			}
+			const C2<T> x0 = in[Pad<T>::of(0)];
+			ar = x0.x + 2 * ar; ai = x0.y + 2 * ai;
+		}
+		s[(size_t)seq * (size_t)f.npad + f.half + Pad<T>::of(k)] = C2<T>{ar, ai};
+	}
+}
+
+// the transform phases between copy-in and copy-out
+template <class T>
+DSP_DEV void transform_phases(C2<T> *s, int nseq, const FftDesc &f, bool fwd, int t0, int t1, int nthr) {
+	if (f.dense) {
+		for (int tid = t0; tid < t1; tid++) dense_dct<T>(s, nseq, f, fwd, tid, nthr);
+		DSP_SYNC();
+		return;
+	}
+	if (!fwd) {
+		for (int tid = t0; tid < t1; tid++) dct3_pre<T>(s, nseq, f, tid, nthr);
+		DSP_SYNC();
+	}
+	fft_dif<T>(s, nseq, f, t0, t1, nthr);
+	if (fwd) {
+		for (int tid = t0; tid < t1; tid++) dct2_post<T>(s, nseq, f, tid, nthr);
+		DSP_SYNC();
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ fused ops
 // A load op maps the value read from global memory to the value entering the transform; a store op maps the
 // transform output to the value written.  Both see the element's logical coordinates.
 // v * f: the lean kernels' only pointwise stage (f = 1 when nothing is fused; dsp_dct_fuse_scale sets it)
 template <class T> struct OpMul {
+	enum { kNeedsCoord = 0 };
 	T f;
 	DSP_DEVM T operator()(T v, const Coord &) const { return v * f; }
 };
 struct OpNone {
+	enum { kNeedsCoord = 0 };
 	template <class T> DSP_DEVM T operator()(T v, const Coord &) const { return v; }
 };
 struct OpScale {                 // v * a   (e.g. scan's 1/(4wh), spec/ispec plain normalisations)
+	enum { kNeedsCoord = 0 };
 	double a;
 	template <class T> DSP_DEVM T operator()(T v, const Coord &) const { return v * (T)a; }
 };
@@ -445,7 +512,7 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 					cb.set(a.ax_slot, x); cb.ch = ch;
 					const T pa = lop(va[t], ca);
 					const T pb = hasb ? lop(vb[t], cb) : (T)0;
-					const int slot = fwd ? ((x & 1) ? n - 1 - (x >> 1) : (x >> 1)) : x;
+					const int slot = (fwd && !a.f.dense) ? ((x & 1) ? n - 1 - (x >> 1) : (x >> 1)) : x;
 					s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + Pad<T>::of(slot)] = C2<T>{pa, pb};
 				}
 			}
@@ -454,15 +521,7 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 	DSP_SYNC();
 
 	// ---- transform
-	if (!fwd) {
-		for (int tid = t0; tid < t1; tid++) dct3_pre<T>(s, nseq, a.f, tid, nthr);
-		DSP_SYNC();
-	}
-	fft_dif<T>(s, nseq, a.f, t0, t1, nthr);
-	if (fwd) {
-		for (int tid = t0; tid < t1; tid++) dct2_post<T>(s, nseq, a.f, tid, nthr);
-		DSP_SYNC();
-	}
+	transform_phases<T>(s, nseq, a.f, fwd, t0, t1, nthr);
 
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
@@ -483,11 +542,11 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 				ra.v[t] = 0; rb.v[t] = 0;
 				if (e >= llen) continue;
 				const int x = (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
-				const C2<T> z = s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + Pad<T>::of((int)DSP_LDG(pos + x))];
+				const C2<T> z = s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + (a.f.dense ? a.f.half : 0) + Pad<T>::of((int)DSP_LDG(pos + x))];
 				ca.set(a.ax_slot, x); ca.ch = ch;
 				cb.set(a.ax_slot, x); cb.ch = ch;
 				ra.v[t] = sop(z.x, ca);
-				rb.v[t] = sop(fwd ? z.y : -z.y, cb);
+				rb.v[t] = sop((fwd || a.f.dense) ? z.y : -z.y, cb);
 			}
 			if (a.vec_out && e0 + VN <= llen) {
 				*(Vec *)(gout + oa + e0) = ra;
@@ -569,7 +628,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 					v[t] = lop(v[t], c);
 				}
 			}
-			const int slot = Pad<T>::of(fwd ? (((int)r & 1) ? n - 1 - ((int)r >> 1) : ((int)r >> 1)) : (int)r);
+			const int slot = Pad<T>::of((fwd && !a.f.dense) ? (((int)r & 1) ? n - 1 - ((int)r >> 1) : ((int)r >> 1)) : (int)r);
 #pragma unroll
 			for (int p = 0; p < VN / 2; p++)
 				if (c0 + 2 * p < ncl)
@@ -579,15 +638,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	DSP_SYNC();
 
 	// ---- transform
-	if (!fwd) {
-		for (int tid = t0; tid < t1; tid++) dct3_pre<T>(s, nseq, a.f, tid, nthr);
-		DSP_SYNC();
-	}
-	fft_dif<T>(s, nseq, a.f, t0, t1, nthr);
-	if (fwd) {
-		for (int tid = t0; tid < t1; tid++) dct2_post<T>(s, nseq, a.f, tid, nthr);
-		DSP_SYNC();
-	}
+	transform_phases<T>(s, nseq, a.f, fwd, t0, t1, nthr);
 
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
@@ -595,7 +646,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n * gpr; idx += (uint32_t)nthr) {
 			const uint32_t r = idx / gpr, cg = idx - r * gpr;
 			const int c0 = (int)cg * VN;
-			const int slot = Pad<T>::of((int)DSP_LDG(pos + r));
+			const int slot = (a.f.dense ? a.f.half : 0) + Pad<T>::of((int)DSP_LDG(pos + r));
 			Coord c = cbase;
 			c.set(a.ax_slot, (int)r);
 			Vec res;
@@ -605,7 +656,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 				if (c0 + 2 * p < ncl) {
 					const C2<T> z = s[(size_t)(c0 / 2 + p) * (size_t)a.f.npad + slot];
 					res.v[2 * p] = z.x;
-					res.v[2 * p + 1] = fwd ? z.y : -z.y;
+					res.v[2 * p + 1] = (fwd || a.f.dense) ? z.y : -z.y;
 				}
 			}
 #pragma unroll

@@ -443,7 +443,7 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op,
 					const int la = line0 + 2 * g;
 					long long ia, ib, oa;
 					Coord c = {0, 0, 0, 0, 0};
-					if (a.simple) { ia = la * a.ls_in; ib = ia + a.ls_in; }
+					if (a.simple && !Op::kNeedsCoord) { ia = la * a.ls_in; ib = ia + a.ls_in; }
 					else { outer_decode(a.o, (uint32_t)la, ia, oa, c); ib = 0; if (2 * g + 1 < nl) outer_decode(a.o, (uint32_t)la + 1, ib, oa, c); }
 					ta[u] = ldg_stream((const Vec *)(gin + ia + 4 * q));
 					if (2 * g + 1 < nl) tb[u] = ldg_stream((const Vec *)(gin + ib + 4 * q));
@@ -460,7 +460,7 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op,
 				const bool hasb = 2 * g + 1 < nl;
 				Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 				long long ia, ib = 0, oa, ob = 0;
-				if (a.simple) { oa = la * a.ls_out; ob = oa + a.ls_out; }
+				if (a.simple && !Op::kNeedsCoord) { oa = la * a.ls_out; ob = oa + a.ls_out; }
 				else { outer_decode(a.o, (uint32_t)la, ia, oa, ca); if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb); }
 				C2<T> *sg = s + g * f.npad;
 				const int s0 = (int)DSP_LDG(f.sig + 2 * q), s1 = (int)DSP_LDG(f.sig + n - 2 - 2 * q);

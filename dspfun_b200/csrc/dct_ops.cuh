@@ -24,6 +24,7 @@ enum {
 };
 
 struct OpAny {
+	enum { kNeedsCoord = 1 };
 	int kind;
 	int scaletype, signtype, rangetype;
 	int d, w, h, flag;

@@ -75,6 +75,10 @@ struct Tables {
 	// power-of-two fast path (n = r0 * 16^(nmid+1)); sig == nullptr when not applicable
 	int r0, nmid;
 	uint16_t *sig;
+	// dense fallback
+	bool dense;
+	int half;
+	void *ctab;
 };
 static std::map<std::pair<int, std::pair<int, char>>, Tables *> g_tables;
 
@@ -86,12 +90,15 @@ template <class T> static Tables *build_tables(int n) {
 	t->prec = sizeof(T) == 4 ? 'f' : 'd';
 	t->tw = t->om = nullptr;
 	t->pos2 = t->pos3 = nullptr;
-	if (!factorize(n, t->fac)) {
-		g_err = "transform length " + std::to_string(n) + " has a prime factor > 13 (not supported by the on-chip FFT path yet)";
-		delete t;
-		return nullptr;
-	}
+	t->dense = false; t->half = 0; t->ctab = nullptr; t->sig = nullptr;
 	t->npad = pad_of<T>(n - 1) + 1;
+	if (!factorize(n, t->fac)) {
+		// a prime factor > 13: direct evaluation of the definition (O(n^2) per line, exact same results contract)
+		t->dense = true;
+		t->fac.clear();
+		t->half = t->npad;
+		t->npad = 2 * t->half;
+	}
 	const long double pi = 3.141592653589793238462643383279502884L;
 	std::vector<C2<T>> tw(n), om(n / 2 + 1);
 	for (int k = 0; k < n; k++) {
@@ -108,13 +115,18 @@ template <class T> static Tables *build_tables(int n) {
 	for (int k = 0; k < n; k++) {
 		int kk = k, P = 0, stride = n;
 		for (int r : t->fac) { stride /= r; P += (kk % r) * stride; kk /= r; }
-		pos2[k] = (uint16_t)P;
+		pos2[k] = (uint16_t)(t->dense ? k : P);
 	}
-	for (int j = 0; j < n; j++) pos3[j] = pos2[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)];
+	for (int j = 0; j < n; j++) pos3[j] = t->dense ? (uint16_t)j : pos2[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)];
+	std::vector<T> ctab;
+	if (t->dense) {
+		ctab.resize(4 * (size_t)n);
+		for (long m = 0; m < 4L * n; m++) ctab[m] = (T)cosl(pi * (long double)m / (2 * (long double)n));
+	}
 	// fast path: n = r0 * 16^(nmid+1), r0 in {1,2,4,8,16,32}
-	t->sig = nullptr; t->r0 = 0; t->nmid = 0;
+	t->r0 = 0; t->nmid = 0;
 	std::vector<uint16_t> sig;
-	if (n >= 16 && (n & (n - 1)) == 0 && !getenv("DSP_DCT_NO_FAST") && (sizeof(T) == 4 || DSP_FAST_F64)) {
+	if (!t->dense && n >= 16 && (n & (n - 1)) == 0 && !getenv("DSP_DCT_NO_FAST") && (sizeof(T) == 4 || DSP_FAST_F64)) {
 		int a = 0;
 		while ((1 << a) < n) a++;
 		int l0 = (a - 4) % 4;                       // log2 r0 in {0,1,2,3} ...
@@ -139,11 +151,13 @@ template <class T> static Tables *build_tables(int n) {
 	          rt_h2d(t->tw, tw.data(), sizeof(C2<T>) * n, 0, err) && rt_h2d(t->om, om.data(), sizeof(C2<T>) * (n / 2 + 1), 0, err) &&
 	          rt_h2d(t->pos2, pos2.data(), sizeof(uint16_t) * n, 0, err) && rt_h2d(t->pos3, pos3.data(), sizeof(uint16_t) * n, 0, err) &&
 	          rt_sync(0, err);
+	if (ok && t->dense)
+		ok = rt_malloc(&t->ctab, sizeof(T) * ctab.size(), err) && rt_h2d(t->ctab, ctab.data(), sizeof(T) * ctab.size(), 0, err) && rt_sync(0, err);
 	if (ok && !sig.empty())
 		ok = rt_malloc((void **)&t->sig, sizeof(uint16_t) * n, err) && rt_h2d(t->sig, sig.data(), sizeof(uint16_t) * n, 0, err) && rt_sync(0, err);
 	if (!ok) {
 		g_err = err;
-		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig);
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig); rt_free(t->ctab);
 		delete t;
 		return nullptr;
 	}
@@ -176,6 +190,8 @@ static void fill_fft(FftDesc &f, const Tables *t) {
 	f.npad = t->npad;
 	f.tw = t->tw; f.om = t->om; f.pos2 = t->pos2; f.pos3 = t->pos3;
 	f.dHalf = mk_fd((uint32_t)(t->n / 2 + 1));
+	f.dense = t->dense ? 1 : 0; f.half = t->half; f.ctab = t->ctab;
+	f.dN = mk_fd((uint32_t)t->n);
 }
 
 template <class T> static void fill_fast_t(FastDesc &f, const Tables *t) {
@@ -618,7 +634,7 @@ void dsp_dct_cleanup(void) {
 	std::lock_guard<std::mutex> lock(g_mu);
 	for (auto &kv : g_tables) {
 		Tables *t = kv.second;
-		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig);
+		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig); rt_free(t->ctab);
 		delete t;
 	}
 	g_tables.clear();
@@ -751,5 +767,93 @@ int dsp_dct_fuse_ispec(dsp_dct_plan p, const dsp_ispec_params *ip) {
 	p->fuse_kind = 2;
 	return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ scan session
+struct dsp_scan_s {
+	char prec;
+	int h, w, d;
+	size_t bytes;
+	void *d_coeffs, *d_image, *d_sum;
+	int32_t *d_index;
+	dsp_dct_plan inverse;
+};
+
+static void scan_free(dsp_scan_s *s) {
+	if (!s) return;
+	if (s->inverse) dsp_dct_destroy(s->inverse);
+	rt_free(s->d_coeffs); rt_free(s->d_image); rt_free(s->d_sum); rt_free(s->d_index);
+	delete s;
+}
+
+dsp_scan dsp_scan_create(char prec, int h, int w, int d, const void *pixels, const int32_t *index_map) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || h < 1 || w < 1 || d < 1 || d > 4 || !pixels || !index_map) { g_err = "bad scan arguments"; return nullptr; }
+	dsp_scan_s *s = new dsp_scan_s();
+	memset(s, 0, sizeof(*s));
+	s->prec = prec; s->h = h; s->w = w; s->d = d;
+	const size_t es = prec == 'f' ? 4 : 8, l = (size_t)h * w * d;
+	s->bytes = l * es;
+	const int n[2] = {h, w}, k10[2] = {DSP_DCT_REDFT10, DSP_DCT_REDFT10}, k01[2] = {DSP_DCT_REDFT01, DSP_DCT_REDFT01};
+	const int hm = d, st = d > 1 ? d : 1, di = d > 1 ? 1 : 0;
+	bool ok = rt_init(g_err) && rt_malloc(&s->d_coeffs, s->bytes, g_err) && rt_malloc(&s->d_image, s->bytes, g_err) &&
+	          rt_malloc(&s->d_sum, s->bytes, g_err) && rt_malloc((void **)&s->d_index, sizeof(int32_t) * (size_t)h * w, g_err) &&
+	          rt_h2d(s->d_coeffs, pixels, s->bytes, 0, g_err) && rt_h2d(s->d_index, index_map, sizeof(int32_t) * (size_t)h * w, 0, g_err);
+	dsp_dct_plan fwd = nullptr;
+	if (ok) {
+		// scan.c:292-298: forward transform, coefficients normalised to the non-uniform range -1..1
+		fwd = dsp_dct_plan_many(prec, 2, n, hm, s->d_coeffs, nullptr, st, di, s->d_coeffs, nullptr, st, di, k10, 0);
+		ok = fwd && dsp_dct_fuse_scale(fwd, 1.0, 1.0 / (4.0 * (double)w * (double)h)) == 0 &&
+		     dsp_dct_execute_dev(fwd, s->d_coeffs, s->d_coeffs, nullptr) == 0;
+	}
+	if (fwd) { rt_sync(0, g_err); dsp_dct_destroy(fwd); }
+	if (ok) {
+		// scan.c:381-383: the sum starts as the DC value of every channel
+		std::vector<unsigned char> dc(es * (size_t)d), fill(s->bytes);
+		ok = rt_d2h(dc.data(), s->d_coeffs, dc.size(), 0, g_err) && rt_sync(0, g_err);
+		for (size_t i = 0; ok && i < (size_t)h * w; i++) memcpy(fill.data() + i * dc.size(), dc.data(), dc.size());
+		ok = ok && rt_h2d(s->d_sum, fill.data(), s->bytes, 0, g_err) && rt_sync(0, g_err);
+	}
+	if (ok) {
+		// scan.c:359: out-of-place inverse plan reconstruction -> image
+		s->inverse = dsp_dct_plan_many(prec, 2, n, hm, s->d_coeffs, nullptr, st, di, s->d_image, nullptr, st, di, k01, 0);
+		ok = s->inverse != nullptr;
+	}
+	if (ok) {
+		PassPlan &f = s->inverse->passes.front(), &l2 = s->inverse->passes.back();
+		memset(&f.lop, 0, sizeof(OpAny));
+		f.lop.kind = OP_SCAN_MASK; f.lop.w = w; f.lop.h = h; f.lop.d = d; f.lop.aux_c = s->d_index; f.lop.lo = 0; f.lop.hi = 0;
+		f.fused = true;
+		memset(&l2.sop, 0, sizeof(OpAny));
+		l2.sop.kind = OP_SCAN_ACCUM; l2.sop.w = w; l2.sop.h = h; l2.sop.d = d; l2.sop.aux = s->d_sum;
+		l2.fused = true;
+		s->inverse->fuse_kind = 3;
+	}
+	if (!ok) { scan_free(s); return nullptr; }
+	return s;
+}
+
+int dsp_scan_frame(dsp_scan s, int lo, int hi, void *frame) {
+	g_err.clear();
+	if (!s) { g_err = "null scan"; return 1; }
+	PassPlan &f = s->inverse->passes.front();
+	f.lop.lo = lo; f.lop.hi = hi;
+	if (dsp_dct_execute_dev(s->inverse, s->d_coeffs, s->d_image, nullptr) != 0) return 1;
+	if (frame && !rt_d2h(frame, s->d_image, s->bytes, 0, g_err)) return 1;
+	return rt_sync(0, g_err) ? 0 : 1;
+}
+
+int dsp_scan_coeffs(dsp_scan s, void *coeffs) {
+	g_err.clear();
+	if (!s || !coeffs) { g_err = "null scan"; return 1; }
+	return (rt_d2h(coeffs, s->d_coeffs, s->bytes, 0, g_err) && rt_sync(0, g_err)) ? 0 : 1;
+}
+
+int dsp_scan_sum(dsp_scan s, void *sum) {
+	g_err.clear();
+	if (!s || !sum) { g_err = "null scan"; return 1; }
+	return (rt_d2h(sum, s->d_sum, s->bytes, 0, g_err) && rt_sync(0, g_err)) ? 0 : 1;
+}
+
+void dsp_scan_destroy(dsp_scan s) { scan_free(s); }
 
 }  // extern "C"

@@ -140,6 +140,22 @@ typedef struct {
 } dsp_ispec_params;
 int dsp_dct_fuse_ispec(dsp_dct_plan p, const dsp_ispec_params *ip);
 
+/* ---- scan: progressive reconstruction (scan/scan.c:292-298, 352-459) ------------------------------------------
+ * A scan session keeps the coefficient plane, the scan-order index map and the running sum on the GPU:
+ *   create : REDFT10 x REDFT10 of the [h][w][d] interleaved pixels, fused 1/(4wh) (scan.c:292-298);
+ *            sum[y][x][z] = DC[z] (scan.c:381-383).  index_map[y][x] is the scan step that delivers
+ *            coefficient (y, x) -- the "index" serialisation of scan/scan_precomputed.c:133-153.
+ *   frame  : one output frame: keep coefficients with lo <= index < hi, clear DC (scan.c:429-445), REDFT01 x
+ *            REDFT01 (scan.c:447), sum += image, frame = sum (scan.c:451-456).  The mask rides in the inverse's
+ *            first pass and the accumulation in its last pass; `frame` (host, T[h][w][d]) may be NULL.
+ *   coeffs / sum : copy the normalised coefficient plane / current sum to host buffers. */
+typedef struct dsp_scan_s *dsp_scan;
+dsp_scan dsp_scan_create(char prec, int h, int w, int d, const void *pixels, const int32_t *index_map);
+int dsp_scan_frame(dsp_scan s, int lo, int hi, void *frame);
+int dsp_scan_coeffs(dsp_scan s, void *coeffs);
+int dsp_scan_sum(dsp_scan s, void *sum);
+void dsp_scan_destroy(dsp_scan s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,28 @@ def base16enc(raw: bytes) -> str:
 def base16dec(s: str) -> bytes:
     """spec/spec.h:164-168."""
     return bytes(((ord(s[i]) - 65) | ((ord(s[i + 1]) - 65) << 4)) & 0xFF for i in range(0, len(s), 2))
+
+
+def scan_frames(pixels, index_map, step=1, nframes=None, fast=False):
+    """scan/scan.c:292-298 (forward, /= 4wh), :377-383 (sum = DC), :421-459 (per frame: zero reconstruction, copy the
+    interval's coefficients, clear DC, REDFT01 x REDFT01, sum += image, emit sum).  Default options."""
+    C = pixels.dtype.type
+    h, w, d = pixels.shape
+    coeffs = _transform(np.ascontiguousarray(pixels), [odct.REDFT10, odct.REDFT10], fast)   # :292-294
+    coeffs = (coeffs / C(w * h * 4)).astype(C)                                                # :297-298
+    total = np.empty_like(coeffs)
+    total[:, :, :] = coeffs[0, 0, :]                                                          # :381-383
+    limit = int(index_map.max()) + 1
+    if not nframes or nframes > limit // step:
+        nframes = (limit + step - 1) // step                                                  # :346-347
+    frames = []
+    for i in range(nframes):
+        lo, hi = i * step, min(i * step + step, limit)
+        recon = np.zeros_like(coeffs)                                                         # :429
+        sel = (index_map >= lo) & (index_map < hi)
+        recon[sel] = coeffs[sel]                                                              # :430-432
+        recon[0, 0, :] = 0                                                                    # :445
+        image = _transform(recon, [odct.REDFT01, odct.REDFT01], fast)                         # :447
+        total = (total + image).astype(C)                                                     # :454
+        frames.append(total.copy())
+    return frames, coeffs

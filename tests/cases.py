@@ -100,6 +100,7 @@ def check_golden_1d(lib, golden, prec, n, typ):
 SHAPES_2D = [
     (8, 8, 1), (16, 32, 3), (12, 20, 3), (30, 14, 1), (64, 48, 3), (1, 16, 1), (16, 1, 3), (1, 1, 3), (5, 7, 2),
     (2, 3, 4), (256, 256, 1), (100, 135, 3), (33, 77, 1), (26, 22, 3), (128, 512, 3), (1024, 16, 1), (49, 81, 2),
+    (17, 17, 1), (34, 19, 3), (509, 3, 1), (6, 211, 2),          # prime factors > 13: dense fallback
 ]
 
 
@@ -188,3 +189,33 @@ def check_spec_options(lib, prec):
             assert od.rel_l2(b1, b0) < OK[prec], (params, od.rel_l2(b1, b0))
             b2 = gspec.ispec(s0, dc0, None, preserve_dc=True, lib=lib, **kw)
             assert od.rel_l2(b2, pl.ispec_inverse(s0, dc0, params=params, custom_gain=37.5, intermediate=I, preserve_dc=True)) < OK[prec]
+
+
+# ---------------------------------------------------------------------------------------------- scan
+from dspfun_b200 import scan as gscan           # noqa: E402
+
+
+def check_scan(lib, prec, h, w, d, order="diagonal", step=1, seed=4):
+    """Fused masked inverse + accumulate (scan/scan.c:421-459) vs the restated loop; the last frame must also pass
+    the reference's own --measure-parity self-check (scan/scan.c:508-526) at the source bit depth."""
+    rng = np.random.default_rng(seed)
+    px8 = rng.integers(0, 256, (h, w, d))
+    px = (px8 / 255.0).astype(DT[prec])
+    idx = gscan.order_diagonal(h, w) if order == "diagonal" else gscan.order_horizontal(h, w)
+    ref_frames, ref_coeffs = pl.scan_frames(px, idx, step=step, fast=max(h, w) > 64)
+    s = gscan.Scan(px, idx, lib=lib)
+    assert od.rel_l2(s.coeffs(), ref_coeffs) < OK[prec]
+    limit = int(idx.max()) + 1
+    nframes = (limit + step - 1) // step
+    assert nframes == len(ref_frames)
+    worst = 0.0
+    for i in range(nframes):
+        want = i % max(1, nframes // 6) == 0 or i == nframes - 1          # D2H only a few frames; all are computed
+        f = s.frame(i * step, min((i + 1) * step, limit), want=want)
+        if want:
+            worst = max(worst, od.rel_l2(f, ref_frames[i]))
+    s.destroy()
+    assert worst < OK[prec] * 4, worst
+    # scan.c:508-526: lround(orig * (2^depth - 1)) == lround(sum * (2^depth - 1))
+    assert np.array_equal(np.round(f.astype(np.float64) * 255).astype(np.int64), px8)
+    return worst

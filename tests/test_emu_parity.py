@@ -52,7 +52,7 @@ def test_batched_images_roundtrip(lib, prec):
 
 @pytest.mark.parametrize("prec", ["f", "d"])
 @pytest.mark.parametrize("typ", [2, 3])
-@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 17, 32, 64, 128, 256, 512, 1024])
 def test_fftw_golden_vectors(lib, golden, prec, typ, n):
     cases.check_golden_1d(lib, golden, prec, n, typ)
 

@@ -72,7 +72,7 @@ def test_batched_images_roundtrip(lib, prec):
 
 @pytest.mark.parametrize("prec", ["f", "d"])
 @pytest.mark.parametrize("typ", [2, 3])
-@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 12, 15, 16, 17, 32, 64, 128, 256, 512, 1024])
 def test_fftw_golden_vectors(lib, golden, prec, typ, n):
     cases.check_golden_1d(lib, golden, prec, n, typ)
 
@@ -168,3 +168,12 @@ def test_spec_c1_roundtrip_512(lib, prec, preset):
     """BASELINE config 0: spec + ispec round trip on a synthetic 512x512 RGB image, 16-bit spectrogram, 8/16-bit pixels."""
     f16, f8 = cases.check_spec_c1_roundtrip(lib, prec, 512, 512, 3, preset)
     assert f8 < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- scan (fused mask + accumulate)
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_scan_frames(lib, prec):
+    cases.check_scan(lib, prec, 8, 8, 3, "diagonal")
+    cases.check_scan(lib, prec, 16, 12, 3, "horizontal", step=16)
+    cases.check_scan(lib, prec, 32, 32, 1, "diagonal", step=3)
+    cases.check_scan(lib, prec, 256, 192, 3, "diagonal", step=8)
