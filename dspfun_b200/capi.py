@@ -25,6 +25,7 @@ SYMBOLS = [
     "dsp_dct_last_error", "dsp_dct_launch_count", "dsp_dct_fuse_scale", "dsp_dct_fuse_spec", "dsp_dct_spec_dc",
     "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
+    "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy",
 ]
 
 
@@ -41,6 +42,13 @@ class PassStat(ctypes.Structure):
     _fields_ = [("is_row", ctypes.c_int), ("axis", ctypes.c_int), ("n", ctypes.c_int), ("grid", ctypes.c_int),
                 ("block", ctypes.c_int), ("smem_bytes", ctypes.c_size_t), ("launches", ctypes.c_int),
                 ("ms_total", ctypes.c_double), ("samples", ctypes.c_double)]
+
+
+class MotionParams(ctypes.Structure):
+    _fields_ = [("block", ctypes.c_int * 3), ("scaled", ctypes.c_int * 3), ("float_pixels", ctypes.c_int),
+                ("damp", ctypes.c_double), ("boost", ctypes.c_double), ("bp_begin", ctypes.c_int * 3),
+                ("bp_end", ctypes.c_int * 3), ("threshold_min", ctypes.c_double), ("threshold_max", ctypes.c_double),
+                ("quant", ctypes.c_double), ("preserve_dc", ctypes.c_int)]
 
 
 class IspecParams(ctypes.Structure):
@@ -93,6 +101,14 @@ def bind(path):
     lib.dsp_scan_sum.argtypes = [vp, vp]
     lib.dsp_scan_destroy.restype = None
     lib.dsp_scan_destroy.argtypes = [vp]
+    lib.dsp_motion_create.restype = vp
+    lib.dsp_motion_create.argtypes = [ctypes.c_char, ctypes.POINTER(MotionParams)]
+    lib.dsp_motion_block.restype = ci
+    lib.dsp_motion_block.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.dsp_motion_block_dev.restype = ci
+    lib.dsp_motion_block_dev.argtypes = [vp, vp, vp, vp]
+    lib.dsp_motion_destroy.restype = None
+    lib.dsp_motion_destroy.argtypes = [vp]
     lib.dsp_dct_profile.restype = ci
     lib.dsp_dct_profile.argtypes = [vp, ci]
     lib.dsp_dct_num_passes.restype = ci

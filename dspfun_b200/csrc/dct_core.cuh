@@ -456,7 +456,11 @@ struct RowArgs {
 	const void *in;
 	void *out;
 	int vec_in, vec_out;         // 16-byte access legal
+	int in_u8, out_u8;           // the global side holds unsigned 8-bit samples (motion's pels); implies vec_* == 0
 };
+
+// 8-bit store: the value has already been clamped and rounded by the store op (motion/motion.c:776)
+template <class T> DSP_DEV unsigned char to_u8(T v) { return (unsigned char)(int)v; }
 
 template <class T, class LoadOp, class StoreOp>
 DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1, int nthr,
@@ -497,10 +501,16 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 					for (int t = 0; t < VN; t++) vb[t] = tb.v[t];
 				}
 			} else {
+				const unsigned char *g8 = (const unsigned char *)a.in;
 #pragma unroll
 				for (int t = 0; t < VN; t++) {
-					va[t] = (e0 + t < llen) ? gin[ia + e0 + t] : (T)0;
-					vb[t] = (hasb && e0 + t < llen) ? gin[ib + e0 + t] : (T)0;
+					if (a.in_u8) {
+						va[t] = (e0 + t < llen) ? (T)g8[ia + e0 + t] : (T)0;
+						vb[t] = (hasb && e0 + t < llen) ? (T)g8[ib + e0 + t] : (T)0;
+					} else {
+						va[t] = (e0 + t < llen) ? gin[ia + e0 + t] : (T)0;
+						vb[t] = (hasb && e0 + t < llen) ? gin[ib + e0 + t] : (T)0;
+					}
 				}
 			}
 #pragma unroll
@@ -552,11 +562,17 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 				*(Vec *)(gout + oa + e0) = ra;
 				if (hasb) *(Vec *)(gout + ob + e0) = rb;
 			} else {
+				unsigned char *o8 = (unsigned char *)a.out;
 #pragma unroll
 				for (int t = 0; t < VN; t++)
 					if (e0 + t < llen) {
-						gout[oa + e0 + t] = ra.v[t];
-						if (hasb) gout[ob + e0 + t] = rb.v[t];
+						if (a.out_u8) {
+							o8[oa + e0 + t] = to_u8(ra.v[t]);
+							if (hasb) o8[ob + e0 + t] = to_u8(rb.v[t]);
+						} else {
+							gout[oa + e0 + t] = ra.v[t];
+							if (hasb) gout[ob + e0 + t] = rb.v[t];
+						}
 					}
 			}
 		}

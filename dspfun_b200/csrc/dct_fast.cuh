@@ -364,6 +364,13 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 #pragma unroll
 								for (int t = 0; t < VN; t++) vb[u][t] = tb.v[t];
 							}
+						} else if (a.in_u8) {
+							const unsigned char *g8 = (const unsigned char *)a.in;
+#pragma unroll
+							for (int t = 0; t < VN; t++) {
+								va[u][t] = (e0 + t < llen) ? (T)g8[ia + e0 + t] : (T)0;
+								vb[u][t] = (hasb && e0 + t < llen) ? (T)g8[ib + e0 + t] : (T)0;
+							}
 						} else {
 #pragma unroll
 							for (int t = 0; t < VN; t++) {
@@ -403,6 +410,14 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 							for (int t = 0; t < VN; t++) { ra.v[t] = va[u][t]; rb.v[t] = vb[u][t]; }
 							*(Vec *)(qa + e0) = ra;
 							if (hasb) *(Vec *)(qb + e0) = rb;
+						} else if (a.out_u8) {
+							unsigned char *o8 = (unsigned char *)a.out;
+#pragma unroll
+							for (int t = 0; t < VN; t++)
+								if (e0 + t < llen) {
+									o8[oa + e0 + t] = to_u8(va[u][t]);
+									if (hasb) o8[ob + e0 + t] = to_u8(vb[u][t]);
+								}
 						} else {
 #pragma unroll
 							for (int t = 0; t < VN; t++)

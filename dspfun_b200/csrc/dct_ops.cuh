@@ -21,6 +21,9 @@ enum {
 	OP_ISPEC,        // load side of ispec's first pass
 	OP_SCAN_MASK,    // load side: keep coefficient iff lo <= index[y][x] < hi, zero DC   (scan/scan.c:429-445)
 	OP_SCAN_ACCUM,   // store side: sum[i] += v ; out = sum[i]                             (scan/scan.c:451-456)
+	OP_MOTION_COEFF, // load side of motion's inverse: zero-pad/crop, normalise, band-pass damp/boost, threshold,
+	                 // preserve-dc, quantise, de-normalise                               (motion/motion.c:617,644-751)
+	OP_MOTION_STORE, // store side of motion's inverse: scale, clamp, round to the 8-bit range  (motion/motion.c:757-776)
 };
 
 struct OpAny {
@@ -32,6 +35,9 @@ struct OpAny {
 	double p[4];             // OP_SCALE: p[0] = factor.  OP_SPEC/ISPEC: p[0] = gain, p[1] = norm (2wh)
 	double q[4];             // OP_ISPEC: log1p(max[z]) or max[z] per channel; OP_SPEC (range one): the same
 	double dc[4];            // OP_ISPEC preserve_dc values
+	int a3[3], b3[3], e3[3]; // OP_MOTION_COEFF: active box, band-pass begin / end (d, h, w order)
+	double m[8];             // OP_MOTION_*: damp, boost, threshold min, max, quantizer, grey offset, output scale, -
+	int flag2;               // OP_MOTION_STORE: float pixels
 	const void *aux_c;       // OP_SPEC: double[8] device scalars {scale_z[4], -, -, -, -};  OP_ISPEC: u8 signmap;  OP_SCAN_MASK: int32 index map
 	void *aux;               // OP_ACCUM_DC: double[4] accumulators;  OP_SPEC: double[4] DC out;  OP_SCAN_ACCUM: T sum buffer
 
@@ -95,6 +101,43 @@ struct OpAny {
 			if (y == 0 && x == 0) return (T)0;                                                       // scan.c:445
 			const int idx = DSP_LDG((const int *)aux_c + (size_t)y * w + x);
 			return (idx >= lo && idx < hi) ? v : (T)0;                                               // scan.c:429-432
+		}
+		case OP_MOTION_COEFF: {
+			const int z = c.i0, y = c.i1, x = c.i2;
+			if (z >= a3[0] || y >= a3[1] || x >= a3[2]) return (T)0;                                 // outside the active box: motion.c:617
+			const I nf = (2 * SQRT2) / ((x ? 1.0 : SQRT2) * (y ? 1.0 : SQRT2) * (z ? 1.0 : SQRT2));
+			T f = (T)((I)v * nf);                                                                    // :644-647
+			const T dc0 = f;
+			const bool inside = z >= b3[0] && z < e3[0] && y >= b3[1] && y < e3[1] && x >= b3[2] && x < e3[2];
+			if (!inside) { if (m[0] != 1.0) f = f * (T)m[0]; }                                       // :683-713
+			else if (m[1] != 1.0) f = f * (T)m[1];                                                   // :714-719
+			if (m[3] != 0.0) {                                                                       // :721-728
+				const T af = f < 0 ? -f : f;
+				if (af < (T)m[2] || af > (T)m[3]) f = 0;
+			}
+			if (flag && !(z | y | x)) {                                                              // :730-738
+				const bool dcstop = (b3[0] | b3[1] | b3[2]) != 0;
+				if (dcstop || m[1] != 1.0 || m[3] != 0.0) {
+					if (flag == 1) f = dc0;
+					else f = (T)((I)f + (1.0 - (dcstop ? m[0] : m[1])) * m[5]);
+				}
+			}
+			if (m[4] != 0.0) {                                                                       // :740-744
+				f = (T)(round((I)f / m[4]) * m[4]);
+				if (f != 0 && aux) {
+#if DSP_GPU
+					atomicAdd((unsigned long long *)aux, 1ull);
+#else
+					*(unsigned long long *)aux += 1ull;
+#endif
+				}
+			}
+			return (T)((I)f / nf);                                                                   // :748-751
+		}
+		case OP_MOTION_STORE: {
+			const I pel = (I)v * m[6];                                                               // :757,767
+			if (flag2) return (T)(pel / 255.0);                                                      // :773
+			return (T)(pel > 255.0 ? 255.0 : pel < 0.0 ? 0.0 : (I)lround(pel));                      // :776
 		}
 		case OP_SCAN_ACCUM: {
 			T *sum = (T *)aux + (((size_t)c.i1 * w + c.i2) * d + c.ch);

@@ -249,6 +249,7 @@ struct dsp_dct_plan_s {
 	int fuse_kind;                           // 0 none, 1 spec, 2 ispec
 	double *d_scalars;                       // acc[4] | scale_z[4] | dc_out[4]
 	unsigned char *d_signmap;
+	void *d_work;                            // T scratch the passes run in when the final store is 8-bit
 	bool need_acc;
 	rt_stream last_stream;
 	// per-pass profiling
@@ -420,7 +421,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 	if (pp.row) {
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
-		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
+		a.vec_in = pp.vec_in_layout && ain && !a.in_u8; a.vec_out = pp.vec_out_layout && aout && !a.out_u8;
 		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
@@ -446,8 +447,11 @@ static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st)
 	if (P->need_acc && !rt_zero(P->d_scalars, sizeof(double) * 4, st, g_err)) return false;
 	for (size_t i = 0; i < P->passes.size(); i++) {
 		PassPlan &pp = P->passes[i];
-		const void *in = i == 0 ? d_in : d_out;
-		DSP_TRACE("launch pass %zu in=%p out=%p", i, in, d_out);
+		// with an 8-bit final store the T-typed intermediate lives in the plan's work buffer
+		void *mid = P->d_work ? P->d_work : d_out;
+		const void *in = i == 0 ? d_in : mid;
+		void *out = (i + 1 == P->passes.size()) ? d_out : mid;
+		DSP_TRACE("launch pass %zu in=%p out=%p", i, in, out);
 #if DSP_GPU
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
 		if (P->profiling) {
@@ -455,7 +459,7 @@ static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st)
 			cudaEventRecord(e0, st);
 		}
 #endif
-		const bool ok = run_pass(P, pp, in, d_out, st);
+		const bool ok = run_pass(P, pp, in, out, st);
 		if (!ok) return false;
 #if DSP_GPU
 		if (P->profiling) {
@@ -504,6 +508,7 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->fuse_kind = 0;
 	P->d_scalars = nullptr;
 	P->d_signmap = nullptr;
+	P->d_work = nullptr;
 	P->need_acc = false;
 	P->last_stream = 0;
 	P->profiling = false;
@@ -613,6 +618,7 @@ void dsp_dct_destroy(dsp_dct_plan p) {
 	rt_free(p->d_out);
 	rt_free(p->d_scalars);
 	rt_free(p->d_signmap);
+	rt_free(p->d_work);
 #if DSP_GPU
 	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
 #endif
@@ -855,5 +861,119 @@ int dsp_scan_sum(dsp_scan s, void *sum) {
 }
 
 void dsp_scan_destroy(dsp_scan s) { scan_free(s); }
+
+// ------------------------------------------------------------------------------------------------ motion session
+struct dsp_motion_s {
+	char prec;
+	dsp_motion_params mp;
+	int minbuf[3];
+	size_t pels, pel_bytes, coeff_bytes;
+	dsp_dct_plan fwd, inv;
+	void *d_coeffs;                 // T [minbuf]: zero outside the block box for the life of the session
+	void *d_in, *d_out;             // staging for the host entry
+	unsigned long long *d_counter;
+};
+
+static void motion_free(dsp_motion_s *m) {
+	if (!m) return;
+	if (m->fwd) dsp_dct_destroy(m->fwd);
+	if (m->inv) dsp_dct_destroy(m->inv);
+	rt_free(m->d_coeffs); rt_free(m->d_in); rt_free(m->d_out); rt_free(m->d_counter);
+	delete m;
+}
+
+dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || !mp) { g_err = "bad motion arguments"; return nullptr; }
+	for (int i = 0; i < 3; i++)
+		if (mp->block[i] < 1 || mp->scaled[i] < 1) { g_err = "motion block / scaled sizes must be >= 1"; return nullptr; }
+	dsp_motion_s *m = new dsp_motion_s();
+	memset(m, 0, sizeof(*m));
+	m->prec = prec; m->mp = *mp;
+	int active[3];
+	for (int i = 0; i < 3; i++) {
+		m->minbuf[i] = mp->block[i] > mp->scaled[i] ? mp->block[i] : mp->scaled[i];       // motion.c:491-493
+		active[i] = mp->block[i] < mp->scaled[i] ? mp->block[i] : mp->scaled[i];          // motion.c:494-496
+		if (mp->bp_begin[i] < 0 || mp->bp_end[i] > active[i] || mp->bp_begin[i] > mp->bp_end[i]) { g_err = "band-pass box outside the active box"; delete m; return nullptr; }
+	}
+	const size_t es = prec == 'f' ? 4 : 8;
+	m->pels = (size_t)m->minbuf[0] * m->minbuf[1] * m->minbuf[2];
+	m->pel_bytes = m->pels * (mp->float_pixels ? 4 : 1);
+	m->coeff_bytes = m->pels * es;
+	if (mp->float_pixels && prec != 'f') { g_err = "float pels need the float build (COEFF_PRECISION=F)"; delete m; return nullptr; }
+	const int k10[3] = {DSP_DCT_REDFT10, DSP_DCT_REDFT10, DSP_DCT_REDFT10}, k01[3] = {DSP_DCT_REDFT01, DSP_DCT_REDFT01, DSP_DCT_REDFT01};
+	bool ok = rt_init(g_err) && rt_malloc(&m->d_coeffs, m->coeff_bytes, g_err) && rt_zero(m->d_coeffs, m->coeff_bytes, 0, g_err) &&
+	          rt_malloc((void **)&m->d_counter, sizeof(unsigned long long), g_err) && rt_zero(m->d_counter, sizeof(unsigned long long), 0, g_err) &&
+	          rt_sync(0, g_err);
+	if (ok) {
+		// motion.c:535-538 / :549-552: both plans address their box inside the same minbuf-sized buffer
+		m->fwd = dsp_dct_plan_many(prec, 3, mp->block, 1, nullptr, m->minbuf, 1, 0, nullptr, m->minbuf, 1, 0, k10, 0);
+		m->inv = m->fwd ? dsp_dct_plan_many(prec, 3, mp->scaled, 1, nullptr, m->minbuf, 1, 0, nullptr, m->minbuf, 1, 0, k01, 0) : nullptr;
+		ok = m->fwd && m->inv;
+	}
+	if (ok) {
+		const double sw = mp->scaled[2], sh = mp->scaled[1], sd = mp->scaled[0];
+		const double bw = mp->block[2], bh = mp->block[1], bd = mp->block[0];
+		const double scalefactor = (sw * sh * sd) / (bw * bh * bd);                        // motion.c:566
+		const double norm = 1.0 / sqrt(sw * sh * sd * 8.0);                                 // motion.c:567
+		// forward: first pass (row pass over w) reads the pels
+		PassPlan &f0 = m->fwd->passes.front();
+		if (!mp->float_pixels) f0.ra.in_u8 = 1;
+		else { f0.lop.kind = OP_SCALE; f0.lop.p[0] = 255.0; }                               // motion.c:622
+		// inverse: first pass carries every coefficient-space stage, last pass the pel store
+		PassPlan &i0 = m->inv->passes.front(), &il = m->inv->passes.back();
+		OpAny op;
+		memset(&op, 0, sizeof(op));
+		op.kind = OP_MOTION_COEFF;
+		for (int i = 0; i < 3; i++) { op.a3[i] = active[i]; op.b3[i] = mp->bp_begin[i]; op.e3[i] = mp->bp_end[i]; }
+		op.m[0] = mp->damp; op.m[1] = mp->boost;
+		op.m[2] = mp->threshold_min * 255.0 / norm / norm; op.m[3] = mp->threshold_max * 255.0 / norm / norm;   // motion.c:571-572
+		if (prec == 'f') { op.m[2] = (double)(float)op.m[2]; op.m[3] = (double)(float)op.m[3]; }
+		op.m[4] = mp->quant * 8.0 * sqrt(sw * sh * sd);                                     // motion.c:570
+		if (prec == 'f') op.m[4] = (double)(float)op.m[4];
+		op.m[5] = 127.5 / (norm * norm * scalefactor);                                      // motion.c:736
+		op.flag = mp->preserve_dc;
+		op.aux = m->d_counter;
+		i0.lop = op; i0.fused = true;
+		memset(&op, 0, sizeof(op));
+		op.kind = OP_MOTION_STORE;
+		op.m[6] = scalefactor * norm * norm;                                                // motion.c:757,767
+		op.flag2 = mp->float_pixels;
+		il.sop = op; il.fused = true;
+		if (!mp->float_pixels) {
+			il.ra.out_u8 = 1;
+			ok = rt_malloc(&m->inv->d_work, m->coeff_bytes, g_err);
+		}
+		m->inv->fuse_kind = 4;
+	}
+	if (!ok) { motion_free(m); return nullptr; }
+	return m;
+}
+
+int dsp_motion_block_dev(dsp_motion m, const void *d_pels_in, void *d_pels_out, void *stream) {
+	g_err.clear();
+	if (!m || !d_pels_in || !d_pels_out) { g_err = "null motion session or buffer"; return 1; }
+	// forward: pels -> coefficients (block box of the zero-initialised buffer); inverse: coefficients -> pels
+	if (dsp_dct_execute_dev(m->fwd, (void *)d_pels_in, m->d_coeffs, stream) != 0) return 1;
+	return dsp_dct_execute_dev(m->inv, m->d_coeffs, d_pels_out, stream);
+}
+
+int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned long long *coeffs_coded) {
+	g_err.clear();
+	if (!m || !pels_in || !pels_out) { g_err = "null motion session or buffer"; return 1; }
+	if (!m->d_in && !(rt_malloc(&m->d_in, m->pel_bytes, g_err) && rt_malloc(&m->d_out, m->pel_bytes, g_err))) return 1;
+	if (!rt_h2d(m->d_in, pels_in, m->pel_bytes, 0, g_err)) return 1;
+	// the reference writes the result over the staging block, leaving pels outside the scaled box as they were
+	if (!rt_d2d(m->d_out, m->d_in, m->pel_bytes, 0, g_err)) return 1;
+	if (!rt_zero(m->d_counter, sizeof(unsigned long long), 0, g_err)) return 1;
+	if (dsp_motion_block_dev(m, m->d_in, m->d_out, nullptr) != 0) return 1;
+	if (!rt_d2h(pels_out, m->d_out, m->pel_bytes, 0, g_err)) return 1;
+	unsigned long long cnt = 0;
+	if (!rt_d2h(&cnt, m->d_counter, sizeof(cnt), 0, g_err) || !rt_sync(0, g_err)) return 1;
+	if (coeffs_coded) *coeffs_coded += cnt;
+	return 0;
+}
+
+void dsp_motion_destroy(dsp_motion m) { motion_free(m); }
 
 }  // extern "C"

@@ -156,6 +156,33 @@ int dsp_scan_coeffs(dsp_scan s, void *coeffs);
 int dsp_scan_sum(dsp_scan s, void *sum);
 void dsp_scan_destroy(dsp_scan s);
 
+/* ---- motion: 3-D DCT -> coefficient-space filters -> 3-D inverse DCT of one plane block ----------------------
+ * (motion/motion.c:525-573 plans and constants, :617-788 per-block body; options -p/--bandpass, -D/--damp, -B/--boost,
+ * --threshold, -q/--quant, --preserve-dc, -s/--size.)  One block = the staging buffer the reference fills per
+ * (plane, spatial block, temporal block): [minbuf.d][minbuf.h][minbuf.w] pels, 8-bit or float32, with
+ * minbuf = max(block, scaled).  The forward REDFT10^3 runs over `block`, the inverse REDFT01^3 over `scaled` in the
+ * same padded box, so scaled != block resamples by spectral zero-pad / crop.  Fused: 8-bit load in the first pass
+ * of the forward transform; zero-pad/crop + normalise + band-pass + threshold + preserve-dc + quantise +
+ * de-normalise in the first pass of the inverse; scale + clamp + lround + 8-bit store in its last pass.
+ * Not covered (host-side / sequential in the reference): --coeff-limit, --eval, --dither, spectrogram in/out modes,
+ * linear-light transfer curves.  All dims are (d, h, w). */
+typedef struct {
+	int block[3], scaled[3];
+	int float_pixels;             /* 0: 8-bit pels; 1: float32 pels in [0,1] (motion.c:621-624, 773) */
+	double damp, boost;           /* 1 = off */
+	int bp_begin[3], bp_end[3];   /* band-pass box, 0 <= begin <= end <= min(block, scaled) */
+	double threshold_min, threshold_max;   /* as given on the command line; max == 0 = off */
+	double quant;                 /* 0 = off */
+	int preserve_dc;              /* 0 none, 1 dc, 2 grey */
+} dsp_motion_params;
+typedef struct dsp_motion_s *dsp_motion;
+dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp);
+/* host staging buffers (pels_out may equal pels_in); *coeffs_coded += non-zero coefficients after --quant */
+int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned long long *coeffs_coded);
+/* device-resident: same layout, device pointers, enqueued on `stream` */
+int dsp_motion_block_dev(dsp_motion m, const void *d_pels_in, void *d_pels_out, void *stream);
+void dsp_motion_destroy(dsp_motion m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,3 +162,62 @@ def scan_frames(pixels, index_map, step=1, nframes=None, fast=False):
         total = (total + image).astype(C)                                                     # :454
         frames.append(total.copy())
     return frames, coeffs
+
+
+def motion_block(pels, block, scaled=None, damp=1.0, boost=1.0, bandpass=None, threshold=(0.0, 0.0), quant=0.0,
+                 preserve_dc=None, coeff=np.float32, intermediate=np.float64, fast=True):
+    """motion/motion.c:617-788 for one plane block with spec/ispec/linear/dither/coeff-limit/eval off.
+    pels: staging block [minbuf.d][minbuf.h][minbuf.w], uint8 or float32.  Sizes are (d, h, w).
+    Returns (processed block, coefficients coded)."""
+    C, I = coeff, intermediate
+    scaled = tuple(scaled) if scaled is not None else tuple(block)
+    block = tuple(block)
+    minbuf = tuple(max(a, b) for a, b in zip(block, scaled))                                  # :491-493
+    active = tuple(min(a, b) for a, b in zip(block, scaled))                                  # :494-496
+    assert pels.shape == minbuf
+    float_pixels = pels.dtype != np.uint8
+    sf = I(scaled[0] * scaled[1] * scaled[2]) / I(block[0] * block[1] * block[2])             # :566
+    norm = 1 / np.sqrt(I(scaled[0] * scaled[1] * scaled[2] * 8))                              # :567
+    quantizer = C(quant * 8 * np.sqrt(I(scaled[0] * scaled[1] * scaled[2])))                  # :570
+    thr = (C(threshold[0] * 255 / norm / norm), C(threshold[1] * 255 / norm / norm))          # :571-572
+    bsl = tuple(slice(0, v) for v in block)
+    asl = tuple(slice(0, v) for v in active)
+    ssl = tuple(slice(0, v) for v in scaled)
+    coeffs = np.zeros(minbuf, dtype=C)                                                        # :617
+    src = pels[bsl].astype(I)
+    coeffs[bsl] = (src * 255 if float_pixels else src).astype(C)                              # :618-637
+    coeffs[bsl] = (odct.dctn_fast(coeffs[bsl], [odct.REDFT10] * 3) if fast else odct.dctn_def(coeffs[bsl], [odct.REDFT10] * 3)).astype(C)   # :641
+    z, y, x = np.meshgrid(*[np.arange(v) for v in active], indexing="ij")
+    s2 = np.sqrt(I(2))
+    nf = (2 * s2) / (np.where(x > 0, I(1), s2) * np.where(y > 0, I(1), s2) * np.where(z > 0, I(1), s2))
+    a = (coeffs[asl].astype(I) * nf).astype(C)                                                # :644-647
+    dc = a[0, 0, 0]                                                                           # :649
+    bb, be = bandpass if bandpass is not None else ((0, 0, 0), active)
+    inside = ((z >= bb[0]) & (z < be[0]) & (y >= bb[1]) & (y < be[1]) & (x >= bb[2]) & (x < be[2]))
+    if damp != 1:
+        a = np.where(inside, a, (a * C(damp)).astype(C))                                      # :683-713
+    if boost != 1:
+        a = np.where(inside, (a * C(boost)).astype(C), a)                                     # :714-719
+    if threshold[1]:
+        aa = np.abs(a)
+        a = np.where((aa < thr[0]) | (aa > thr[1]), C(0), a)                                  # :721-728
+    if preserve_dc:
+        dcstop = bool(bb[0] or bb[1] or bb[2])
+        if dcstop or boost != 1 or threshold[1]:                                              # :730-738
+            if preserve_dc == "dc":
+                a[0, 0, 0] = dc
+            else:
+                a[0, 0, 0] = C(I(a[0, 0, 0]) + (1 - (damp if dcstop else boost)) * I(127.5) / (norm * norm * sf))
+    coded = 0
+    if quant:
+        a = (np.round(a.astype(I) / quantizer) * quantizer).astype(C)                         # :740-744
+        coded = int(np.count_nonzero(a))
+    coeffs[asl] = (a.astype(I) / nf).astype(C)                                                # :748-751
+    coeffs[ssl] = (odct.dctn_fast(coeffs[ssl], [odct.REDFT01] * 3) if fast else odct.dctn_def(coeffs[ssl], [odct.REDFT01] * 3)).astype(C)   # :753
+    pel = coeffs[ssl].astype(I) * sf * norm * norm                                            # :757,767
+    out = pels.copy()
+    if float_pixels:
+        out[ssl] = (pel / 255).astype(np.float32)                                             # :773
+    else:
+        out[ssl] = np.where(pel > 255, 255, np.where(pel < 0, 0, np.floor(np.abs(pel) + 0.5) * np.sign(pel))).astype(np.uint8)   # :776 lround
+    return out, coded, pel

@@ -219,3 +219,42 @@ def check_scan(lib, prec, h, w, d, order="diagonal", step=1, seed=4):
     # scan.c:508-526: lround(orig * (2^depth - 1)) == lround(sum * (2^depth - 1))
     assert np.array_equal(np.round(f.astype(np.float64) * 255).astype(np.int64), px8)
     return worst
+
+
+# ---------------------------------------------------------------------------------------------- motion
+from dspfun_b200 import motion as gmotion       # noqa: E402
+
+
+def check_motion(lib, block, scaled=None, prec="f", float_pixels=False, seed=6, **filt):
+    """motion's per-block body on the GPU vs the restated loop (motion/motion.c:617-788).  8-bit output must be
+    bit-exact except where the reference's own unrounded pel sits on a rounding tie."""
+    rng = np.random.default_rng(seed)
+    scaled = tuple(scaled) if scaled is not None else tuple(block)
+    minbuf = tuple(max(a, b) for a, b in zip(block, scaled))
+    if float_pixels:
+        pels = (rng.integers(16, 236, minbuf) / 255.0).astype(np.float32)
+    else:
+        pels = rng.integers(16, 236, minbuf).astype(np.uint8)
+    # smooth the volume a little so that quantisation / thresholds leave something behind
+    m = gmotion.Motion(block, scaled, float_pixels=float_pixels, prec=prec, lib=lib, **filt)
+    got = m.process(pels)
+    coded = m.coeffs_coded
+    m.destroy()
+    want, coded_ref, pel = pl.motion_block(pels, block, scaled, coeff=DT[prec],
+                                           intermediate=np.float64 if prec == "f" else np.longdouble, **filt)
+    ssl = tuple(slice(0, v) for v in scaled)
+    outside = np.ones(minbuf, bool)
+    outside[ssl] = False
+    assert np.array_equal(got[outside], pels[outside]), "pels outside the scaled box must be untouched"
+    if float_pixels:
+        assert od.rel_l2(got[ssl], want[ssl]) < 1e-5
+        return 0.0
+    diff = got[ssl].astype(np.int64) != want[ssl].astype(np.int64)
+    if diff.any():
+        assert np.abs(got[ssl].astype(np.int64) - want[ssl].astype(np.int64)).max() <= 1
+        frac = np.abs(pel.astype(np.float64))
+        dist = np.abs(frac - np.floor(frac) - 0.5)
+        assert (dist[diff] < (2e-3 if prec == "f" else 1e-8)).all(), dist[diff].max()
+    if filt.get("quant"):
+        assert abs(coded - coded_ref) <= max(2, coded_ref // 500), (coded, coded_ref)
+    return float(diff.mean())

@@ -177,3 +177,30 @@ def test_scan_frames(lib, prec):
     cases.check_scan(lib, prec, 16, 12, 3, "horizontal", step=16)
     cases.check_scan(lib, prec, 32, 32, 1, "diagonal", step=3)
     cases.check_scan(lib, prec, 256, 192, 3, "diagonal", step=8)
+
+
+# ---------------------------------------------------------------------------------------------- motion (3-D, fused 8-bit I/O + filters)
+def test_motion_identity_and_filters(lib):
+    assert cases.check_motion(lib, (4, 8, 8)) == 0.0
+    assert cases.check_motion(lib, (1, 16, 24)) == 0.0
+    assert cases.check_motion(lib, (8, 12, 20), prec="d") == 0.0
+    cases.check_motion(lib, (8, 16, 16), damp=0.0, bandpass=((0, 0, 0), (4, 8, 8)))
+    cases.check_motion(lib, (8, 16, 16), boost=1.5, bandpass=((1, 2, 2), (6, 12, 12)), preserve_dc="dc")
+    cases.check_motion(lib, (4, 16, 16), damp=0.25, bandpass=((0, 1, 1), (4, 16, 16)), preserve_dc="grey")
+    cases.check_motion(lib, (4, 8, 8), quant=0.02)
+    cases.check_motion(lib, (4, 8, 8), threshold=(0.001, 0.5))
+
+
+def test_motion_resample_and_float(lib):
+    cases.check_motion(lib, (4, 8, 8), scaled=(4, 16, 16))
+    cases.check_motion(lib, (8, 16, 16), scaled=(4, 8, 12))
+    cases.check_motion(lib, (4, 10, 12), scaled=(6, 10, 9))
+    cases.check_motion(lib, (4, 8, 16), float_pixels=True)
+    cases.check_motion(lib, (4, 8, 16), scaled=(4, 12, 16), float_pixels=True, quant=0.01)
+
+
+def test_motion_config5_scaled_volume(lib):
+    """BASELINE config 4 at 1/8 linear scale per plane (Y 32x135x240, chroma 32x68x120), identity and low-pass."""
+    assert cases.check_motion(lib, (32, 135, 240)) < 1e-4
+    cases.check_motion(lib, (32, 68, 120), damp=0.0, bandpass=((0, 0, 0), (16, 34, 60)))
+    cases.check_motion(lib, (16, 128, 256))                          # power-of-two sizes: fast path
