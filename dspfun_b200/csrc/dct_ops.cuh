@@ -11,6 +11,12 @@
 #include "dct_core.cuh"
 #include <math.h>
 
+#if DSP_GPU
+#define DSP_OPANY_ATTR __device__ __noinline__
+#else
+#define DSP_OPANY_ATTR inline
+#endif
+
 namespace dsp {
 
 enum {
@@ -41,7 +47,9 @@ struct OpAny {
 	const void *aux_c;       // OP_SPEC: double[8] device scalars {scale_z[4], -, -, -, -};  OP_ISPEC: u8 signmap;  OP_SCAN_MASK: int32 index map
 	void *aux;               // OP_ACCUM_DC: double[4] accumulators;  OP_SPEC: double[4] DC out;  OP_SCAN_ACCUM: T sum buffer
 
-	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+	// Not inlined on the GPU: the unrolled passes call it per element, and dozens of inlined copies of this switch
+	// overflow the instruction cache (measured: "no instruction" became the top stall of the fused kernels).
+	template <class T> DSP_OPANY_ATTR T operator()(T v, const Coord &c) const {
 		typedef double I;
 		const I SQRT2 = 1.41421356237309504880168872420969808;
 		switch (kind) {

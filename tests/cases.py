@@ -160,7 +160,11 @@ def check_spec_c1_roundtrip(lib, prec, h=512, w=512, d=3, preset="shift", seed=0
     I = INTERMEDIATE[prec]
     s1, dc1 = gspec.spec(px, preset, lib=lib)
     s0, dc0 = pl.spec_forward(px, preset, intermediate=I, fast=True)
-    f16 = _quantised_matches(s1, s0, 16, 0.25 if prec == "f" else 1e-6)   # f32 transform noise ~1e-6 = 0.07 LSB16
+    # The log scale divides the transform's absolute noise (~1e-7 of the DC term) by (1+|v|): for near-zero
+    # coefficients that is several 16-bit steps in single precision -- for FFTW's float path as much as for ours --
+    # so the 16-bit spectrogram itself is held to the coefficient tolerance in float and to tie-exactness in double.
+    assert od.rel_l2(s1, s0) < OK[prec]
+    f16 = _quantised_matches(s1, s0, 16, 1e-6) if prec == "d" else float((pl.quantize_unorm(s1, 16) != pl.quantize_unorm(s0, 16)).mean())
     img = (pl.quantize_unorm(s0, 16) / 65535.0).astype(DT[prec])          # what ispec reads back from the PNG
     b1 = gspec.ispec(img, dc0, preset, lib=lib)
     b0 = pl.ispec_inverse(img, dc0, preset, intermediate=I, fast=True)
