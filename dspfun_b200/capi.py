@@ -26,6 +26,7 @@ SYMBOLS = [
     "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy",
+    "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
 ]
 
 
@@ -49,6 +50,12 @@ class MotionParams(ctypes.Structure):
                 ("damp", ctypes.c_double), ("boost", ctypes.c_double), ("bp_begin", ctypes.c_int * 3),
                 ("bp_end", ctypes.c_int * 3), ("threshold_min", ctypes.c_double), ("threshold_max", ctypes.c_double),
                 ("quant", ctypes.c_double), ("preserve_dc", ctypes.c_int)]
+
+
+class ZoomParams(ctypes.Structure):
+    _fields_ = [("basis", ctypes.c_int), ("xscale_num", ctypes.c_double), ("xscale_den", ctypes.c_double),
+                ("yscale_num", ctypes.c_double), ("yscale_den", ctypes.c_double), ("vx", ctypes.c_double),
+                ("vy", ctypes.c_double), ("vw", ctypes.c_int), ("vh", ctypes.c_int)]
 
 
 class IspecParams(ctypes.Structure):
@@ -109,6 +116,16 @@ def bind(path):
     lib.dsp_motion_block_dev.argtypes = [vp, vp, vp, vp]
     lib.dsp_motion_destroy.restype = None
     lib.dsp_motion_destroy.argtypes = [vp]
+    lib.dsp_zoom_create.restype = vp
+    lib.dsp_zoom_create.argtypes = [ctypes.c_char, ci, ci, vp]
+    lib.dsp_zoom_view_size.restype = ci
+    lib.dsp_zoom_view_size.argtypes = [vp, ctypes.POINTER(ZoomParams), ip, ip]
+    lib.dsp_zoom_frame.restype = ci
+    lib.dsp_zoom_frame.argtypes = [vp, ctypes.POINTER(ZoomParams), vp]
+    lib.dsp_zoom_last_path.restype = ci
+    lib.dsp_zoom_last_path.argtypes = [vp]
+    lib.dsp_zoom_destroy.restype = None
+    lib.dsp_zoom_destroy.argtypes = [vp]
     lib.dsp_dct_profile.restype = ci
     lib.dsp_dct_profile.argtypes = [vp, ci]
     lib.dsp_dct_num_passes.restype = ci

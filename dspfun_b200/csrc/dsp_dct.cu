@@ -976,4 +976,123 @@ int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned
 
 void dsp_motion_destroy(dsp_motion m) { motion_free(m); }
 
+// ------------------------------------------------------------------------------------------------ zoom session
+struct dsp_zoom_s {
+	char prec;
+	int h, w;
+	size_t es;
+	void *d_coeffs;                        // [h][w][3] REDFT10 x REDFT10 of the pixels
+	void *d_xb, *d_yb, *d_tmp, *d_out, *d_pad;
+	size_t xb_bytes, yb_bytes, tmp_bytes, out_bytes, pad_bytes;
+	int last_path;
+};
+
+static bool zoom_reserve(void **p, size_t *have, size_t need) {
+	if (*have >= need) return true;
+	rt_free(*p);
+	*p = nullptr; *have = 0;
+	if (!rt_malloc(p, need, g_err)) return false;
+	*have = need;
+	return true;
+}
+
+static void zoom_free(dsp_zoom_s *z) {
+	if (!z) return;
+	rt_free(z->d_coeffs); rt_free(z->d_xb); rt_free(z->d_yb); rt_free(z->d_tmp); rt_free(z->d_out); rt_free(z->d_pad);
+	delete z;
+}
+
+// zoom.c:37-41: scales below one sample clamp to 1/len; ncomponents = min(len, round(len * scale))
+static void zoom_axis(int len, double &num, double &den, int &ncomp) {
+	if (len * num / den < 1) { num = 1; den = len; }
+	const double r = round(len * num / den);
+	ncomp = (int)(r < len ? r : len);
+	if (ncomp < 1) ncomp = 1;
+}
+
+dsp_zoom dsp_zoom_create(char prec, int h, int w, const void *pixels) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || h < 1 || w < 1 || !pixels) { g_err = "bad zoom arguments"; return nullptr; }
+	dsp_zoom_s *z = new dsp_zoom_s();
+	memset(z, 0, sizeof(*z));
+	z->prec = prec; z->h = h; z->w = w; z->es = prec == 'f' ? 4 : 8;
+	const size_t bytes = (size_t)h * w * 3 * z->es;
+	const int n[2] = {h, w}, k10[2] = {DSP_DCT_REDFT10, DSP_DCT_REDFT10};
+	bool ok = rt_init(g_err) && rt_malloc(&z->d_coeffs, bytes, g_err) && rt_h2d(z->d_coeffs, pixels, bytes, 0, g_err);
+	dsp_dct_plan fwd = ok ? dsp_dct_plan_many(prec, 2, n, 3, z->d_coeffs, nullptr, 3, 1, z->d_coeffs, nullptr, 3, 1, k10, 0) : nullptr;   // zoom.c:263
+	ok = ok && fwd && dsp_dct_execute_dev(fwd, z->d_coeffs, z->d_coeffs, nullptr) == 0 && rt_sync(0, g_err);
+	if (fwd) dsp_dct_destroy(fwd);
+	if (!ok) { zoom_free(z); return nullptr; }
+	return z;
+}
+
+int dsp_zoom_view_size(dsp_zoom z, const dsp_zoom_params *zp, int *vw, int *vh) {
+	if (!z || !zp || !vw || !vh) return 1;
+	double xn = zp->xscale_num, xd = zp->xscale_den, yn = zp->yscale_num, yd = zp->yscale_den;
+	int cw, ch;
+	zoom_axis(z->w, xn, xd, cw); zoom_axis(z->h, yn, yd, ch);
+	*vw = zp->vw ? zp->vw : (int)(z->w * xn / xd);                                       // zoom.c:286-289
+	*vh = zp->vh ? zp->vh : (int)(z->h * yn / yd);
+	return 0;
+}
+
+int dsp_zoom_last_path(dsp_zoom z) { return z ? z->last_path : -1; }
+
+int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out) {
+	g_err.clear();
+	if (!z || !zp || !out) { g_err = "null zoom session or buffer"; return 1; }
+	double xn = zp->xscale_num, xd = zp->xscale_den, yn = zp->yscale_num, yd = zp->yscale_den;
+	int cw, ch, vw, vh;
+	zoom_axis(z->w, xn, xd, cw); zoom_axis(z->h, yn, yd, ch);
+	dsp_zoom_view_size(z, zp, &vw, &vh);
+	if (vw < 1 || vh < 1) { g_err = "empty zoom view"; return 1; }
+	const int W = z->w, H = z->h;
+	const size_t es = z->es;
+	const double inv_wh = 1.0 / ((double)W * (double)H);                                 // zoom.c:373
+	if (!zoom_reserve(&z->d_out, &z->out_bytes, (size_t)vh * vw * 3 * es)) return 1;
+
+	// ---- fast path: native basis, integer scaled size, whole image, no offset == zero-padded / cropped REDFT01
+	const double sw = W * xn / xd, sh = H * yn / yd;
+	const bool native_fft = zp->basis == 2 && zp->vx == 0 && zp->vy == 0 && sw == floor(sw) && sh == floor(sh) &&
+	                        vw == (int)sw && vh == (int)sh;
+	if (native_fft) {
+		// out[j][i] = (C00/4 + ...)/(WH) = REDFT01^2 (zero-padded or cropped C) / (4 W H)
+		const int pw = vw > W ? vw : W, ph = vh > H ? vh : H;                            // padded box holding both sub-boxes
+		const size_t pbytes = (size_t)ph * pw * 3 * es;
+		if (!zoom_reserve(&z->d_pad, &z->pad_bytes, pbytes)) return 1;
+		if (!rt_zero(z->d_pad, pbytes, 0, g_err)) return 1;
+		// copy the coefficient sub-box that survives (crop) into the padded box, row by row
+		const int cwid = W < vw ? W : vw, chei = H < vh ? H : vh;
+		for (int y = 0; y < chei; y++)
+			if (!rt_d2d((char *)z->d_pad + (size_t)y * pw * 3 * es, (char *)z->d_coeffs + (size_t)y * W * 3 * es, (size_t)cwid * 3 * es, 0, g_err)) return 1;
+		const int n[2] = {vh, vw}, emb[2] = {ph, pw}, k01[2] = {DSP_DCT_REDFT01, DSP_DCT_REDFT01};
+		dsp_dct_plan inv = dsp_dct_plan_many(z->prec, 2, n, 3, z->d_pad, emb, 3, 1, z->d_out, n, 3, 1, k01, 0);
+		if (!inv) return 1;
+		bool ok = dsp_dct_fuse_scale(inv, 1.0, inv_wh / 4.0) == 0 && dsp_dct_execute_dev(inv, z->d_pad, z->d_out, nullptr) == 0 &&
+		          rt_d2h(out, z->d_out, (size_t)vh * vw * 3 * es, 0, g_err) && rt_sync(0, g_err);
+		dsp_dct_destroy(inv);
+		z->last_path = 1;
+		return ok ? 0 : 1;
+	}
+
+	// ---- general path: scaled bases (zoom.c:347-358) and the separable synthesis (zoom.c:361-375)
+	if (!zoom_reserve(&z->d_xb, &z->xb_bytes, (size_t)vw * cw * es) || !zoom_reserve(&z->d_yb, &z->yb_bytes, (size_t)vh * ch * es) ||
+	    !zoom_reserve(&z->d_tmp, &z->tmp_bytes, (size_t)ch * vw * es))
+		return 1;
+	if (!launch_zoom_basis(z->prec, z->d_xb, vw, cw, zp->basis, xn, xd, zp->vx, W, 0, g_err)) return 1;
+	if (!launch_zoom_basis(z->prec, z->d_yb, vh, ch, zp->basis, yn, yd, zp->vy, H, 0, g_err)) return 1;
+	g_launches += 2;
+	for (int c = 0; c < 3; c++) {
+		// tmp[row][i] = sum_u C[row][u][c] * xb[i][u]      (zoom.c:363-367; xb[i][0] = 1/2)
+		if (!launch_zoom_gemm(z->prec, ch, vw, cw, (char *)z->d_coeffs + c * es, (long long)W * 3, 3, z->d_xb, 1, cw, z->d_tmp, vw, 1, 1.0, 0, g_err)) return 1;
+		// out[j][i][c] = sum_v yb[j][v] * tmp[v][i] / (W H)   (zoom.c:368-374; yb[j][0] = 1/2)
+		if (!launch_zoom_gemm(z->prec, vh, vw, ch, z->d_yb, ch, 1, z->d_tmp, vw, 1, (char *)z->d_out + c * es, (long long)vw * 3, 3, inv_wh, 0, g_err)) return 1;
+		g_launches += 2;
+	}
+	z->last_path = 0;
+	return (rt_d2h(out, z->d_out, (size_t)vh * vw * 3 * es, 0, g_err) && rt_sync(0, g_err)) ? 0 : 1;
+}
+
+void dsp_zoom_destroy(dsp_zoom z) { zoom_free(z); }
+
 }  // extern "C"

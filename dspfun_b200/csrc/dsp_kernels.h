@@ -29,4 +29,9 @@ DSP_DECL_LAUNCH(launch_col_fast_f64, ColArgs)
 
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
 
+bool launch_zoom_basis(char prec, void *basis, int nvec, int ncomp, int type, double num, double den, double offset, int len,
+                       rt_stream st, std::string &err);
+bool launch_zoom_gemm(char prec, int M, int N, int K, const void *A, long long ar, long long ac, const void *B, long long br,
+                      long long bc, void *Cm, long long cr, long long cc, double alpha, rt_stream st, std::string &err);
+
 }  // namespace dsp

@@ -183,6 +183,27 @@ int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned
 int dsp_motion_block_dev(dsp_motion m, const void *d_pels_in, void *d_pels_out, void *stream);
 void dsp_motion_destroy(dsp_motion m);
 
+/* ---- zoom: DCT-domain resampling of an RGB image (zoom/zoom.c:263-266 forward plan, :36-68 scaled basis,
+ * :361-375 synthesis).  create: REDFT10 x REDFT10 of the [h][w][3] interleaved pixels, kept on the GPU.
+ * frame: one output view.  Scale is num/den per axis; (vx, vy) the view offset in output samples; (vw, vh) the
+ * view size (0 = the whole scaled image, zoom.c:286-289).  basis: 0 interpolated (default), 1 centered, 2 native.
+ * A native basis with integer scaled size and zero offset is a spectral zero-pad / crop and runs as one inverse
+ * DCT; every other case runs the reference's separable cosine synthesis as dense contractions.
+ * out: host buffer [vh][vw][3] of the coefficient type, the values zoom hands to ffapi_setpelf (zoom.c:393-400). */
+typedef struct {
+	int basis;
+	double xscale_num, xscale_den, yscale_num, yscale_den;
+	double vx, vy;
+	int vw, vh;
+} dsp_zoom_params;
+typedef struct dsp_zoom_s *dsp_zoom;
+dsp_zoom dsp_zoom_create(char prec, int h, int w, const void *pixels);
+int dsp_zoom_view_size(dsp_zoom z, const dsp_zoom_params *zp, int *vw, int *vh);
+int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out);
+/* which path the last frame took: 1 = inverse-DCT fast path, 0 = dense synthesis */
+int dsp_zoom_last_path(dsp_zoom z);
+void dsp_zoom_destroy(dsp_zoom z);
+
 #ifdef __cplusplus
 }
 #endif

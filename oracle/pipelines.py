@@ -221,3 +221,48 @@ def motion_block(pels, block, scaled=None, damp=1.0, boost=1.0, bandpass=None, t
     else:
         out[ssl] = np.where(pel > 255, 255, np.where(pel < 0, 0, np.floor(np.abs(pel) + 0.5) * np.sign(pel))).astype(np.uint8)   # :776 lround
     return out, coded, pel
+
+
+def zoom_basis(scaling_type, num, den, offset, nvectors, sampling_len, coeff=np.float64, intermediate=np.longdouble):
+    """zoom/zoom.c:36-68 generate_scaled_basis.  Returns (basis[nvectors][ncomponents-1] in coeff precision, ncomponents)."""
+    I = intermediate
+    num, den, offset = I(num), I(den), I(offset)
+    if sampling_len * num / den < 1:                                                          # :37-40
+        num, den = I(1), I(sampling_len)
+    ncomp = int(min(sampling_len, np.round(sampling_len * num / den)))                        # :41
+    b = np.arange(nvectors, dtype=I)[:, None]
+    n = np.arange(1, ncomp, dtype=I)[None, :]
+    if scaling_type == "native":                                                              # :50-53
+        k, N = b + offset, sampling_len * num / den
+    elif scaling_type == "interpolated":                                                      # :54-57
+        k, N = (b + offset) * den / num, I(sampling_len)
+    else:                                                                                     # :58-61 centered
+        k, N = (b + offset) * (sampling_len - 1) * den / (sampling_len * num - den), I(sampling_len)
+    pi = I(np.pi) if I is not np.longdouble else np.longdouble("3.14159265358979323846264338327950288")
+    return np.cos(pi * (k + I(0.5)) * n / N).astype(coeff), ncomp                             # :63
+
+
+def zoom_synthesise(pixels, scale=(1, 1), basis="interpolated", pos=(0.0, 0.0), view=(0, 0), xscale=None, yscale=None,
+                    intermediate=np.longdouble, fast=True):
+    """zoom/zoom.c:263-266 (forward), :268-289 (scale / view), :347-358 (bases), :361-375 (synthesis), one frame."""
+    C, I = pixels.dtype.type, intermediate
+    H, W, _ = pixels.shape
+    coeffs = _transform(np.ascontiguousarray(pixels), [odct.REDFT10, odct.REDFT10], fast)     # :263-265
+    xn, xd = (xscale if xscale is not None else scale)
+    yn, yd = (yscale if yscale is not None else scale)
+    xn, xd, yn, yd = I(xn), I(xd), I(yn), I(yd)
+    if W * xn / xd < 1:
+        xn, xd = I(1), I(W)                                                                   # :277-280
+    if H * yn / yd < 1:
+        yn, yd = I(1), I(H)                                                                   # :281-284
+    vw = view[0] or int(W * xn / xd)                                                          # :286-289
+    vh = view[1] or int(H * yn / yd)
+    xb, cw = zoom_basis(basis, xn, xd, pos[0], vw, W, C, I)                                   # :348
+    yb, ch = zoom_basis(basis, yn, yd, pos[1], vh, H, C, I)                                   # :356
+    out = np.empty((vh, vw, 3), dtype=C)
+    for z in range(3):                                                                        # :361-375
+        cz = coeffs[:ch, :cw, z].astype(I)
+        tmp = cz[:, 0:1] / 2 + cz[:, 1:] @ xb.astype(I).T                                     # tmp[row] per output column i
+        s = tmp[0:1, :] / 2 + yb.astype(I) @ tmp[1:, :]
+        out[:, :, z] = (s / (W * H)).astype(C)
+    return out

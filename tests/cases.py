@@ -262,3 +262,26 @@ def check_motion(lib, block, scaled=None, prec="f", float_pixels=False, seed=6, 
     if filt.get("quant"):
         assert abs(coded - coded_ref) <= max(2, coded_ref // 500), (coded, coded_ref)
     return float(diff.mean())
+
+
+# ---------------------------------------------------------------------------------------------- zoom
+from dspfun_b200 import zoom as gzoom           # noqa: E402
+
+
+def check_zoom(lib, prec, h, w, seed=8, **kw):
+    """zoom's scaled-basis synthesis (zoom/zoom.c:36-68, 361-375) on the GPU vs the restated loops."""
+    rng = np.random.default_rng(seed)
+    px = (rng.integers(0, 256, (h, w, 3)) / 255.0).astype(DT[prec])
+    z = gzoom.Zoom(px, lib=lib)
+    got = z.frame(**kw)
+    path = z.last_path
+    z.destroy()
+    okw = dict(kw)
+    for k in ("scale", "xscale", "yscale"):
+        if k in okw and not isinstance(okw[k], (tuple, list)):
+            okw[k] = (okw[k], 1)
+    want = pl.zoom_synthesise(px, intermediate=np.longdouble, **okw)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = od.rel_l2(got, want)
+    assert err < OK[prec], (kw, err)
+    return path, got, want

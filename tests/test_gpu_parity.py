@@ -204,3 +204,38 @@ def test_motion_config5_scaled_volume(lib):
     assert cases.check_motion(lib, (32, 135, 240)) < 1e-4
     cases.check_motion(lib, (32, 68, 120), damp=0.0, bandpass=((0, 0, 0), (16, 34, 60)))
     cases.check_motion(lib, (16, 128, 256))                          # power-of-two sizes: fast path
+
+
+# ---------------------------------------------------------------------------------------------- zoom
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_zoom_bases(lib, prec):
+    assert cases.check_zoom(lib, prec, 16, 24, scale=2)[0] == "dense"
+    cases.check_zoom(lib, prec, 12, 20, scale=(3, 2))
+    cases.check_zoom(lib, prec, 16, 24, scale=2, pos=(3.5, 1.25), view=(20, 12))
+    assert cases.check_zoom(lib, prec, 16, 24, scale=2, basis="native")[0] == "inverse-dct"
+    assert cases.check_zoom(lib, prec, 16, 24, scale=(1, 2), basis="native")[0] == "inverse-dct"
+    cases.check_zoom(lib, prec, 12, 16, scale=2, basis="centered")
+    cases.check_zoom(lib, prec, 128, 192, scale=2)
+    cases.check_zoom(lib, prec, 256, 256, scale=2, basis="native")
+
+
+def test_zoom_config2_spot_check(lib):
+    """BASELINE config 1 geometry at 1/4 linear size (1024^2 RGB -> 2048^2, float, default interpolated basis): 48 random
+    output samples against the synthesis sum evaluated directly in float64, plus the even-sample identity."""
+    from dspfun_b200 import zoom as gzoom
+    rng = np.random.default_rng(1)
+    n = 1024
+    px = (rng.integers(0, 256, (n, n, 3)) / 255.0).astype(np.float32)
+    z = gzoom.Zoom(px)
+    out = z.frame(scale=2)
+    z.destroy()
+    assert out.shape == (2 * n, 2 * n, 3)
+    assert np.abs(out[::2, ::2] - px).max() < 2e-5          # interpolated basis: even outputs are the input samples
+    C = od.dctn_fast(px.astype(np.float64), [od.REDFT10] * 2, axes=(0, 1))
+    u = np.arange(n)
+    for _ in range(48):
+        j, i, c = int(rng.integers(0, 2 * n)), int(rng.integers(0, 2 * n)), int(rng.integers(0, 3))
+        xb = np.cos(np.pi * (i / 2 + 0.5) * u / n); xb[0] = 0.5
+        yb = np.cos(np.pi * (j / 2 + 0.5) * u / n); yb[0] = 0.5
+        want = yb @ C[:, :, c] @ xb / (n * n)
+        assert abs(out[j, i, c] - want) < 2e-5, (j, i, c, out[j, i, c], want)
