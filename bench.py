@@ -36,6 +36,9 @@ WORKLOADS = {
     "spec512": (512, 512, 3, 64, "f"),
     "plane4096x3": (4096, 4096, 3, 2, "f"),
 }
+# motion -b 0x0x0 on the luma plane of BASELINE config 4 (1920x1080x256): ONE volume sharded by frame slabs over
+# the ranks (strong scaling), NCCL all-to-all transpose around the temporal transform
+MOTION3D = (256, 1080, 1920)
 
 
 def peaks():
@@ -114,7 +117,104 @@ def cpu_roundtrip(h, w, d, prec, reps, nplanes=1):
     return nplanes * h * w * d / best / 1e9, cores, best
 
 
+def run_motion3d(args):
+    """3-D DCT-II + DCT-III round trip of one 256x1080x1920 float volume, frame slabs over the ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dspfun_b200 import capi
+    from dspfun_b200.dist3d import Dist3D
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.load()
+    D, H, W = MOTION3D
+    d3 = Dist3D(D, H, W, "f")
+    g = torch.Generator(device="cuda").manual_seed(3 + rank)
+    slab = torch.rand((D // world, H, W), device="cuda", dtype=torch.float32, generator=g)
+    ref = slab[0].clone()
+    scale = 1.0 / (8.0 * D * H * W)
+
+    def step(x):
+        c = d3.forward(x)
+        y = d3.inverse(c)
+        y.mul_(scale)            # keeps the round trip an identity across steps
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x = slab
+    for _ in range(args.warmup):
+        x = step(x)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.dsp_dct_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        x = step(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.dsp_dct_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    err = (torch.linalg.norm((x[0] - ref).double()) / torch.linalg.norm(ref.double())).item()
+    samples = D * H * W
+    value = samples * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    # end to end: pinned host slab -> device -> forward + inverse -> host
+    hbuf = torch.empty(slab.shape, dtype=torch.float32).pin_memory()
+    hbuf.copy_(slab)
+    barrier()
+    t0 = time.perf_counter()
+    ks = 2
+    for _ in range(ks):
+        dev = hbuf.to("cuda", non_blocking=True)
+        out = step(dev)
+        hbuf.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    dt = (time.perf_counter() - t0) / ks
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "motion3d", "shape": [D, H, W], "bytes_total": samples * 4,
+                       "l2_policy": "inputs larger than L2 (%.0f MB per GPU)" % (samples * 4 / world / 1e6),
+                       "parallelism": "frame slabs; all-to-all transpose around the temporal transform" if world > 1 else "single GPU, one rank-3 plan"},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": (16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9) / peak,
+                         "traffic": None, "peak_source": peak_src},
+            "cpu_baseline": None,
+            "e2e": {"value": samples / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": samples * 4 // world,
+                    "d2h_bytes_per_step": samples * 4 // world, "steps": ks, "ms_per_step": dt * 1e3},
+            "gpu_launches": launches, "clocks": clocks, "roundtrip_rel_l2": err,
+            "nvlink_bytes_per_gpu_per_step": d3.a2a_bytes // max(1, args.steps + args.warmup + ks),
+        }))
+    d3.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
+    if args.workload == "motion3d":
+        return run_reference_motion3d(args)
     h, w, d, planes, prec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,13 +247,39 @@ def run_reference(args):
     }))
 
 
+def run_reference_motion3d(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    from oracle import dct as od
+    D, H, W = MOTION3D
+    Ds = 32                                               # bounded sample: 1/8 of the frames
+    cores = os.cpu_count() or 1
+    x = np.random.default_rng(0).random((Ds, H, W)).astype(np.float32)
+    steps = min(args.steps, 3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = od.dctn_fast(x, [od.REDFT10] * 3, workers=cores)
+        od.dctn_fast(y, [od.REDFT01] * 3, workers=cores)
+    dt = (time.perf_counter() - t0) / steps
+    val = Ds * H * W / dt / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "motion3d", "shape": [D, H, W]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%dx%dx%d of the volume per step, scipy pocketfft workers=%d (FFTW not in image)" % (Ds, H, W, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="plane8192", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="plane8192", choices=sorted(WORKLOADS) + ["motion3d"])
     ap.add_argument("--planes", type=int, default=0, help="planes/images per GPU (0 = workload default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -162,6 +288,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "motion3d":
+        return run_motion3d(args)
 
     import numpy as np
     import torch

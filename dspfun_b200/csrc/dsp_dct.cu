@@ -327,7 +327,10 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		memset(&pp.lop, 0, sizeof(pp.lop)); memset(&pp.sop, 0, sizeof(pp.sop));
 		pp.fused = false;
 		pp.axis = ax;
-		pp.row = ax == r - 1;
+		// the contiguous-axis (row) kernel keeps all d interleaved sequences of a line on chip; a wide interleave
+		// (e.g. a temporal transform over [D][H*W] with stride H*W) is a strided axis over d contiguous columns instead
+		const bool wide = d > 4;
+		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
 		memset(&pp.ff, 0, sizeof(pp.ff));
 		if (pp.fast) fill_fast(pp.ff, t);
@@ -375,15 +378,18 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			ColArgs &A = pp.ca;
 			fill_fft(A.f, t);
 			A.kind = P->kind[ax];
-			A.ncols = P->n[r - 1] * d;
+			const bool lastax = ax == r - 1;                   // only with a wide interleave: the columns are the d channels
+			A.ncols = lastax ? d : P->n[r - 1] * d;
 			A.d = d; A.dd = mk_fd((uint32_t)d);
+
 			A.ax_is = sIn[ax]; A.ax_os = sO[ax];
 			if (A.ax_is % VN) vin = false;
 			if (A.ax_os % VN) vout = false;
 			long long no = 1;
 			for (auto &l : lv) { no *= l.cnt; if (l.cnt > 1 && (l.is % VN)) vin = false; if (l.cnt > 1 && (l.os % VN)) vout = false; }
 			if (!set_outer(A.o, lv)) return false;
-			A.ax_slot = ax + 3 - r; A.col_slot = 2;
+			A.ax_slot = ax + 3 - r; A.col_slot = lastax ? 3 : 2;
+			if (lastax) { A.d = 1; A.dd = mk_fd(1); }          // column index == channel index
 			// columns per CTA: as wide as fits ~64 KB (wider rows of the tile = longer contiguous global segments)
 			const int cand[] = {8 * VN, 4 * VN, 2 * VN, VN};
 			int tc = 0;

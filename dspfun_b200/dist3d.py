@@ -1,0 +1,108 @@
+"""dist3d -- motion's full-volume 3-D DCT (`motion -b 0x0x0`, /root/reference/motion/motion.c:525-554, 641, 753)
+sharded over the GPUs of one node: one process per GPU, torch.distributed (NCCL over NVLink) for the exchange.
+
+Decomposition: rank r owns frames [r D/G, (r+1) D/G) of the [D][H][W] volume.
+  forward : (1) 2-D REDFT10 over (h, w) of every local frame        -- one batched plan, no communication
+            (2) all-to-all: rank r now owns every frame of the flattened spatial positions [r HW/G, (r+1) HW/G)
+            (3) 1-D REDFT10 of length D along time over those positions -- strided-axis (column) kernel
+  inverse : (3) (2) (1) mirrored with REDFT01.
+The flattened h*w index is partitioned (not rows), so chroma planes whose height does not divide by G still shard.
+With G = 1 the same object runs one rank-3 plan.  The reference has no distributed path; its single buffer
+(`coeffs`, motion.c:500) is what the slabs partition.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .plan import Plan
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+class Dist3D:
+    def __init__(self, D, H, W, prec="f", group=None, lib=None):
+        self.D, self.H, self.W = int(D), int(H), int(W)
+        self.prec = prec
+        self.tdt = torch.float32 if prec == "f" else torch.float64
+        self.group = group
+        self.G = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.G > 1 else 0
+        G = self.G
+        if self.D % G or (self.H * self.W) % G:
+            raise ValueError("frames (%d) and h*w (%d) must divide by the number of ranks (%d)" % (D, H * W, G))
+        self.Dl, self.Pl = self.D // G, (self.H * self.W) // G
+        kw = dict(lib=lib)
+        if G == 1:
+            self.fwd3 = Plan(prec, [D, H, W], [capi.REDFT10] * 3, **kw)
+            self.inv3 = Plan(prec, [D, H, W], [capi.REDFT01] * 3, **kw)
+        else:
+            hw = self.H * self.W
+            self.fwd2 = Plan(prec, [H, W], [capi.REDFT10] * 2, 1, None, 1, 0, None, 1, 0, self.Dl, hw, hw, **kw)
+            self.inv2 = Plan(prec, [H, W], [capi.REDFT01] * 2, 1, None, 1, 0, None, 1, 0, self.Dl, hw, hw, **kw)
+            # time axis of a [D][Pl] array: stride Pl, Pl adjacent columns
+            self.fwdt = Plan(prec, [D], [capi.REDFT10], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
+            self.invt = Plan(prec, [D], [capi.REDFT01], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
+        self.a2a_bytes = 0
+
+    # -- exchange ------------------------------------------------------------------------------------------------
+    def _all_to_all(self, out, inp):
+        """out[g] <- rank g's inp[self.rank]; inp/out are [G][...] contiguous."""
+        try:
+            dist.all_to_all_single(out, inp, group=self.group)
+        except (RuntimeError, NotImplementedError):
+            # gloo (CPU test suite) has no all_to_all: pairwise exchange
+            reqs = []
+            out[self.rank].copy_(inp[self.rank])
+            for g in range(self.G):
+                if g != self.rank:
+                    reqs.append(dist.isend(inp[g].contiguous(), g, group=self.group))
+                    reqs.append(dist.irecv(out[g], g, group=self.group))
+            for r in reqs:
+                r.wait()
+        self.a2a_bytes += inp.numel() * inp.element_size() * (self.G - 1) // self.G
+
+    def _stream(self, t):
+        return torch.cuda.current_stream().cuda_stream if t.is_cuda else None
+
+    # -- transforms ------------------------------------------------------------------------------------------------
+    def forward(self, slab):
+        """slab: [D/G][H][W] local frames (modified in place as scratch).  Returns the coefficients this rank owns:
+        G == 1: [D][H][W];  G > 1: [D][HW/G] -- all temporal frequencies of its slice of flattened (h, w)."""
+        assert slab.dtype == self.tdt and slab.is_contiguous()
+        st = self._stream(slab)
+        if self.G == 1:
+            self.fwd3.execute_dev(_ptr(slab), _ptr(slab), st)
+            return slab
+        G, Dl, Pl = self.G, self.Dl, self.Pl
+        self.fwd2.execute_dev(_ptr(slab), _ptr(slab), st)
+        send = slab.view(Dl, G, Pl).permute(1, 0, 2).contiguous()          # [G][Dl][Pl]
+        recv = torch.empty_like(send)
+        self._all_to_all(recv, send)
+        cols = recv.view(self.D, Pl)                                        # frames in global order
+        self.fwdt.execute_dev(_ptr(cols), _ptr(cols), st)
+        return cols
+
+    def inverse(self, coeffs):
+        """Inverse of forward() (unnormalised: returns 8 D H W times the original)."""
+        assert coeffs.dtype == self.tdt and coeffs.is_contiguous()
+        st = self._stream(coeffs)
+        if self.G == 1:
+            self.inv3.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
+            return coeffs
+        G, Dl, Pl = self.G, self.Dl, self.Pl
+        self.invt.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
+        send = coeffs.view(G, Dl, Pl)                                       # chunk g = frames of rank g
+        recv = torch.empty_like(send)
+        self._all_to_all(recv, send.contiguous())
+        slab = recv.permute(1, 0, 2).contiguous().view(Dl, self.H, self.W)
+        self.inv2.execute_dev(_ptr(slab), _ptr(slab), st)
+        return slab
+
+    def destroy(self):
+        for n in ("fwd3", "inv3", "fwd2", "inv2", "fwdt", "invt"):
+            p = getattr(self, n, None)
+            if p is not None:
+                p.destroy()

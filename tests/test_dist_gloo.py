@@ -1,0 +1,70 @@
+"""CPU suite, world_size 2 over gloo: the slab-sharded 3-D transform's host logic (partitioning, all-to-all order,
+plan geometry) with the emulated kernels, and the batched-images sharding used by bench.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dct as od
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, D, H, W, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dspfun_b200.dist3d import Dist3D
+        from tests.emu import emu
+        lib = emu.load()
+        rng = np.random.default_rng(7)
+        vol = rng.random((D, H, W)).astype(np.float64)
+        d3 = Dist3D(D, H, W, prec="d", lib=lib)
+        Dl, Pl = D // world, H * W // world
+        slab = torch.from_numpy(vol[rank * Dl:(rank + 1) * Dl].copy())
+        cols = d3.forward(slab)
+        ref = od.dctn_fast(vol, [od.REDFT10] * 3).reshape(D, H * W)[:, rank * Pl:(rank + 1) * Pl]
+        e_fwd = od.rel_l2(cols.numpy(), ref)
+        back = d3.inverse(cols.clone()) / (8.0 * D * H * W)
+        e_inv = od.rel_l2(back.numpy(), vol[rank * Dl:(rank + 1) * Dl])
+        d3.destroy()
+        q.put((rank, e_fwd, e_inv, d3.a2a_bytes))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(8, 6, 10), (16, 9, 16), (4, 27, 30)])
+def test_slab_sharded_3d_world2(shape):
+    D, H, W = shape
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, D, H, W, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e_fwd, e_inv, nbytes in res:
+        assert e_fwd < 1e-12 and e_inv < 1e-12, (rank, e_fwd, e_inv)
+        assert nbytes == 2 * (D // 2) * (H * W) * 8 // 2          # two exchanges, half the local slab leaves each time
+
+
+def test_single_rank_uses_one_rank3_plan():
+    from dspfun_b200.dist3d import Dist3D
+    from tests.emu import emu
+    rng = np.random.default_rng(3)
+    vol = rng.random((4, 6, 8))
+    d3 = Dist3D(4, 6, 8, prec="d", lib=emu.load())
+    out = d3.forward(torch.from_numpy(vol.copy()))
+    assert od.rel_l2(out.numpy(), od.dctn_fast(vol, [od.REDFT10] * 3)) < 1e-12
+    d3.destroy()
