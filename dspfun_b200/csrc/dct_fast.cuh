@@ -157,6 +157,32 @@ template <class T> struct OmConst {
 template <class T> DSP_DEV C2<T> om_plus(C2<T> wi, C2<T> e) { return C2<T>{wi.x * e.x - wi.y * e.y, wi.y * e.x + wi.x * e.y}; }   // angle(i) + angle(e)
 template <class T> DSP_DEV C2<T> om_minus(C2<T> wi, C2<T> e) { return C2<T>{e.x * wi.x + e.y * wi.y, e.y * wi.x - e.x * wi.y}; }  // angle(e) - angle(i)
 
+// ------------------------------------------------------------------------------------------------ butterfly storage
+// Where the outer pass finds (DCT-II) or leaves (DCT-III) element j of butterfly i.
+// SmemBf: slot Pad(i) + Pad(j M) of a sequence in shared memory.
+template <class T> struct SmemBf {
+	C2<T> *base;
+	const int *poff;             // Pad(j * M), j < 16
+	struct Row {
+		C2<T> *p; const int *poff;
+		DSP_DEVM C2<T> get(int j) const { return p[poff[j]]; }
+		DSP_DEVM void put(int j, C2<T> v) const { p[poff[j]] = v; }
+	};
+	DSP_DEVM Row row(int i) const { return Row{base + Pad<T>::of(i), poff}; }
+};
+// GlobBf: row (j M + i) of a [16 M][...] global scratch, one complex (= one column pair) per row
+template <class T> struct GlobBf {
+	C2<T> *base;                 // scratch + column pair
+	long long rs;                // row stride in complex elements
+	int M;
+	struct Row {
+		C2<T> *p; long long js;
+		DSP_DEVM C2<T> get(int j) const { return p[j * js]; }
+		DSP_DEVM void put(int j, C2<T> v) const { p[j * js] = v; }
+	};
+	DSP_DEVM Row row(int i) const { return Row{base + (long long)i * rs, (long long)M * rs}; }
+};
+
 // ------------------------------------------------------------------------------------------------ DCT-II outer pass
 // pair (k, n-k), k <= n/2: Z = spectrum value at k, Y at n-k, w = (cos, sin)(pi k / 2n).
 template <class T, class Sink>
@@ -166,15 +192,15 @@ DSP_DEV void dct2_pair(C2<T> w, int k, int n, C2<T> z, C2<T> y, bool self, Sink 
 	if (!self) sink.put(n - k, w.y * ar - w.x * ai, w.y * br - w.x * bi);
 }
 
-template <class T, class Sink>
-DSP_DEV void dct2_outer_unit(C2<T> *base, const FastDesc &f, int i, Sink &sink) {
-	const int n = f.n, M = f.M, q = f.nmid;
+template <class T, class Bf, class Sink>
+DSP_DEV void dct2_outer_unit(const Bf &bf, const FastDesc &f, int i, Sink &sink) {
+	const int n = f.n, M = f.M;
 	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
-		const C2<T> *p = base;
+		const typename Bf::Row p = bf.row(0);
 #pragma unroll
-		for (int j = 0; j < 16; j++) a[j] = p[f.poff[q][j]];
+		for (int j = 0; j < 16; j++) a[j] = p.get(j);
 		Dft<T, 16>::run(a);                                       // a[m] = Z[M m]
 		dct2_pair<T>(OmConst<T>::e(0), 0, n, a[0], a[0], true, sink);
 #pragma unroll
@@ -184,9 +210,9 @@ DSP_DEV void dct2_outer_unit(C2<T> *base, const FastDesc &f, int i, Sink &sink) 
 	}
 	tw_powers<T>(tw, i, w);
 	if (2 * i == M) {
-		const C2<T> *p = base + Pad<T>::of(i);
+		const typename Bf::Row p = bf.row(i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) a[j] = p[f.poff[q][j]];
+		for (int j = 0; j < 16; j++) a[j] = p.get(j);
 #pragma unroll
 		for (int j = 1; j < 16; j++) a[j] = cmul(a[j], w[j]);
 		Dft<T, 16>::run(a);                                       // a[m] = Z[M/2 + M m]; partner of m is 15-m
@@ -197,14 +223,14 @@ DSP_DEV void dct2_outer_unit(C2<T> *base, const FastDesc &f, int i, Sink &sink) 
 	const C2<T> wi = ldg_c2(om + i);
 	C2<T> b[16];
 	{
-		const C2<T> *p = base + Pad<T>::of(i);
+		const typename Bf::Row p = bf.row(i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) a[j] = p[f.poff[q][j]];
+		for (int j = 0; j < 16; j++) a[j] = p.get(j);
 	}
 	{
-		const C2<T> *p = base + Pad<T>::of(M - i);
+		const typename Bf::Row p = bf.row(M - i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) b[j] = p[f.poff[q][j]];
+		for (int j = 0; j < 16; j++) b[j] = p.get(j);
 	}
 #pragma unroll
 	for (int j = 1; j < 16; j++) { a[j] = cmul(a[j], w[j]); b[j] = cmul_conj(b[j], w[j]); }
@@ -227,9 +253,9 @@ DSP_DEV void dct3_pair(C2<T> w, C2<T> xk, C2<T> xn, C2<T> &wk, C2<T> &wn) {
 	wn = C2<T>{pa + qb, -(pb - qa)};
 }
 
-template <class T, class Source>
-DSP_DEV void dct3_outer_unit(C2<T> *base, const FastDesc &f, int i, Source &src) {
-	const int M = f.M, q = f.nmid;
+template <class T, class Bf, class Source>
+DSP_DEV void dct3_outer_unit(const Bf &bf, const FastDesc &f, int i, Source &src) {
+	const int M = f.M;
 	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
@@ -242,9 +268,9 @@ DSP_DEV void dct3_outer_unit(C2<T> *base, const FastDesc &f, int i, Source &src)
 		for (int j = 1; j < 8; j++) dct3_pair<T>(OmConst<T>::e(j), x[j], x[16 - j], a[j], a[16 - j]);
 		{ C2<T> dummy; dct3_pair<T>(OmConst<T>::e(8), x[8], x[8], a[8], dummy); }
 		Dft<T, 16>::run(a);
-		C2<T> *p = base;
+		const typename Bf::Row p = bf.row(0);
 #pragma unroll
-		for (int j = 0; j < 16; j++) p[f.poff[q][j]] = a[j];
+		for (int j = 0; j < 16; j++) p.put(j, a[j]);
 		return;
 	}
 	if (2 * i == M) {
@@ -257,9 +283,9 @@ DSP_DEV void dct3_outer_unit(C2<T> *base, const FastDesc &f, int i, Source &src)
 		tw_powers<T>(tw, i, w);
 #pragma unroll
 		for (int j = 1; j < 16; j++) a[j] = cmul(a[j], w[j]);
-		C2<T> *p = base + Pad<T>::of(i);
+		const typename Bf::Row p = bf.row(i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) p[f.poff[q][j]] = a[j];
+		for (int j = 0; j < 16; j++) p.put(j, a[j]);
 		return;
 	}
 	const C2<T> wi = ldg_c2(om + i);
@@ -282,14 +308,14 @@ DSP_DEV void dct3_outer_unit(C2<T> *base, const FastDesc &f, int i, Source &src)
 #pragma unroll
 	for (int j = 1; j < 16; j++) { a[j] = cmul(a[j], w[j]); b[j] = cmul_conj(b[j], w[j]); }
 	{
-		C2<T> *p = base + Pad<T>::of(i);
+		const typename Bf::Row p = bf.row(i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) p[f.poff[q][j]] = a[j];
+		for (int j = 0; j < 16; j++) p.put(j, a[j]);
 	}
 	{
-		C2<T> *p = base + Pad<T>::of(M - i);
+		const typename Bf::Row p = bf.row(M - i);
 #pragma unroll
-		for (int j = 0; j < 16; j++) p[f.poff[q][j]] = b[j];
+		for (int j = 0; j < 16; j++) p.put(j, b[j]);
 	}
 }
 
@@ -546,7 +572,7 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 				sink.ca.ch = ch; sink.cb.ch = ch;
 				sink.pa = gout + oa + ch; sink.pb = hasb ? gout + ob + ch : (T *)0;
 				sink.d = d; sink.ax_slot = a.ax_slot; sink.op = &sop;
-				dct2_outer_unit<T>(s + seq * f.npad, f, i, sink);
+				dct2_outer_unit<T>(SmemBf<T>{s + seq * f.npad, f.poff[f.nmid]}, f, i, sink);
 			}
 		}
 		return;
@@ -568,7 +594,7 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 			src.ca.ch = ch; src.cb.ch = ch;
 			src.pa = (T *)gin + ia + ch; src.pb = hasb ? (T *)gin + ib + ch : (T *)0;
 			src.d = d; src.ax_slot = a.ax_slot; src.op = &lop;
-			dct3_outer_unit<T>(s + seq * f.npad, f, i, src);
+			dct3_outer_unit<T>(SmemBf<T>{s + seq * f.npad, f.poff[f.nmid]}, f, i, src);
 		}
 	}
 	DSP_SYNC();
@@ -689,12 +715,74 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 	}
 }
 
+// Lean tile move for the common case -- float, full 16-byte groups, a power-of-two number of groups per row that
+// divides the thread count, and a pointwise stage that ignores coordinates (OpMul): each thread keeps one column
+// group and walks down the rows, so the only per-row work is the row / slot mapping.
+//   rowmap(r)  -> global row of tile row r      slotmap(r) -> padded smem slot of tile row r
+template <class T, bool IN, class Op, class RowMap, class SlotMap>
+DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int lg, const Op &op, bool negim, const RowMap &rowmap,
+                            const SlotMap &slotmap, int npad, int tid, int nthr, C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	const int UNR = 8;
+	const int cg = tid & ((1 << lg) - 1), dr = nthr >> lg;
+	C2<T> *sq = s + (2 * cg) * npad;
+	const T *gp = gin + 4 * cg;
+	T *gq = gout + 4 * cg;
+	const Coord cz = {0, 0, 0, 0, 0};
+	for (int r0 = tid >> lg; r0 < nrows; r0 += dr * UNR) {
+		Vec v[UNR];
+		if (IN) {
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int r = r0 + u * dr;
+				if (r < nrows) v[u] = ldg_stream((const Vec *)(gp + (long long)rowmap(r) * rs));
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int r = r0 + u * dr;
+			if (r < nrows) {
+				const int slot = slotmap(r);
+				if (IN) {
+					sq[slot] = C2<T>{op(v[u].v[0], cz), op(v[u].v[1], cz)};
+					sq[npad + slot] = C2<T>{op(v[u].v[2], cz), op(v[u].v[3], cz)};
+				} else {
+					const C2<T> z0 = sq[slot], z1 = sq[npad + slot];
+					Vec o;
+					o.v[0] = op(z0.x, cz); o.v[1] = op(negim ? -z0.y : z0.y, cz);
+					o.v[2] = op(z1.x, cz); o.v[3] = op(negim ? -z1.y : z1.y, cz);
+					*(Vec *)(gq + (long long)rowmap(r) * rs) = o;
+				}
+			}
+		}
+	}
+}
+struct RowIdent { DSP_DEVM int operator()(int r) const { return r; } };
+template <class T> struct SlotNat { DSP_DEVM int operator()(int r) const { return Pad<T>::of(r); } };
+struct SlotSigMakhoul {                                       // DCT-II input / DCT-III output of a whole axis
+	const uint16_t *sig; int n;
+	DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + makhoul(r, n)); }
+};
+DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
+	const int gpr = tc / 4;
+	return aligned && ncl == tc && (tc % 4) == 0 && (gpr & (gpr - 1)) == 0 && (nthr % gpr) == 0;
+}
+
 // picks the access width: full 16-byte groups when the tile allows it, else 8-byte (float) pairs, else scalar
 template <class T, bool IN, class Op>
 DSP_DEV void col_move_any(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
                           long long gbase, const Coord &cbase, int tid, int nthr, C2<T> *s) {
 	const int VN = VecOf<T>::N;
 	const bool al = IN ? a.vec_in : a.vec_out;
+	if (sizeof(T) == 4 && !Op::kNeedsCoord && lean_ok(ncl, a.tc, nthr, al)) {
+		const T *gin = (const T *)a.in + gbase + col0;
+		T *gout = (T *)a.out + gbase + col0;
+		const long long rs = IN ? a.ax_is : a.ax_os;
+		const int lg = ilog2(a.tc / 4);
+		if (scatter) tile_move_lean<T, IN, Op>(gin, gout, rs, f.n, lg, op, negim, RowIdent(), SlotSigMakhoul{f.sig, f.n}, f.npad, tid, nthr, s);
+		else tile_move_lean<T, IN, Op>(gin, gout, rs, f.n, lg, op, negim, RowIdent(), SlotNat<T>(), f.npad, tid, nthr, s);
+		return;
+	}
 	if (al && (ncl % VN) == 0) col_move<T, VecOf<T>::N, IN, Op>(a, f, op, scatter, negim, true, col0, ncl, gbase, cbase, tid, nthr, s);
 	else if (sizeof(T) == 4 && al && (ncl % 2) == 0 && (a.tc % 2) == 0) col_move<T, 2, IN, Op>(a, f, op, scatter, negim, true, col0, ncl, gbase, cbase, tid, nthr, s);
 	else col_move<T, 2, IN, Op>(a, f, op, scatter, negim, false, col0, ncl, gbase, cbase, tid, nthr, s);
@@ -730,7 +818,7 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 				const int i = (int)(u - seq * upseq);
 				SmemNat<T> sink;
 				sink.base = s + seq * f.npad;
-				dct2_outer_unit<T>(sink.base, f, i, sink);
+				dct2_outer_unit<T>(SmemBf<T>{sink.base, f.poff[f.nmid]}, f, i, sink);
 			}
 		}
 		DSP_SYNC();
@@ -741,7 +829,7 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 				const int i = (int)(u - seq * upseq);
 				SmemNat<T> src;
 				src.base = s + seq * f.npad;
-				dct3_outer_unit<T>(src.base, f, i, src);
+				dct3_outer_unit<T>(SmemBf<T>{src.base, f.poff[f.nmid]}, f, i, src);
 			}
 		}
 		DSP_SYNC();

@@ -1,0 +1,250 @@
+// dct_split.cuh -- long strided (column) axes as two L2-resident sub-passes, n = 16 M (power of two, float).
+//
+// A column tile of the full length does not leave room for a second tile in shared memory (n = 8192: 4 columns x
+// 8192 x 8.5 B = 140 KB), so the single-kernel column pass cannot overlap its load / compute / store phases and only
+// ever touches 16 B per row.  Here the length-n transform is split along its outermost radix-16 stage:
+//
+//   DCT-II :  A) 16 independent M-point FFTs per column pair (rows e = 16 e' + j of the permuted sequence), tiles of
+//                32 columns x M rows (70 KB at M = 512; several CTAs per SM; 128 B row segments), results written to
+//                a panel-sized scratch [16 M][P] that stays in L2;
+//             B) the outer radix-16 butterflies + (k, n-k) post-twiddle straight from / to global memory, one thread
+//                per (column pair, butterfly pair i | M-i), lanes along columns (256 B per warp instruction), no smem.
+//   DCT-III:  B') pre-twiddle + outer radix-16 into the scratch, then A') the M-point FFTs and the un-permuting store.
+//
+// The plane is processed in panels of P columns (n * P * 4 B ~ 32 MB), A then B per panel, so the scratch traffic
+// never reaches HBM: per sample the pass still reads 4 B and writes 4 B of DRAM.
+#pragma once
+#include "dct_fast.cuh"
+
+namespace dsp {
+
+struct SplitArgs {
+	int n, M;                    // n = 16 M
+	int kind;
+	int d;                       // interleave of the column index (col = x*d + ch), for coordinates only
+	FastDiv dd;
+	long long ax_is, ax_os;      // row strides of in / out (elements)
+	long long ax_ss;             // row stride of the scratch (elements, even)
+	int ax_slot, col_slot;
+	const void *in;              // already offset to the outer index (batch / frame) of this launch
+	void *out;
+	void *scratch;
+	Coord cbase;                 // coordinates of the outer index
+	int pcol0, pcols;            // panel column range [pcol0, pcol0 + pcols)
+	int tc, ntiles;              // sub-pass A: columns per CTA, tiles per panel
+	int ngroups;                 // sub-pass B: 32-pair column groups per panel
+};
+
+DSP_DEV int split_row(int e, int n) { return e < n / 2 ? 2 * e : 2 * (n - 1 - e) + 1; }   // inverse Makhoul: row holding v[e]
+
+// ------------------------------------------------------------------------------------------------ sub-pass A
+// idx -> (global row, smem slot) for the four moves of sub-pass A
+template <class T, int W, bool IN, bool GLOBAL_SIDE_IS_IMAGE, class Op>
+DSP_DEV void split_move(const SplitArgs &a, const FastDesc &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
+                        int nthr, C2<T> *s) {
+	typedef VecW<T, W> Vec;
+	const int UNR = 8;
+	const int M = a.M, n = a.n;
+	const int gpr = (ncl + W - 1) / W;
+	const int total = M * gpr;
+	const bool vec = (ncl % W) == 0;
+	const int lg = (gpr & (gpr - 1)) == 0 ? ilog2(gpr) : -1;
+	const T *gin = (const T *)(GLOBAL_SIDE_IS_IMAGE ? a.in : a.scratch);
+	T *gout = (T *)(GLOBAL_SIDE_IS_IMAGE ? a.out : a.scratch);
+	const long long rs = GLOBAL_SIDE_IS_IMAGE ? (IN ? a.ax_is : a.ax_os) : a.ax_ss;
+	const int cofs = GLOBAL_SIDE_IS_IMAGE ? col0 : col0 - a.pcol0;
+	for (int i0 = tid; i0 < total; i0 += nthr * UNR) {
+		T v[UNR][W];
+		if (IN) {
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int idx = i0 + u * nthr;
+				if (idx < total) {
+					const int r = lg >= 0 ? idx >> lg : idx / gpr, cg = idx - r * gpr;
+					const int c0 = cg * W;
+					const long long grow = GLOBAL_SIDE_IS_IMAGE ? split_row(16 * r + j, n) : (long long)j * M + r;
+					const T *src = gin + grow * rs + cofs + c0;
+					if (vec) {
+						const Vec tv = ldg_stream((const Vec *)src);
+#pragma unroll
+						for (int t = 0; t < W; t++) v[u][t] = tv.v[t];
+					} else {
+#pragma unroll
+						for (int t = 0; t < W; t++) v[u][t] = (c0 + t < ncl) ? src[t] : (T)0;
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int idx = i0 + u * nthr;
+			if (idx < total) {
+				const int r = lg >= 0 ? idx >> lg : idx / gpr, cg = idx - r * gpr;
+				const int c0 = cg * W;
+				const int grow = GLOBAL_SIDE_IS_IMAGE ? split_row(16 * r + j, n) : j * M + r;
+				// image side: element e' of sub-FFT j lives at the digit-reversed slot; scratch side: natural order
+				const int slot = GLOBAL_SIDE_IS_IMAGE ? (int)DSP_LDG(fM.sig + r) : Pad<T>::of(r);
+				Coord c = a.cbase;
+				c.set(a.ax_slot, grow);
+				if (!IN) {
+#pragma unroll
+					for (int p = 0; p < W / 2; p++) {
+						v[u][2 * p] = 0; v[u][2 * p + 1] = 0;
+						if (c0 + 2 * p < ncl) {
+							const C2<T> z = s[(c0 / 2 + p) * fM.npad + slot];
+							v[u][2 * p] = z.x;
+							v[u][2 * p + 1] = negim ? -z.y : z.y;
+						}
+					}
+				}
+				if (GLOBAL_SIDE_IS_IMAGE) {
+#pragma unroll
+					for (int t = 0; t < W; t++) {
+						if (c0 + t < ncl) {
+							const int col = col0 + c0 + t;
+							int x = col, ch = 0;
+							if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
+							c.set(a.col_slot, x); c.ch = ch;
+							v[u][t] = op(v[u][t], c);
+						}
+					}
+				}
+				if (IN) {
+#pragma unroll
+					for (int p = 0; p < W / 2; p++)
+						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * fM.npad + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
+				} else {
+					T *dst = gout + (long long)grow * rs + cofs + c0;
+					if (vec) {
+						Vec res;
+#pragma unroll
+						for (int t = 0; t < W; t++) res.v[t] = v[u][t];
+						*(Vec *)dst = res;
+					} else {
+#pragma unroll
+						for (int t = 0; t < W; t++)
+							if (c0 + t < ncl) dst[t] = v[u][t];
+					}
+				}
+			}
+		}
+	}
+}
+
+struct RowSplitImage { int j, n; DSP_DEVM int operator()(int r) const { return split_row(16 * r + j, n); } };
+struct RowSplitScratch { int base; DSP_DEVM int operator()(int r) const { return base + r; } };
+struct SlotSig { const uint16_t *sig; DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + r); } };
+
+// image-side and scratch-side moves of sub-pass A with the lean path when the tile is full and aligned
+template <class T, bool IN, bool IMAGE, class Op>
+DSP_DEV void split_move_any(const SplitArgs &a, const FastDesc &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
+                            int nthr, C2<T> *s) {
+	const int W = VecOf<T>::N;
+	if (sizeof(T) == 4 && !Op::kNeedsCoord && lean_ok(ncl, a.tc, nthr, true)) {
+		const int lg = ilog2(a.tc / 4);
+		if (IMAGE) {
+			const T *gin = (const T *)a.in + col0;
+			T *gout = (T *)a.out + col0;
+			tile_move_lean<T, IN, Op>(gin, gout, IN ? a.ax_is : a.ax_os, a.M, lg, op, negim, RowSplitImage{j, a.n}, SlotSig{fM.sig}, fM.npad, tid, nthr, s);
+		} else {
+			const T *g = (const T *)a.scratch + (col0 - a.pcol0);
+			tile_move_lean<T, IN, Op>(g, (T *)g, a.ax_ss, a.M, lg, op, negim, RowSplitScratch{j * a.M}, SlotNat<T>(), fM.npad, tid, nthr, s);
+		}
+		return;
+	}
+	split_move<T, W, IN, IMAGE, Op>(a, fM, op, j, col0, ncl, negim, tid, nthr, s);
+}
+
+// CTA = (column tile, sub-FFT j).  FWD: image rows -> M-point DIT FFT -> scratch block j.
+// !FWD: scratch block j -> M-point DIF FFT -> image rows (un-permuted).
+template <class T, bool FWD, class LoadOp, class StoreOp>
+DSP_DEV void cta_split_fft(const SplitArgs &a, const FastDesc &fM, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
+                           int nthr, C2<T> *s) {
+	const int j = cta / a.ntiles, tile = cta - j * a.ntiles;
+	const int col0 = a.pcol0 + tile * a.tc;
+	int ncl = a.pcol0 + a.pcols - col0;
+	if (ncl > a.tc) ncl = a.tc;
+	const int nseq = (ncl + 1) / 2;
+	if (FWD) {
+		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, true, LoadOp>(a, fM, lop, j, col0, ncl, false, tid, nthr, s);
+		DSP_SYNC();
+		contig_pass<T>(s, nseq, fM, t0, t1, nthr);
+		for (int q = 0; q <= fM.nmid; q++) {
+			for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, fM, q, tid, nthr);
+			DSP_SYNC();
+		}
+		for (int tid = t0; tid < t1; tid++) split_move_any<T, false, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
+	} else {
+		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
+		DSP_SYNC();
+		for (int q = fM.nmid; q >= 0; q--) {
+			for (int tid = t0; tid < t1; tid++) mid_pass<T, false>(s, nseq, fM, q, tid, nthr);
+			DSP_SYNC();
+		}
+		contig_pass<T>(s, nseq, fM, t0, t1, nthr);
+		for (int tid = t0; tid < t1; tid++) split_move_any<T, false, true, StoreOp>(a, fM, sop, j, col0, ncl, true, tid, nthr, s);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ sub-pass B
+// one column pair of the image: rows k of two adjacent columns, through the fused op
+template <class T, class Op> struct GlobalCols {
+	T *p;                        // image + column
+	long long rs;                // row stride (elements)
+	bool hasb, vec;              // second column exists; 8-byte access legal
+	int ax_slot;
+	Coord ca, cb;
+	const Op *op;
+	DSP_DEVM void put(int k, T xa, T xb) {
+		ca.set(ax_slot, k); cb.set(ax_slot, k);
+		const T ya = (*op)(xa, ca), yb = hasb ? (*op)(xb, cb) : (T)0;
+		T *q = p + (long long)k * rs;
+		if (vec) *(C2<T> *)q = C2<T>{ya, yb};
+		else { q[0] = ya; if (hasb) q[1] = yb; }
+	}
+	DSP_DEVM C2<T> get(int k) {
+		ca.set(ax_slot, k); cb.set(ax_slot, k);
+		const T *q = p + (long long)k * rs;
+		C2<T> v;
+		if (vec) v = *(const C2<T> *)q;
+		else { v.x = q[0]; v.y = hasb ? q[1] : (T)0; }
+		return C2<T>{(*op)(v.x, ca), hasb ? (*op)(v.y, cb) : (T)0};
+	}
+};
+
+// thread = (column pair, unit i): lanes run along the columns, one warp per unit
+template <class T, bool FWD, class LoadOp, class StoreOp>
+DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const LoadOp &lop, const StoreOp &sop, int gwarp, int lane) {
+	const int group = gwarp % a.ngroups, i = gwarp / a.ngroups;
+	if (i > a.M / 2) return;
+	const int pair = group * 32 + lane;
+	const int col = a.pcol0 + 2 * pair;
+	if (col >= a.pcol0 + a.pcols) return;
+	const bool hasb = col + 1 < a.pcol0 + a.pcols;
+	GlobBf<T> bf;
+	bf.base = (C2<T> *)a.scratch + pair;
+	bf.rs = a.ax_ss / 2;
+	bf.M = a.M;
+	Coord ca = a.cbase, cb = a.cbase;
+	{
+		int x = col, ch = 0;
+		if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
+		ca.set(a.col_slot, x); ca.ch = ch;
+		x = col + 1; ch = 0;
+		if (a.d != 1) { x = (int)fd_div((uint32_t)(col + 1), a.dd); ch = col + 1 - x * a.d; }
+		cb.set(a.col_slot, x); cb.ch = ch;
+	}
+	if (FWD) {
+		GlobalCols<T, StoreOp> sink;
+		sink.p = (T *)a.out + col; sink.rs = a.ax_os; sink.hasb = hasb; sink.vec = hasb && (a.ax_os % 2) == 0 && (((size_t)a.out / sizeof(T) + col) % 2) == 0;
+		sink.ax_slot = a.ax_slot; sink.ca = ca; sink.cb = cb; sink.op = &sop;
+		dct2_outer_unit<T>(bf, fN, i, sink);
+	} else {
+		GlobalCols<T, LoadOp> src;
+		src.p = (T *)a.in + col; src.rs = a.ax_is; src.hasb = hasb; src.vec = hasb && (a.ax_is % 2) == 0 && (((size_t)a.in / sizeof(T) + col) % 2) == 0;
+		src.ax_slot = a.ax_slot; src.ca = ca; src.cb = cb; src.op = &lop;
+		dct3_outer_unit<T>(bf, fN, i, src);
+	}
+}
+
+}  // namespace dsp

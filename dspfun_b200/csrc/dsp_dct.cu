@@ -6,6 +6,7 @@
 // last, so a forward+inverse round trip meets in the middle on the same column tiles (L2 reuse).
 #include "../../include/dsp_dct.h"
 #include "dsp_kernels.h"
+#include "dct_split.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -226,6 +227,11 @@ struct PassPlan {
 	bool vec_in_layout, vec_out_layout;
 	OpAny lop, sop;
 	bool fused;
+	// split column pass (dct_split.cuh): n = 16 M in two L2-resident sub-passes per panel of sp_P columns
+	bool split;
+	FastDesc ffM;
+	int sp_P, sp_tc;
+	size_t sp_smem;
 };
 
 }  // namespace dsp
@@ -250,6 +256,8 @@ struct dsp_dct_plan_s {
 	double *d_scalars;                       // acc[4] | scale_z[4] | dc_out[4]
 	unsigned char *d_signmap;
 	void *d_work;                            // T scratch the passes run in when the final store is 8-bit
+	void *d_split;                           // panel scratch of the split column passes
+	size_t split_bytes;
 	bool need_acc;
 	rt_stream last_stream;
 	// per-pass profiling
@@ -332,6 +340,8 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		const bool wide = d > 4;
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
+		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0;
+		memset(&pp.ffM, 0, sizeof(pp.ffM));
 		memset(&pp.ff, 0, sizeof(pp.ff));
 		if (pp.fast) fill_fast(pp.ff, t);
 		const size_t seqb = (size_t)t->npad * cbytes;
@@ -409,21 +419,52 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			if (g >= (1ll << 31)) { g_err = "too many column tiles"; return false; }
 			pp.grid = (int)g;
 			pp.smem = (size_t)((tc + 1) / 2) * seqb;
+			// long power-of-two axes: two L2-resident sub-passes per column panel (dct_split.cuh)
+			// Measured on B200 (profiles/): the split wins for the forward transform at n = 8192 (0.76 vs 0.88 ms per
+			// 2 planes) and loses for the inverse (its first sub-pass reads 32 strided rows per thread straight from
+			// DRAM and is latency-bound), so it is on for REDFT10, n >= 4096.  DSP_DCT_SPLIT_MIN=<n> forces it for both.
+			int split_min = 4096;
+			bool split_inv = false;
+			if (getenv("DSP_DCT_SPLIT_MIN")) { split_min = atoi(getenv("DSP_DCT_SPLIT_MIN")); split_inv = true; }
+			const int nn = P->n[ax];
+			if (pp.fast && P->prec == 'f' && nn >= split_min && nn >= 256 && vin && vout && !lastax &&
+			    (split_inv || P->kind[ax] == DSP_DCT_REDFT10)) {
+				Tables *tM = get_tables(nn / 16, P->prec);
+				if (tM && tM->sig) {
+					pp.split = true;
+					fill_fast(pp.ffM, tM);
+					long long pw = (32ll << 20) / ((long long)nn * P->es);
+					if (getenv("DSP_DCT_SPLIT_PANEL_MB")) pw = ((long long)atoi(getenv("DSP_DCT_SPLIT_PANEL_MB")) << 20) / ((long long)nn * P->es);
+					pw = (pw / 64) * 64;
+					if (pw < 64) pw = 64;
+					const long long cap = ((A.ncols + 63) / 64) * 64;
+					if (pw > cap) pw = cap;
+					pp.sp_P = (int)pw;
+					const size_t seqM = (size_t)tM->npad * cbytes;
+					int stc = 32;
+					while (stc > VN && (size_t)(stc / 2) * seqM > 72 * 1024) stc /= 2;
+					pp.sp_tc = stc;
+					pp.sp_smem = (size_t)(stc / 2) * seqM;
+					const size_t need = (size_t)nn * (size_t)pw * (size_t)P->es;
+					if (need > P->split_bytes) P->split_bytes = need;
+				}
+			}
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
 		// one CTA per SM (big tile): run it with 512 threads; otherwise 256 and rely on several CTAs per SM
 		pp.block = (pp.fast && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;
 		if (pp.fast && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
-		DSP_TRACE("pass %zu: %s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid);
+		DSP_TRACE("pass %zu: %s%s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d panel=%d tcA=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", pp.split ? "(split)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid, pp.sp_P, pp.sp_tc);
 		P->passes.push_back(pp);
 	}
+	if (P->split_bytes && !rt_malloc(&P->d_split, P->split_bytes, g_err)) return false;
 	return true;
 }
 
 static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st) {
 	const bool ain = ((uintptr_t)in % 16) == 0, aout = ((uintptr_t)out % 16) == 0;
 	const bool f32 = P->prec == 'f';
-	bool ok;
+	bool ok = false;
 	if (pp.row) {
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
@@ -434,6 +475,55 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 #endif
 		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
 		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+	} else if (pp.split && ain && aout) {
+		// per outer index (batch / frame) and per column panel: sub-pass A then B (forward) or B' then A' (inverse)
+		const ColArgs &c = pp.ca;
+		const bool fwd = c.kind == DSP_KIND_REDFT10;
+		long long no = 1;
+		for (int k = 0; k < 4; k++) no *= c.o.cnt[k];
+		const int M = c.f.n / 16;
+		ok = true;
+		for (long long oi = 0; oi < no && ok; oi++) {
+			long long rem = oi, ioff = 0, ooff = 0;
+			SplitArgs sa;
+			memset(&sa, 0, sizeof(sa));
+			for (int k = 0; k < 4; k++) {
+				const long long idx = rem % c.o.cnt[k];
+				rem /= c.o.cnt[k];
+				ioff += idx * c.o.is[k]; ooff += idx * c.o.os[k];
+				sa.cbase.set(c.o.slot[k], (int)idx);
+			}
+			sa.n = c.f.n; sa.M = M; sa.kind = c.kind; sa.d = c.d; sa.dd = c.dd;
+			sa.ax_is = c.ax_is; sa.ax_os = c.ax_os; sa.ax_ss = pp.sp_P;
+			sa.ax_slot = c.ax_slot; sa.col_slot = c.col_slot;
+			sa.in = (const char *)in + ioff * P->es; sa.out = (char *)out + ooff * P->es; sa.scratch = P->d_split;
+			sa.tc = pp.sp_tc;
+			const int npanels = (c.ncols + pp.sp_P - 1) / pp.sp_P;
+			for (int pi = 0; pi < npanels && ok; pi++) {
+				// the inverse walks the panels backwards: a forward+inverse round trip then starts on the columns the
+				// forward pass touched last, which are the ones still resident in L2
+				const int pn = fwd ? pi : npanels - 1 - pi;
+				sa.pcol0 = pn * pp.sp_P;
+				sa.pcols = c.ncols - sa.pcol0 < pp.sp_P ? c.ncols - sa.pcol0 : pp.sp_P;
+				sa.ntiles = (sa.pcols + sa.tc - 1) / sa.tc;
+				sa.ngroups = ((sa.pcols + 1) / 2 + 31) / 32;
+				const int gridA = sa.ntiles * 16, warpsB = sa.ngroups * (M / 2 + 1);
+				// start pulling the next panel's columns into L2 while this panel computes
+				static const bool pf = getenv("DSP_DCT_PREFETCH") != nullptr;   // measured: no gain, off by default
+				if (pf && pi + 1 < npanels) {
+					const int nx = fwd ? pn + 1 : pn - 1;
+					const int nc0 = nx * pp.sp_P;
+					const int ncols = c.ncols - nc0 < pp.sp_P ? c.ncols - nc0 : pp.sp_P;
+					ok = launch_l2_prefetch((const char *)sa.in + (size_t)nc0 * P->es, sa.ax_is * P->es, c.f.n, ncols * P->es, st, g_err);
+				}
+				if (ok && fwd) ok = launch_split_fft_f32(sa, pp.ffM, pp.fused, pp.lop, pp.sop, gridA, pp.sp_smem, st, g_err) &&
+				              launch_split_outer_f32(sa, pp.ff, pp.fused, pp.lop, pp.sop, warpsB, st, g_err);
+				else if (ok) ok = launch_split_outer_f32(sa, pp.ff, pp.fused, pp.lop, pp.sop, warpsB, st, g_err) &&
+				          launch_split_fft_f32(sa, pp.ffM, pp.fused, pp.lop, pp.sop, gridA, pp.sp_smem, st, g_err);
+				if (ok) g_launches++;          // (the second launch is counted by the caller)
+			}
+		}
+		if (ok) g_launches--;                  // the caller adds one
 	} else {
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
@@ -515,6 +605,8 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->d_scalars = nullptr;
 	P->d_signmap = nullptr;
 	P->d_work = nullptr;
+	P->d_split = nullptr;
+	P->split_bytes = 0;
 	P->need_acc = false;
 	P->last_stream = 0;
 	P->profiling = false;
@@ -625,6 +717,7 @@ void dsp_dct_destroy(dsp_dct_plan p) {
 	rt_free(p->d_scalars);
 	rt_free(p->d_signmap);
 	rt_free(p->d_work);
+	rt_free(p->d_split);
 #if DSP_GPU
 	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
 #endif

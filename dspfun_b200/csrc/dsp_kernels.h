@@ -27,7 +27,14 @@ DSP_DECL_LAUNCH(launch_col_fast_f32, ColArgs)
 DSP_DECL_LAUNCH(launch_col_fast_f64, ColArgs)
 #undef DSP_DECL_LAUNCH
 
+bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int row_bytes, rt_stream st, std::string &err);
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
+
+struct SplitArgs;
+bool launch_split_fft_f32(const SplitArgs &a, const FastDesc &fM, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,
+                          rt_stream st, std::string &err);
+bool launch_split_outer_f32(const SplitArgs &a, const FastDesc &fN, bool fused, const OpAny &lop, const OpAny &sop, int nwarps,
+                            rt_stream st, std::string &err);
 
 bool launch_zoom_basis(char prec, void *basis, int nvec, int ncomp, int type, double num, double den, double offset, int len,
                        rt_stream st, std::string &err);
