@@ -27,6 +27,34 @@ struct FastDesc {
 	const uint16_t *sig;         // [n] padded smem slot of natural index e under the digit reversal
 	int poff[4][16];             // poff[q][j] = Pad(j * Lprev_q) for radix-16 pass q (0..nmid-1 middle, nmid = outer)
 	FastDiv dHalf;               // divide by M/2+1 (outer-pass units per sequence)
+	// accessors shared with FastFixed (the compile-time variant below)
+	DSP_HDM int N() const { return n; }
+	DSP_HDM int Mq() const { return M; }
+	DSP_HDM int R0() const { return r0; }
+	DSP_HDM int NMID() const { return nmid; }
+	DSP_HDM int NPAD() const { return npad; }
+	DSP_HDM int PO(int q, int j) const { return poff[q][j]; }
+	DSP_DEVM uint32_t divHalf(uint32_t u) const { return fd_div(u, dHalf); }
+};
+
+// The same description with the length fixed at compile time (float padding): every smem offset, loop bound and
+// division of the passes folds to an immediate.  Kernels are instantiated for the common lengths; the runtime
+// FastDesc serves the rest.
+template <int LG> struct FastFixed {
+	const void *tw, *om;
+	const uint16_t *sig;
+	static constexpr int kA = LG - 4;
+	static constexpr int kL0raw = kA % 4, kKraw = (kA - kL0raw) / 4;
+	static constexpr int kL0 = (kL0raw == 0 && kKraw > 0) ? 4 : ((kL0raw == 1 && kKraw > 0) ? 5 : kL0raw);
+	static constexpr int kK = ((kL0raw == 0 || kL0raw == 1) && kKraw > 0) ? kKraw - 1 : kKraw;
+	DSP_HDM static constexpr int padc(int e) { return e + (e >> 4) + (e >> 8) + (e >> 12); }
+	DSP_HDM constexpr int N() const { return 1 << LG; }
+	DSP_HDM constexpr int Mq() const { return 1 << (LG - 4); }
+	DSP_HDM constexpr int R0() const { return 1 << kL0; }
+	DSP_HDM constexpr int NMID() const { return kK; }
+	DSP_HDM constexpr int NPAD() const { return padc((1 << LG) - 1) + 1; }
+	DSP_HDM constexpr int PO(int q, int j) const { return padc(j * ((1 << kL0) << (4 * q))); }
+	DSP_DEVM uint32_t divHalf(uint32_t u) const { return u / (uint32_t)((1 << (LG - 4)) / 2 + 1); }
 };
 
 // ------------------------------------------------------------------------------------------------ radix 32
@@ -76,13 +104,13 @@ template <class T> DSP_DEV C2<T> cmul_conj(C2<T> a, C2<T> b) {   // a * conj(b)
 // ------------------------------------------------------------------------------------------------ inner passes
 DSP_DEV int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
-template <class T, int R>
-DSP_DEV void contig_pass_r(C2<T> *s, int nseq, const FastDesc &f, int tid, int nthr) {
-	const int lnb = ilog2(f.n / R);                           // butterflies per sequence (power of two)
+template <class T, int R, class F>
+DSP_DEV void contig_pass_r(C2<T> *s, int nseq, const F &f, int tid, int nthr) {
+	const int lnb = ilog2(f.N() / R);                           // butterflies per sequence (power of two)
 	const int total = nseq << lnb;
 	for (int g = tid; g < total; g += nthr) {
 		const int seq = g >> lnb, b = g & ((1 << lnb) - 1);
-		C2<T> *p = s + seq * f.npad + Pad<T>::of(b * R);
+		C2<T> *p = s + seq * f.NPAD() + Pad<T>::of(b * R);
 		C2<T> v[R];
 #pragma unroll
 		for (int j = 0; j < R; j++) v[j] = p[Pad<T>::of(j)];      // b*R and j are bit-disjoint (R <= 32): Pad is additive
@@ -92,11 +120,11 @@ DSP_DEV void contig_pass_r(C2<T> *s, int nseq, const FastDesc &f, int tid, int n
 	}
 }
 
-template <class T>
-DSP_DEV void contig_pass(C2<T> *s, int nseq, const FastDesc &f, int t0, int t1, int nthr) {
-	if (f.r0 <= 1) return;
+template <class T, class F>
+DSP_DEV void contig_pass(C2<T> *s, int nseq, const F &f, int t0, int t1, int nthr) {
+	if (f.R0() <= 1) return;
 	for (int tid = t0; tid < t1; tid++) {
-		switch (f.r0) {
+		switch (f.R0()) {
 		case 2:  contig_pass_r<T, 2>(s, nseq, f, tid, nthr); break;
 		case 4:  contig_pass_r<T, 4>(s, nseq, f, tid, nthr); break;
 		case 8:  contig_pass_r<T, 8>(s, nseq, f, tid, nthr); break;
@@ -109,21 +137,21 @@ DSP_DEV void contig_pass(C2<T> *s, int nseq, const FastDesc &f, int t0, int t1, 
 }
 
 // radix-16 middle pass q (Lprev = r0 * 16^q, L = 16 Lprev).  DIT: twiddle the inputs; DIF: twiddle the outputs.
-template <class T, bool DIT>
-DSP_DEV void mid_pass(C2<T> *s, int nseq, const FastDesc &f, int q, int tid, int nthr) {
-	const int lsh = ilog2(f.r0) + 4 * q;                      // log2 Lprev
-	const int lnb = ilog2(f.n) - 4;                           // log2 (butterflies per sequence)
+template <class T, bool DIT, class F>
+DSP_DEV void mid_pass(C2<T> *s, int nseq, const F &f, int q, int tid, int nthr) {
+	const int lsh = ilog2(f.R0()) + 4 * q;                      // log2 Lprev
+	const int lnb = ilog2(f.N()) - 4;                           // log2 (butterflies per sequence)
 	const int total = nseq << lnb;
-	const int twsh = ilog2(f.n) - lsh - 4;                    // log2 (n / L)
+	const int twsh = ilog2(f.N()) - lsh - 4;                    // log2 (n / L)
 	const C2<T> *tw = (const C2<T> *)f.tw;
 	for (int g = tid; g < total; g += nthr) {
 		const int seq = g >> lnb, b = g & ((1 << lnb) - 1);
 		const int blk = b >> lsh, i = b & ((1 << lsh) - 1);
-		C2<T> *p = s + seq * f.npad + Pad<T>::of((blk << (lsh + 4)) + i);
+		C2<T> *p = s + seq * f.NPAD() + Pad<T>::of((blk << (lsh + 4)) + i);
 		C2<T> v[16], w[16];
 		if (i != 0) tw_powers<T>(tw, i << twsh, w);
 #pragma unroll
-		for (int j = 0; j < 16; j++) v[j] = p[f.poff[q][j]];
+		for (int j = 0; j < 16; j++) v[j] = p[f.PO(q, j)];
 		if (DIT && i != 0) {
 #pragma unroll
 			for (int j = 1; j < 16; j++) v[j] = cmul(v[j], w[j]);
@@ -134,7 +162,7 @@ DSP_DEV void mid_pass(C2<T> *s, int nseq, const FastDesc &f, int q, int tid, int
 			for (int j = 1; j < 16; j++) v[j] = cmul(v[j], w[j]);
 		}
 #pragma unroll
-		for (int j = 0; j < 16; j++) p[f.poff[q][j]] = v[j];
+		for (int j = 0; j < 16; j++) p[f.PO(q, j)] = v[j];
 	}
 }
 
@@ -160,15 +188,15 @@ template <class T> DSP_DEV C2<T> om_minus(C2<T> wi, C2<T> e) { return C2<T>{e.x 
 // ------------------------------------------------------------------------------------------------ butterfly storage
 // Where the outer pass finds (DCT-II) or leaves (DCT-III) element j of butterfly i.
 // SmemBf: slot Pad(i) + Pad(j M) of a sequence in shared memory.
-template <class T> struct SmemBf {
+template <class T, class F> struct SmemBf {
 	C2<T> *base;
-	const int *poff;             // Pad(j * M), j < 16
+	const F *f;                  // slot of element j: Pad(i) + PO(nmid, j) = Pad(i) + Pad(j * M)
 	struct Row {
-		C2<T> *p; const int *poff;
-		DSP_DEVM C2<T> get(int j) const { return p[poff[j]]; }
-		DSP_DEVM void put(int j, C2<T> v) const { p[poff[j]] = v; }
+		C2<T> *p; const F *f;
+		DSP_DEVM C2<T> get(int j) const { return p[f->PO(f->NMID(), j)]; }
+		DSP_DEVM void put(int j, C2<T> v) const { p[f->PO(f->NMID(), j)] = v; }
 	};
-	DSP_DEVM Row row(int i) const { return Row{base + Pad<T>::of(i), poff}; }
+	DSP_DEVM Row row(int i) const { return Row{base + Pad<T>::of(i), f}; }
 };
 // GlobBf: row (j M + i) of a [16 M][...] global scratch, one complex (= one column pair) per row
 template <class T> struct GlobBf {
@@ -192,9 +220,9 @@ DSP_DEV void dct2_pair(C2<T> w, int k, int n, C2<T> z, C2<T> y, bool self, Sink 
 	if (!self) sink.put(n - k, w.y * ar - w.x * ai, w.y * br - w.x * bi);
 }
 
-template <class T, class Bf, class Sink>
-DSP_DEV void dct2_outer_unit(const Bf &bf, const FastDesc &f, int i, Sink &sink) {
-	const int n = f.n, M = f.M;
+template <class T, class Bf, class Sink, class F>
+DSP_DEV void dct2_outer_unit(const Bf &bf, const F &f, int i, Sink &sink) {
+	const int n = f.N(), M = f.Mq();
 	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
@@ -253,9 +281,9 @@ DSP_DEV void dct3_pair(C2<T> w, C2<T> xk, C2<T> xn, C2<T> &wk, C2<T> &wn) {
 	wn = C2<T>{pa + qb, -(pb - qa)};
 }
 
-template <class T, class Bf, class Source>
-DSP_DEV void dct3_outer_unit(const Bf &bf, const FastDesc &f, int i, Source &src) {
-	const int M = f.M;
+template <class T, class Bf, class Source, class F>
+DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
+	const int M = f.Mq();
 	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
@@ -351,14 +379,14 @@ DSP_DEV int makhoul(int x, int n) { return (x & 1) ? n - 1 - (x >> 1) : (x >> 1)
 // Moves the CTA's lines between global memory and smem in vector groups, `UNR` groups per thread in flight.
 // FWD (DCT-II scatter-load):  global -> lop -> s[sig[makhoul(x)]]
 // !FWD (DCT-III gather-store): s[sig[makhoul(x)]] -> (re, -im) -> sop -> global
-template <class T, bool FWD, class Op>
-DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
+template <class T, bool FWD, class Op, class F>
+DSP_DEV void row_move(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
 	typedef typename VecOf<T>::type Vec;
 	const int VN = VecOf<T>::N;
 	const int UNR = 4;
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
-	const int n = f.n, d = a.d;
+	const int n = f.N(), d = a.d;
 	const int llen = n * d;
 	const int gpl = (llen + VN - 1) / VN;
 	const int npairs = (nl + 1) / 2;
@@ -372,7 +400,7 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 		if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
 		const T *pa = gin + ia, *pb = gin + ib;
 		T *qa = gout + oa, *qb = gout + ob;
-		C2<T> *sg = s + g * d * f.npad;
+		C2<T> *sg = s + g * d * f.NPAD();
 		for (int q0 = tid; q0 < gpl; q0 += nthr * UNR) {
 			T va[UNR][VecOf<T>::N], vb[UNR][VecOf<T>::N];
 			if (FWD) {
@@ -419,7 +447,7 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 							if (d != 1) { x = (int)fd_div((uint32_t)e, a.dd); ch = e - x * d; }
 							ca.set(a.ax_slot, x); ca.ch = ch;
 							cb.set(a.ax_slot, x); cb.ch = ch;
-							C2<T> *slot = sg + ch * f.npad + (int)DSP_LDG(f.sig + makhoul(x, n));
+							C2<T> *slot = sg + ch * f.NPAD() + (int)DSP_LDG(f.sig + makhoul(x, n));
 							if (FWD) {
 								*slot = C2<T>{op(va[u][t], ca), hasb ? op(vb[u][t], cb) : (T)0};
 							} else {
@@ -462,17 +490,17 @@ DSP_DEV void row_move(const RowArgs &a, const FastDesc &f, const Op &op, int lin
 // planar float lines (d == 1, 16-byte access legal): one vector group = x in [4q, 4q+4) of lines A and B =
 // elements 2q, 2q+1 (even x) and n-2-2q, n-1-2q (odd x) of the permuted sequence.  sig[e+1] = sig[e] + Pad(M)
 // for even e, so two table lookups place (or fetch) all four complex values.
-template <class T, bool FWD, class Op>
-DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
+template <class T, bool FWD, class Op, class F>
+DSP_DEV void row_move_planar4(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
 	typedef typename VecOf<T>::type Vec;
 	const int UNR = 8;
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
-	const int n = f.n;
+	const int n = f.N();
 	const int lgq = ilog2(n) - 2;                             // log2 (vector groups per line)
 	const int npairs = (nl + 1) / 2;
 	const int total = npairs << lgq;
-	const int padM = f.poff[f.nmid][1];
+	const int padM = f.PO(f.NMID(), 1);
 	for (int i0 = tid; i0 < total; i0 += nthr * UNR) {
 		Vec ta[UNR], tb[UNR];
 		if (FWD) {
@@ -503,7 +531,7 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op,
 				long long ia, ib = 0, oa, ob = 0;
 				if (a.simple && !Op::kNeedsCoord) { oa = la * a.ls_out; ob = oa + a.ls_out; }
 				else { outer_decode(a.o, (uint32_t)la, ia, oa, ca); if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb); }
-				C2<T> *sg = s + g * f.npad;
+				C2<T> *sg = s + g * f.NPAD();
 				const int s0 = (int)DSP_LDG(f.sig + 2 * q), s1 = (int)DSP_LDG(f.sig + n - 2 - 2 * q);
 				C2<T> *slot[4] = {sg + s0, sg + s1 + padM, sg + s0 + padM, sg + s1};       // x = 4q, 4q+1, 4q+2, 4q+3
 				if (FWD) {
@@ -529,14 +557,14 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const FastDesc &f, const Op &op,
 	}
 }
 
-template <class T, bool FWD, class Op>
-DSP_DEV void row_move_any(const RowArgs &a, const FastDesc &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
-	if (sizeof(T) == 4 && a.d == 1 && (FWD ? a.vec_in : a.vec_out) && f.n >= 4) row_move_planar4<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
+template <class T, bool FWD, class Op, class F>
+DSP_DEV void row_move_any(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
+	if (sizeof(T) == 4 && a.d == 1 && (FWD ? a.vec_in : a.vec_out) && f.N() >= 4) row_move_planar4<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 	else row_move<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 }
 
-template <class T, bool FWD, class LoadOp, class StoreOp>
-DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
+template <class T, bool FWD, class LoadOp, class StoreOp, class F>
+DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
                           int nthr, C2<T> *s) {
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
@@ -546,20 +574,20 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 	if (nl > a.lines_per_cta) nl = a.lines_per_cta;
 	const int npairs = (nl + 1) / 2;
 	const int nseq = npairs * d;
-	const uint32_t upseq = (uint32_t)(f.M / 2 + 1);              // outer-pass units per sequence
+	const uint32_t upseq = (uint32_t)(f.Mq() / 2 + 1);              // outer-pass units per sequence
 
 	if (FWD) {
 		for (int tid = t0; tid < t1; tid++) row_move_any<T, true, LoadOp>(a, f, lop, line0, nl, tid, nthr, s);
 		DSP_SYNC();
 		contig_pass<T>(s, nseq, f, t0, t1, nthr);
-		for (int q = 0; q < f.nmid; q++) {
+		for (int q = 0; q < f.NMID(); q++) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, f, q, tid, nthr);
 			DSP_SYNC();
 		}
 		// ---- outer pass + post-twiddle + direct global store
 		for (int tid = t0; tid < t1; tid++) {
 			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = fd_div(u, f.dHalf);
+				const uint32_t seq = f.divHalf(u);
 				const int i = (int)(u - seq * upseq);
 				const int g = (int)seq / d, ch = (int)seq - g * d;
 				const int la = line0 + 2 * g;
@@ -572,7 +600,7 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 				sink.ca.ch = ch; sink.cb.ch = ch;
 				sink.pa = gout + oa + ch; sink.pb = hasb ? gout + ob + ch : (T *)0;
 				sink.d = d; sink.ax_slot = a.ax_slot; sink.op = &sop;
-				dct2_outer_unit<T>(SmemBf<T>{s + seq * f.npad, f.poff[f.nmid]}, f, i, sink);
+				dct2_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, sink);
 			}
 		}
 		return;
@@ -581,7 +609,7 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 	// ---- DCT-III: outer pass reads the (k, n-k) pairs straight from global memory
 	for (int tid = t0; tid < t1; tid++) {
 		for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-			const uint32_t seq = fd_div(u, f.dHalf);
+			const uint32_t seq = f.divHalf(u);
 			const int i = (int)(u - seq * upseq);
 			const int g = (int)seq / d, ch = (int)seq - g * d;
 			const int la = line0 + 2 * g;
@@ -594,11 +622,11 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const FastDesc &f, const LoadOp &lop
 			src.ca.ch = ch; src.cb.ch = ch;
 			src.pa = (T *)gin + ia + ch; src.pb = hasb ? (T *)gin + ib + ch : (T *)0;
 			src.d = d; src.ax_slot = a.ax_slot; src.op = &lop;
-			dct3_outer_unit<T>(SmemBf<T>{s + seq * f.npad, f.poff[f.nmid]}, f, i, src);
+			dct3_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, src);
 		}
 	}
 	DSP_SYNC();
-	for (int q = f.nmid - 1; q >= 0; q--) {
+	for (int q = f.NMID() - 1; q >= 0; q--) {
 		for (int tid = t0; tid < t1; tid++) mid_pass<T, false>(s, nseq, f, q, tid, nthr);
 		DSP_SYNC();
 	}
@@ -630,14 +658,14 @@ DSP_DEV VecW<double, 2> ldg_stream(const VecW<double, 2> *p) {
 // Moves the CTA's column tile between global memory and smem in groups of W columns, UNR groups per thread in
 // flight.  IN: global -> lop -> slot ; !IN: slot -> (re, +-im) -> sop -> global.  `scatter` selects
 // sig[makhoul(r)] vs Pad(r).  `vec`: W-wide accesses are legal (alignment + the tile is a whole number of groups).
-template <class T, int W, bool IN, class Op>
-DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, bool vec, int col0, int ncl,
+template <class T, int W, bool IN, class Op, class F>
+DSP_DEV void col_move(const ColArgs &a, const F &f, const Op &op, bool scatter, bool negim, bool vec, int col0, int ncl,
                       long long gbase, const Coord &cbase, int tid, int nthr, C2<T> *s) {
 	typedef VecW<T, W> Vec;
 	const int UNR = 8;
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
-	const int n = f.n;
+	const int n = f.N();
 	const int gpr = (ncl + W - 1) / W;                        // groups per axis position
 	const int total = n * gpr;
 	const long long axs = IN ? a.ax_is : a.ax_os;
@@ -677,7 +705,7 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 					for (int p = 0; p < W / 2; p++) {
 						v[u][2 * p] = 0; v[u][2 * p + 1] = 0;
 						if (c0 + 2 * p < ncl) {
-							const C2<T> z = s[(c0 / 2 + p) * f.npad + slot];
+							const C2<T> z = s[(c0 / 2 + p) * f.NPAD() + slot];
 							v[u][2 * p] = z.x;
 							v[u][2 * p + 1] = negim ? -z.y : z.y;
 						}
@@ -696,7 +724,7 @@ DSP_DEV void col_move(const ColArgs &a, const FastDesc &f, const Op &op, bool sc
 				if (IN) {
 #pragma unroll
 					for (int p = 0; p < W / 2; p++)
-						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * f.npad + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
+						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * f.NPAD() + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
 				} else {
 					T *dst = gout + gbase + (long long)r * axs + col0 + c0;
 					if (vec) {
@@ -769,8 +797,8 @@ DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
 }
 
 // picks the access width: full 16-byte groups when the tile allows it, else 8-byte (float) pairs, else scalar
-template <class T, bool IN, class Op>
-DSP_DEV void col_move_any(const ColArgs &a, const FastDesc &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
+template <class T, bool IN, class Op, class F>
+DSP_DEV void col_move_any(const ColArgs &a, const F &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
                           long long gbase, const Coord &cbase, int tid, int nthr, C2<T> *s) {
 	const int VN = VecOf<T>::N;
 	const bool al = IN ? a.vec_in : a.vec_out;
@@ -779,8 +807,8 @@ DSP_DEV void col_move_any(const ColArgs &a, const FastDesc &f, const Op &op, boo
 		T *gout = (T *)a.out + gbase + col0;
 		const long long rs = IN ? a.ax_is : a.ax_os;
 		const int lg = ilog2(a.tc / 4);
-		if (scatter) tile_move_lean<T, IN, Op>(gin, gout, rs, f.n, lg, op, negim, RowIdent(), SlotSigMakhoul{f.sig, f.n}, f.npad, tid, nthr, s);
-		else tile_move_lean<T, IN, Op>(gin, gout, rs, f.n, lg, op, negim, RowIdent(), SlotNat<T>(), f.npad, tid, nthr, s);
+		if (scatter) tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lg, op, negim, RowIdent(), SlotSigMakhoul{f.sig, f.N()}, f.NPAD(), tid, nthr, s);
+		else tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lg, op, negim, RowIdent(), SlotNat<T>(), f.NPAD(), tid, nthr, s);
 		return;
 	}
 	if (al && (ncl % VN) == 0) col_move<T, VecOf<T>::N, IN, Op>(a, f, op, scatter, negim, true, col0, ncl, gbase, cbase, tid, nthr, s);
@@ -788,8 +816,8 @@ DSP_DEV void col_move_any(const ColArgs &a, const FastDesc &f, const Op &op, boo
 	else col_move<T, 2, IN, Op>(a, f, op, scatter, negim, false, col0, ncl, gbase, cbase, tid, nthr, s);
 }
 
-template <class T, bool FWD, class LoadOp, class StoreOp>
-DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
+template <class T, bool FWD, class LoadOp, class StoreOp, class F>
+DSP_DEV void cta_col_fast(const ColArgs &a, const F &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
                           int nthr, C2<T> *s) {
 	const uint32_t oidx = fd_div((uint32_t)cta, a.dtiles);
 	const int tile = cta - (int)oidx * a.ntiles;
@@ -797,7 +825,7 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 	int ncl = a.ncols - col0;
 	if (ncl > a.tc) ncl = a.tc;
 	const int nseq = (ncl + 1) / 2;
-	const uint32_t upseq = (uint32_t)(f.M / 2 + 1);
+	const uint32_t upseq = (uint32_t)(f.Mq() / 2 + 1);
 	Coord cbase = {0, 0, 0, 0, 0};
 	long long ibase, obase;
 	outer_decode(a.o, oidx, ibase, obase, cbase);
@@ -808,32 +836,32 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const FastDesc &f, const LoadOp &lop
 
 	if (FWD) {
 		contig_pass<T>(s, nseq, f, t0, t1, nthr);
-		for (int q = 0; q < f.nmid; q++) {
+		for (int q = 0; q < f.NMID(); q++) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, f, q, tid, nthr);
 			DSP_SYNC();
 		}
 		for (int tid = t0; tid < t1; tid++) {
 			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = fd_div(u, f.dHalf);
+				const uint32_t seq = f.divHalf(u);
 				const int i = (int)(u - seq * upseq);
 				SmemNat<T> sink;
-				sink.base = s + seq * f.npad;
-				dct2_outer_unit<T>(SmemBf<T>{sink.base, f.poff[f.nmid]}, f, i, sink);
+				sink.base = s + seq * f.NPAD();
+				dct2_outer_unit<T>(SmemBf<T, F>{sink.base, &f}, f, i, sink);
 			}
 		}
 		DSP_SYNC();
 	} else {
 		for (int tid = t0; tid < t1; tid++) {
 			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = fd_div(u, f.dHalf);
+				const uint32_t seq = f.divHalf(u);
 				const int i = (int)(u - seq * upseq);
 				SmemNat<T> src;
-				src.base = s + seq * f.npad;
-				dct3_outer_unit<T>(SmemBf<T>{src.base, f.poff[f.nmid]}, f, i, src);
+				src.base = s + seq * f.NPAD();
+				dct3_outer_unit<T>(SmemBf<T, F>{src.base, &f}, f, i, src);
 			}
 		}
 		DSP_SYNC();
-		for (int q = f.nmid - 1; q >= 0; q--) {
+		for (int q = f.NMID() - 1; q >= 0; q--) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, false>(s, nseq, f, q, tid, nthr);
 			DSP_SYNC();
 		}

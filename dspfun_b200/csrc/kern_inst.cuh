@@ -2,6 +2,7 @@
 //   KERN_T (float|double), KERN_SUFFIX (f32|f64), KERN_ROW (1|0), KERN_FAST (1|0)
 #include "dsp_kernels.h"
 #include <vector>
+#include <cstdlib>
 
 #ifndef KERN_ROW_MINB
 #define KERN_ROW_MINB 2
@@ -27,11 +28,23 @@ namespace dsp {
 
 // NB: the element type and the row/fast flags are template parameters so that every translation unit
 // instantiates distinctly named kernels (same-signature templates in different TUs would be merged by the linker).
+// FAST: bit 0 = fast path, bit 1 = forward (fast kernels are specialised on the transform kind),
+// bits 8.. = log2 n when the length is fixed at compile time (FastFixed), 0 = runtime length
 template <class TT, int ROW, int FAST, class L, class S>
 DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int cta, int t0, int t1, int nthr,
                       C2<KERN_T> *smem) {
-	const bool FWD = (FAST & 2) != 0;       // fast kernels are specialised on the transform kind (bit 1 of FAST)
-	(void)FWD;
+#if KERN_FAST
+	if ((FAST >> 8) != 0) {
+		FastFixed<((FAST >> 8) != 0) ? (FAST >> 8) : 8> ff;
+		ff.tw = f.tw; ff.om = f.om; ff.sig = f.sig;
+#if KERN_ROW
+		cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
+#else
+		cta_col_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
+#endif
+		return;
+	}
+#endif
 #if KERN_ROW && KERN_FAST
 	cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, f, l, s, cta, t0, t1, nthr, smem);
 #elif KERN_ROW
@@ -82,6 +95,19 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 	// lean kernels: the only pointwise stage is a multiply (1 unless dsp_dct_fuse_scale set it)
 	const OpMul<KERN_T> lm = {(KERN_T)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(KERN_T)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
 #if KERN_FAST
+	// lean kernels with the length fixed at compile time for the common sizes (float only: FastFixed pads like float)
+	if (!fused && sizeof(KERN_T) == 4 && !getenv("DSP_DCT_NO_FIXED")) {
+		const bool fw = a.kind == DSP_KIND_REDFT10;
+#define DSP_FIXED_CASE(LG)                                                                                                   \
+	case (1 << LG):                                                                                                          \
+		return fw ? launch_t<KERN_T, KERN_ROW, 3 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err) \
+		          : launch_t<KERN_T, KERN_ROW, 1 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
+		switch (f.n) {
+			DSP_FIXED_CASE(8) DSP_FIXED_CASE(9) DSP_FIXED_CASE(10) DSP_FIXED_CASE(11) DSP_FIXED_CASE(12) DSP_FIXED_CASE(13)
+		default: break;
+		}
+#undef DSP_FIXED_CASE
+	}
 	if (a.kind == DSP_KIND_REDFT10) {
 		if (fused) return launch_t<KERN_T, KERN_ROW, 3, OpAny, OpAny>(a, f, lop, sop, grid, block, smem, st, err);
 		return launch_t<KERN_T, KERN_ROW, 3, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
