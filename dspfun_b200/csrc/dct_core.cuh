@@ -125,6 +125,15 @@ DSP_DEV VecOf<double>::type ldg_stream(const VecOf<double>::type *p) {
 template <class V> DSP_DEV V ldg_stream(const V *p) { return *p; }
 #endif
 
+// L2 prefetch of the 128-byte line holding p (no data returned; the transfer overlaps whatever runs next)
+DSP_DEV void prefetch_l2(const void *p) {
+#if DSP_GPU
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+	(void)p;
+#endif
+}
+
 // read-only (LDG) load of a complex table entry
 #if DSP_GPU
 DSP_DEV C2<float> ldg_c2(const C2<float> *p) { const float2 t = __ldg((const float2 *)p); return C2<float>{t.x, t.y}; }
@@ -451,6 +460,7 @@ struct RowArgs {
 	int nlines, lines_per_cta;
 	Outer o;                     // line index -> offsets / coords
 	int ax_slot;                 // coordinate fed by the axis index
+	int pf_dist;                 // > 0: prefetch the input lines of CTA (cta + pf_dist) into L2 while this one computes
 	int simple;                  // line l sits at l * ls_in / l * ls_out (all outer levels collapse to one stride)
 	long long ls_in, ls_out;
 	const void *in;
@@ -596,6 +606,7 @@ struct ColArgs {
 	const void *in;
 	void *out;
 	int vec_in, vec_out;
+	int pf_dist;                 // > 0: prefetch the input tile of CTA (cta + pf_dist) into L2 while this one computes
 };
 
 template <class T, class LoadOp, class StoreOp>

@@ -576,6 +576,17 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 	const int nseq = npairs * d;
 	const uint32_t upseq = (uint32_t)(f.Mq() / 2 + 1);              // outer-pass units per sequence
 
+	// just-in-time L2 prefetch: the lines of the CTA that will take this SM's place (about one resident wave ahead)
+	if (a.pf_dist > 0 && a.simple) {
+		const int pl0 = (cta + a.pf_dist) * a.lines_per_cta;
+		const int lines128 = (f.N() * d * (int)sizeof(T) + 127) / 128;
+		for (int tid = t0; tid < t1; tid++)
+			for (int i = tid; i < a.lines_per_cta * lines128; i += nthr) {
+				const int l = pl0 + i / lines128;
+				if (l < a.nlines) prefetch_l2((const char *)gin + ((long long)l * a.ls_in) * (long long)sizeof(T) + (long long)(i % lines128) * 128);
+			}
+	}
+
 	if (FWD) {
 		for (int tid = t0; tid < t1; tid++) row_move_any<T, true, LoadOp>(a, f, lop, line0, nl, tid, nthr, s);
 		DSP_SYNC();
@@ -829,6 +840,20 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const F &f, const LoadOp &lop, const
 	Coord cbase = {0, 0, 0, 0, 0};
 	long long ibase, obase;
 	outer_decode(a.o, oidx, ibase, obase, cbase);
+
+	// just-in-time L2 prefetch of the tile that will follow on this SM: one 128-byte line per axis position covers
+	// 32 columns, so only every (32 / tc)-th tile issues it
+	if (a.pf_dist > 0) {
+		const int pcta = cta + a.pf_dist;
+		const int tpl = 32 / a.tc > 0 ? 32 / a.tc : 1;
+		const uint32_t po = fd_div((uint32_t)pcta, a.dtiles);
+		const int ptile = pcta - (int)po * a.ntiles;
+		if (po == oidx && ptile < a.ntiles && (ptile % tpl) == 0) {
+			const char *pb = (const char *)a.in + (ibase + (long long)ptile * a.tc) * (long long)sizeof(T);
+			for (int tid = t0; tid < t1; tid++)
+				for (int r = tid; r < f.N(); r += nthr) prefetch_l2(pb + (long long)r * a.ax_is * (long long)sizeof(T));
+		}
+	}
 
 	// ---- copy-in: DCT-II scatters through sig, DCT-III keeps natural order
 	for (int tid = t0; tid < t1; tid++) col_move_any<T, true, LoadOp>(a, f, lop, FWD, false, col0, ncl, ibase, cbase, tid, nthr, s);

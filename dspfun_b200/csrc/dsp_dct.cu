@@ -224,6 +224,7 @@ struct PassPlan {
 	ColArgs ca;
 	int grid, block;
 	size_t smem;
+	int pf_dist;                             // CTAs ahead whose input gets prefetched into L2 (0 = off)
 	bool vec_in_layout, vec_out_layout;
 	OpAny lop, sop;
 	bool fused;
@@ -454,6 +455,15 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		// one CTA per SM (big tile): run it with 512 threads; otherwise 256 and rely on several CTAs per SM
 		pp.block = (pp.fast && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;
 		if (pp.fast && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
+		{
+			// one resident wave ahead: CTAs per SM by shared memory (<= 2 by registers for the fast kernels) x 148 SMs
+			int per_sm = (int)((kMaxSmem) / (pp.smem ? pp.smem : 1));
+			if (per_sm > 2) per_sm = 2;
+			if (per_sm < 1) per_sm = 1;
+			pp.pf_dist = pp.fast ? per_sm * 148 : 0;
+			if (getenv("DSP_DCT_PF")) pp.pf_dist = atoi(getenv("DSP_DCT_PF"));
+			if (pp.pf_dist >= pp.grid) pp.pf_dist = 0;
+		}
 		DSP_TRACE("pass %zu: %s%s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d panel=%d tcA=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", pp.split ? "(split)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid, pp.sp_P, pp.sp_tc);
 		P->passes.push_back(pp);
 	}
@@ -469,6 +479,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain && !a.in_u8; a.vec_out = pp.vec_out_layout && aout && !a.out_u8;
+		a.pf_dist = pp.pf_dist;
 		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
@@ -528,6 +539,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
+		a.pf_dist = pp.pf_dist;
 		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
