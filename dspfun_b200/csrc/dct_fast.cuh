@@ -52,7 +52,8 @@ template <int LG> struct FastFixed {
 	DSP_HDM constexpr int Mq() const { return 1 << (LG - 4); }
 	DSP_HDM constexpr int R0() const { return 1 << kL0; }
 	DSP_HDM constexpr int NMID() const { return kK; }
-	DSP_HDM constexpr int NPAD() const { return padc((1 << LG) - 1) + 1; }
+	static constexpr int kNpad0 = (1 << LG) - 1 + (((1 << LG) - 1) >> 4) + (((1 << LG) - 1) >> 8) + (((1 << LG) - 1) >> 12) + 1;
+	DSP_HDM constexpr int NPAD() const { return kNpad0 + ((17 - kNpad0 % 16) % 16); }   // == 1 (mod 16), as the planner pads
 	DSP_HDM constexpr int PO(int q, int j) const { return padc(j * ((1 << kL0) << (4 * q))); }
 	DSP_DEVM uint32_t divHalf(uint32_t u) const { return u / (uint32_t)((1 << (LG - 4)) / 2 + 1); }
 };

@@ -33,6 +33,7 @@ struct SplitArgs {
 	int pcol0, pcols;            // panel column range [pcol0, pcol0 + pcols)
 	int tc, ntiles;              // sub-pass A: columns per CTA, tiles per panel
 	int ngroups;                 // sub-pass B: 32-pair column groups per panel
+	int pf_warps;                // inverse sub-pass B': L2 prefetch distance in warps (0 = off)
 };
 
 DSP_DEV int split_row(int e, int n) { return e < n / 2 ? 2 * e : 2 * (n - 1 - e) + 1; }   // inverse Makhoul: row holding v[e]
@@ -216,6 +217,18 @@ template <class T, class Op> struct GlobalCols {
 template <class T, bool FWD, class LoadOp, class StoreOp>
 DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const LoadOp &lop, const StoreOp &sop, int gwarp, int lane) {
 	const int group = gwarp % a.ngroups, i = gwarp / a.ngroups;
+	if (!FWD && a.pf_warps > 0) {
+		// the inverse reads 32 strided image rows per thread straight from DRAM: prefetch, one resident wave of warps
+		// ahead, the 2 x 16 row segments (256 B each) the warp `gwarp + pf_warps` is going to load
+		const int pw = gwarp + a.pf_warps;
+		const int pg = pw % a.ngroups, pi = pw / a.ngroups;
+		if (pi <= a.M / 2) {
+			const int prow = (lane < 16 ? pi : (pi == 0 ? 0 : a.M - pi)) + a.M * (lane & 15);
+			const char *pp = (const char *)((const T *)a.in + (long long)prow * a.ax_is + a.pcol0 + 64 * pg);
+			prefetch_l2(pp);
+			prefetch_l2(pp + 128);
+		}
+	}
 	if (i > a.M / 2) return;
 	const int pair = group * 32 + lane;
 	const int col = a.pcol0 + 2 * pair;

@@ -93,6 +93,12 @@ template <class T> static Tables *build_tables(int n) {
 	t->pos2 = t->pos3 = nullptr;
 	t->dense = false; t->half = 0; t->ctab = nullptr; t->sig = nullptr;
 	t->npad = pad_of<T>(n - 1) + 1;
+	// sequence stride == 1 (mod 16 complex floats / 8 complex doubles): the column kernels write the same slot of
+	// neighbouring sequences from neighbouring lanes, and an even multiple of 128 B would put them all in one bank
+	{
+		const int m = sizeof(T) == 4 ? 16 : 8;
+		while (t->npad % m != 1) t->npad++;
+	}
 	if (!factorize(n, t->fac)) {
 		// a prime factor > 13: direct evaluation of the definition (O(n^2) per line, exact same results contract)
 		t->dense = true;
@@ -509,6 +515,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 			sa.ax_slot = c.ax_slot; sa.col_slot = c.col_slot;
 			sa.in = (const char *)in + ioff * P->es; sa.out = (char *)out + ooff * P->es; sa.scratch = P->d_split;
 			sa.tc = pp.sp_tc;
+			sa.pf_warps = getenv("DSP_DCT_PFW") ? atoi(getenv("DSP_DCT_PFW")) : 148 * 16;
 			const int npanels = (c.ncols + pp.sp_P - 1) / pp.sp_P;
 			for (int pi = 0; pi < npanels && ok; pi++) {
 				// the inverse walks the panels backwards: a forward+inverse round trip then starts on the columns the
