@@ -558,9 +558,76 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const F &f, const Op &op, int li
 	}
 }
 
+// channel-interleaved float lines (D = 2..4 channels, 16-byte access legal, n % 4 == 0): one group = x in [4q, 4q+4)
+// of lines A and B = D vectors per line; the slot pattern per channel is the planar one.
+template <class T, int D, bool FWD, class Op, class F>
+DSP_DEV void row_move_inter4(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
+	typedef typename VecOf<T>::type Vec;
+	const T *gin = (const T *)a.in;
+	T *gout = (T *)a.out;
+	const int n = f.N();
+	const int lgq = ilog2(n) - 2;                             // log2 (groups per line)
+	const int npairs = (nl + 1) / 2;
+	const int total = npairs << lgq;
+	const int padM = f.PO(f.NMID(), 1);
+	for (int idx = tid; idx < total; idx += nthr) {
+		const int g = idx >> lgq, q = idx & ((1 << lgq) - 1);
+		const int la = line0 + 2 * g;
+		const bool hasb = 2 * g + 1 < nl;
+		Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
+		long long ia, ib = 0, oa, ob = 0;
+		if (a.simple && !Op::kNeedsCoord) { ia = la * a.ls_in; ib = ia + a.ls_in; oa = la * a.ls_out; ob = oa + a.ls_out; }
+		else { outer_decode(a.o, (uint32_t)la, ia, oa, ca); if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb); }
+		T va[4 * D], vb[4 * D];
+		if (FWD) {
+#pragma unroll
+			for (int v = 0; v < D; v++) {
+				const Vec ta = ldg_stream((const Vec *)(gin + ia + 4 * D * q + 4 * v));
+#pragma unroll
+				for (int t = 0; t < 4; t++) va[4 * v + t] = ta.v[t];
+				if (hasb) {
+					const Vec tb = ldg_stream((const Vec *)(gin + ib + 4 * D * q + 4 * v));
+#pragma unroll
+					for (int t = 0; t < 4; t++) vb[4 * v + t] = tb.v[t];
+				} else {
+#pragma unroll
+					for (int t = 0; t < 4; t++) vb[4 * v + t] = 0;
+				}
+			}
+		}
+		const int s0 = (int)DSP_LDG(f.sig + 2 * q), s1 = (int)DSP_LDG(f.sig + n - 2 - 2 * q);
+		const int slot[4] = {s0, s1 + padM, s0 + padM, s1};       // x = 4q, 4q+1, 4q+2, 4q+3
+		C2<T> *sg = s + g * D * f.NPAD();
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+#pragma unroll
+			for (int ch = 0; ch < D; ch++) {
+				ca.set(a.ax_slot, 4 * q + t); ca.ch = ch; cb.set(a.ax_slot, 4 * q + t); cb.ch = ch;
+				C2<T> *p = sg + ch * f.NPAD() + slot[t];
+				if (FWD) *p = C2<T>{op(va[t * D + ch], ca), hasb ? op(vb[t * D + ch], cb) : (T)0};
+				else { const C2<T> z = *p; va[t * D + ch] = op(z.x, ca); vb[t * D + ch] = op(-z.y, cb); }
+			}
+		}
+		if (!FWD) {
+#pragma unroll
+			for (int v = 0; v < D; v++) {
+				Vec ra, rb;
+#pragma unroll
+				for (int t = 0; t < 4; t++) { ra.v[t] = va[4 * v + t]; rb.v[t] = vb[4 * v + t]; }
+				*(Vec *)(gout + oa + 4 * D * q + 4 * v) = ra;
+				if (hasb) *(Vec *)(gout + ob + 4 * D * q + 4 * v) = rb;
+			}
+		}
+	}
+}
+
 template <class T, bool FWD, class Op, class F>
 DSP_DEV void row_move_any(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
-	if (sizeof(T) == 4 && a.d == 1 && (FWD ? a.vec_in : a.vec_out) && f.N() >= 4) row_move_planar4<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
+	const bool al = (FWD ? a.vec_in : a.vec_out) && f.N() >= 4;
+	if (sizeof(T) == 4 && a.d == 1 && al) row_move_planar4<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
+	else if (sizeof(T) == 4 && a.d == 3 && al) row_move_inter4<T, 3, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
+	else if (sizeof(T) == 4 && a.d == 2 && al) row_move_inter4<T, 2, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
+	else if (sizeof(T) == 4 && a.d == 4 && al) row_move_inter4<T, 4, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 	else row_move<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 }
 
