@@ -369,10 +369,20 @@ def main():
                          "achieved_gbs": 2 * es * s["samples"] / (avg_ms * 1e-3) / 1e9})
     dom = max(kern, key=lambda k: k["avg_ms"]) if kern else None
     roofline = None
+    traffic = None
+    if dom:
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if recorded
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]))
+            if traffic is not None and planes != WORKLOADS[args.workload][3]:
+                traffic = traffic * planes / WORKLOADS[args.workload][3]
+        except Exception:
+            traffic = None
     if dom:
         roofline = {"bound": "hbm", "kernel": "%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]),
                     "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["achieved_gbs"] / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": 2 * es * samples_per_step,
                     "round_trip_frac": (4 * es * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak}
 

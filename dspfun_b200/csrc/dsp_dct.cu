@@ -788,6 +788,7 @@ int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out) {
 	out->block = pp.block;
 	out->smem_bytes = pp.smem;
 	out->samples = p->samples_per_launch;
+	out->split_panels = pp.split ? (pp.ca.ncols + pp.sp_P - 1) / pp.sp_P : 0;
 #if DSP_GPU
 	std::vector<cudaEvent_t> keep;
 	std::vector<int> keep_pass;

@@ -95,9 +95,9 @@ class Plan:
         for i in range(self.lib.dsp_dct_num_passes(self._h)):
             st = capi.PassStat()
             self._check(self.lib.dsp_dct_pass_stat_get(self._h, i, ctypes.byref(st)))
-            out.append(dict(kernel="row" if st.is_row else "col", axis=st.axis, n=st.n, grid=st.grid, block=st.block,
+            out.append(dict(kernel="row" if st.is_row else ("col-split" if st.split_panels else "col"), axis=st.axis, n=st.n, grid=st.grid, block=st.block,
                             smem_bytes=int(st.smem_bytes), launches=st.launches, ms_total=st.ms_total,
-                            samples=st.samples))
+                            samples=st.samples, split_panels=st.split_panels))
         return out
 
     def destroy(self):

@@ -100,6 +100,8 @@ typedef struct {
 	int launches;        /* launches accumulated */
 	double ms_total;     /* their summed device time */
 	double samples;      /* scalar samples one launch reads and writes */
+	int split_panels;    /* > 0: the pass runs as two sub-kernels per column panel (this many panels per plane);
+	                        `launches` then counts passes, not sub-kernel launches */
 } dsp_dct_pass_stat;
 int dsp_dct_profile(dsp_dct_plan p, int enable);
 int dsp_dct_num_passes(dsp_dct_plan p);
