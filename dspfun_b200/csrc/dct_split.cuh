@@ -34,6 +34,7 @@ struct SplitArgs {
 	int tc, ntiles;              // sub-pass A: columns per CTA, tiles per panel
 	int ngroups;                 // sub-pass B: 32-pair column groups per panel
 	int pf_warps;                // inverse sub-pass B': L2 prefetch distance in warps (0 = off)
+	int tci, ntilesi;            // DIT-style inverse, tile sub-pass: columns per CTA (16), tiles per panel
 };
 
 DSP_DEV int split_row(int e, int n) { return e < n / 2 ? 2 * e : 2 * (n - 1 - e) + 1; }   // inverse Makhoul: row holding v[e]
@@ -258,6 +259,140 @@ DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const Lo
 		src.ax_slot = a.ax_slot; src.ca = ca; src.cb = cb; src.op = &lop;
 		dct3_outer_unit<T>(bf, fN, i, src);
 	}
+}
+
+// ================================================================================================ DIT-style inverse
+// DCT-III with the *tile* kernel first and the register kernel last (the efficient order, like the forward split):
+//   A'') per column pair, sub-sequences w_j[k'] = W[16 k' + j] of the pre-twiddled spectrum W (dct3_pair) and their
+//        M-point DIT FFTs G_j.  The pre-twiddle pairs k with n-k, i.e. element k' of sub-sequence j with element
+//        M-1-k' of sub-sequence 16-j (j = 0: k' with M-k'; j = 8: k' with M-1-k'), so one CTA owns the sub-sequence
+//        pair (j, 16-j) of a 16-column tile: 2 x 8 sequences x M.  G_j goes to scratch block j.
+//   B'') F[i + M m] = sum_j W_n^{ij} W_16^{jm} G_j[i]: one plain radix-16 DIT butterfly per thread, lanes along the
+//        columns, output sample e = i + M m stored (re, -im) to image row split_row(e).
+struct RowSubseq { int j; DSP_DEVM int operator()(int r) const { return 16 * r + j; } };
+
+// pre-twiddle of one (k, n-k) pair held in two smem slots (pk holds X[k], pn holds X[n-k]; any order of k vs n/2)
+template <class T>
+DSP_DEV void split_pretw(const C2<T> *om, int k, int n, C2<T> *pk, C2<T> *pn) {
+	if (2 * k <= n) {
+		C2<T> wk, wn;
+		dct3_pair<T>(ldg_c2(om + k), *pk, *pn, wk, wn);
+		*pk = wk; *pn = wn;
+	} else {
+		C2<T> wk, wn;
+		dct3_pair<T>(ldg_c2(om + (n - k)), *pn, *pk, wk, wn);
+		*pn = wk; *pk = wn;
+	}
+}
+
+template <class T, class LoadOp>
+DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const LoadOp &lop, int cta, int t0,
+                               int t1, int nthr, C2<T> *s) {
+	const int M = a.M, n = a.n;
+	const int jj = cta / a.ntilesi, tile = cta - jj * a.ntilesi;          // jj = 0..8
+	const int col0 = a.pcol0 + tile * a.tci;
+	const int nq = a.tci / 2;                                             // complex sequences per sub-sequence
+	const bool paired = jj != 0 && jj != 8;
+	const int ja = jj, jb = 16 - jj;
+	const int nseq = paired ? 2 * nq : nq;
+	const int lg = ilog2(a.tci / 4);
+	const C2<T> *om = (const C2<T> *)fN.om;
+	C2<T> *sA = s, *sB = s + nq * fM.npad;
+	const T *gin = (const T *)a.in + col0;
+	// ---- load both rows of every (k, n-k) pair, pre-twiddle in registers, store to the digit-reversed slots
+	//      (element k' of sub-sequence ja pairs with element kb of sub-sequence jb; for the single sub-sequences 0 and 8
+	//      both live in the same sequence set)
+	typedef VecW<T, 4> Vec;
+	const int UNR = 4;
+	const int npair = paired ? M : (jj == 0 ? M / 2 + 1 : M / 2);
+	C2<T> *sBB = paired ? sB : sA;
+	for (int tid = t0; tid < t1; tid++) {
+		const int cg = tid & ((1 << lg) - 1), dk = nthr >> lg;
+		const T *gp = gin + 4 * cg;
+		C2<T> *qa = sA + (2 * cg) * fM.npad, *qb = sBB + (2 * cg) * fM.npad;
+		for (int k0 = tid >> lg; k0 < npair; k0 += dk * UNR) {
+			Vec va[UNR], vb[UNR];
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int kp = k0 + u * dk;
+				if (kp < npair) {
+					const int kb = paired ? M - 1 - kp : (jj == 0 ? (kp == 0 ? 0 : M - kp) : M - 1 - kp);
+					va[u] = ldg_stream((const Vec *)(gp + (long long)(16 * kp + ja) * a.ax_is));
+					vb[u] = ldg_stream((const Vec *)(gp + (long long)(16 * kb + (paired ? jb : ja)) * a.ax_is));
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int kp = k0 + u * dk;
+				if (kp < npair) {
+					const int kb = paired ? M - 1 - kp : (jj == 0 ? (kp == 0 ? 0 : M - kp) : M - 1 - kp);
+					const int k = 16 * kp + ja;                       // k <= n - k may or may not hold for paired CTAs
+					const int sk = (int)DSP_LDG(fM.sig + kp), sn = (int)DSP_LDG(fM.sig + kb);
+					const Coord cz = {0, 0, 0, 0, 0};
+					const bool self = !paired && kb == kp;            // k = 0 (jj = 0, kp = 0) or k = n/2 (jj = 0, kp = M/2)
+					const C2<T> w = ldg_c2(om + (2 * k <= n ? k : n - k));
+#pragma unroll
+					for (int p = 0; p < 2; p++) {
+						const C2<T> xa = C2<T>{lop(va[u].v[2 * p], cz), lop(va[u].v[2 * p + 1], cz)};
+						const C2<T> xb = C2<T>{lop(vb[u].v[2 * p], cz), lop(vb[u].v[2 * p + 1], cz)};
+						C2<T> wk, wn;
+						if (self && k == 0) { qa[p * fM.npad + sk] = C2<T>{xa.x, -xa.y}; continue; }
+						if (2 * k <= n) { dct3_pair<T>(w, xa, xb, wk, wn); qa[p * fM.npad + sk] = wk; if (!self) qb[p * fM.npad + sn] = wn; }
+						else { dct3_pair<T>(w, xb, xa, wk, wn); qb[p * fM.npad + sn] = wk; qa[p * fM.npad + sk] = wn; }
+					}
+				}
+			}
+		}
+	}
+	DSP_SYNC();
+	// ---- M-point DIT FFTs
+	contig_pass<T>(s, nseq, fM, t0, t1, nthr);
+	for (int q = 0; q <= fM.nmid; q++) {
+		for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, fM, q, tid, nthr);
+		DSP_SYNC();
+	}
+	// ---- natural-order results to scratch blocks j (and 16 - j)
+	T *gs = (T *)a.scratch + (col0 - a.pcol0);
+	for (int tid = t0; tid < t1; tid++) {
+		tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{ja * M}, SlotNat<T>(), fM.npad, tid, nthr, sA);
+		if (paired) tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{jb * M}, SlotNat<T>(), fM.npad, tid, nthr, sB);
+	}
+}
+
+template <class T, class StoreOp>
+DSP_DEV void split_inv_outer_thread(const SplitArgs &a, const FastDesc &fN, const StoreOp &sop, int gwarp, int lane) {
+	const int group = gwarp % a.ngroups, i = gwarp / a.ngroups;
+	if (i >= a.M) return;
+	const int pair = group * 32 + lane;
+	const int col = a.pcol0 + 2 * pair;
+	if (col >= a.pcol0 + a.pcols) return;
+	const bool hasb = col + 1 < a.pcol0 + a.pcols;
+	const C2<T> *g0 = (const C2<T> *)a.scratch + pair + (long long)i * (a.ax_ss / 2);
+	const long long js = (long long)a.M * (a.ax_ss / 2);
+	C2<T> v[16], w[16];
+#pragma unroll
+	for (int j = 0; j < 16; j++) v[j] = g0[j * js];
+	if (i != 0) {
+		tw_powers<T>((const C2<T> *)fN.tw, i, w);
+#pragma unroll
+		for (int j = 1; j < 16; j++) v[j] = cmul(v[j], w[j]);
+	}
+	Dft<T, 16>::run(v);
+	GlobalCols<T, StoreOp> sink;
+	sink.p = (T *)a.out + col; sink.rs = a.ax_os; sink.hasb = hasb;
+	sink.vec = hasb && (a.ax_os % 2) == 0 && (((size_t)a.out / sizeof(T) + col) % 2) == 0;
+	sink.ax_slot = a.ax_slot; sink.op = &sop;
+	sink.ca = a.cbase; sink.cb = a.cbase;
+	{
+		int x = col, ch = 0;
+		if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
+		sink.ca.set(a.col_slot, x); sink.ca.ch = ch;
+		x = col + 1; ch = 0;
+		if (a.d != 1) { x = (int)fd_div((uint32_t)(col + 1), a.dd); ch = col + 1 - x * a.d; }
+		sink.cb.set(a.col_slot, x); sink.cb.ch = ch;
+	}
+#pragma unroll
+	for (int m = 0; m < 16; m++) sink.put(split_row(i + a.M * m, a.n), v[m].x, -v[m].y);
 }
 
 }  // namespace dsp

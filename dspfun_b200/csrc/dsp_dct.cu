@@ -238,7 +238,8 @@ struct PassPlan {
 	bool split;
 	FastDesc ffM;
 	int sp_P, sp_tc;
-	size_t sp_smem;
+	size_t sp_smem, sp_smem_inv;
+	bool sp_force_inv;                       // DSP_DCT_SPLIT_MIN given: use the DIF-style split inverse (experiments)
 };
 
 }  // namespace dsp
@@ -347,7 +348,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		const bool wide = d > 4;
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
-		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0;
+		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0; pp.sp_smem_inv = 0; pp.sp_force_inv = false;
 		memset(&pp.ffM, 0, sizeof(pp.ffM));
 		memset(&pp.ff, 0, sizeof(pp.ff));
 		if (pp.fast) fill_fast(pp.ff, t);
@@ -435,7 +436,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			if (getenv("DSP_DCT_SPLIT_MIN")) { split_min = atoi(getenv("DSP_DCT_SPLIT_MIN")); split_inv = true; }
 			const int nn = P->n[ax];
 			if (pp.fast && P->prec == 'f' && nn >= split_min && nn >= 256 && vin && vout && !lastax &&
-			    (split_inv || P->kind[ax] == DSP_DCT_REDFT10)) {
+			    (split_inv || P->kind[ax] == DSP_DCT_REDFT10 || (A.ncols % 16) == 0)) {
 				Tables *tM = get_tables(nn / 16, P->prec);
 				if (tM && tM->sig) {
 					pp.split = true;
@@ -452,6 +453,8 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 					while (stc > VN && (size_t)(stc / 2) * seqM > 72 * 1024) stc /= 2;
 					pp.sp_tc = stc;
 					pp.sp_smem = (size_t)(stc / 2) * seqM;
+					pp.sp_force_inv = split_inv;
+					pp.sp_smem_inv = 2 * (size_t)(16 / 2) * seqM;               // DIT-style inverse: sub-sequence pair of a 16-column tile
 					const size_t need = (size_t)nn * (size_t)pw * (size_t)P->es;
 					if (need > P->split_bytes) P->split_bytes = need;
 				}
@@ -492,7 +495,8 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 #endif
 		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
 		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
-	} else if (pp.split && ain && aout) {
+	} else if (pp.split && ain && aout &&
+	           (pp.ca.kind == DSP_KIND_REDFT10 || pp.sp_force_inv || (!pp.fused && (pp.ca.ncols % 16) == 0 && !getenv("DSP_DCT_NO_SPLIT_INV")))) {
 		// per outer index (batch / frame) and per column panel: sub-pass A then B (forward) or B' then A' (inverse)
 		const ColArgs &c = pp.ca;
 		const bool fwd = c.kind == DSP_KIND_REDFT10;
@@ -534,7 +538,12 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					const int ncols = c.ncols - nc0 < pp.sp_P ? c.ncols - nc0 : pp.sp_P;
 					ok = launch_l2_prefetch((const char *)sa.in + (size_t)nc0 * P->es, sa.ax_is * P->es, c.f.n, ncols * P->es, st, g_err);
 				}
-				if (ok && fwd) ok = launch_split_fft_f32(sa, pp.ffM, pp.fused, pp.lop, pp.sop, gridA, pp.sp_smem, st, g_err) &&
+				const bool dit_inv = !fwd && !pp.sp_force_inv;
+				if (ok && dit_inv) {
+					sa.tci = 16; sa.ntilesi = (sa.pcols + 15) / 16;
+					ok = launch_split_inv_fft_f32(sa, pp.ffM, pp.ff, pp.lop, sa.ntilesi * 9, pp.sp_smem_inv, st, g_err) &&
+					     launch_split_inv_outer_f32(sa, pp.ff, pp.sop, sa.ngroups * M, st, g_err);
+				} else if (ok && fwd) ok = launch_split_fft_f32(sa, pp.ffM, pp.fused, pp.lop, pp.sop, gridA, pp.sp_smem, st, g_err) &&
 				              launch_split_outer_f32(sa, pp.ff, pp.fused, pp.lop, pp.sop, warpsB, st, g_err);
 				else if (ok) ok = launch_split_outer_f32(sa, pp.ff, pp.fused, pp.lop, pp.sop, warpsB, st, g_err) &&
 				          launch_split_fft_f32(sa, pp.ffM, pp.fused, pp.lop, pp.sop, gridA, pp.sp_smem, st, g_err);
