@@ -264,8 +264,15 @@ struct dsp_dct_plan_s {
 	double *d_scalars;                       // acc[4] | scale_z[4] | dc_out[4]
 	unsigned char *d_signmap;
 	void *d_work;                            // T scratch the passes run in when the final store is 8-bit
-	void *d_split;                           // panel scratch of the split column passes
+	void *d_split;                           // panel scratch of the split column passes (nscratch parts: panels rotate)
 	size_t split_bytes;
+	int nscratch;
+#if DSP_GPU
+	cudaStream_t aux[4];                     // panels rotate over a few streams so that one panel's tail and launch
+	cudaEvent_t ev_fork, ev_join[4];         // gaps are filled by the next panels' kernels
+	bool aux_ok;
+	int naux;
+#endif
 	bool need_acc;
 	rt_stream last_stream;
 	// per-pass profiling
@@ -476,7 +483,19 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		DSP_TRACE("pass %zu: %s%s%s axis=%d n=%d grid=%d smem=%zu vec=%d/%d r0=%d nmid=%d panel=%d tcA=%d", pi, pp.row ? "row" : "col", pp.fast ? "(fast)" : "", pp.split ? "(split)" : "", ax, P->n[ax], pp.grid, pp.smem, (int)vin, (int)vout, pp.ff.r0, pp.ff.nmid, pp.sp_P, pp.sp_tc);
 		P->passes.push_back(pp);
 	}
-	if (P->split_bytes && !rt_malloc(&P->d_split, P->split_bytes, g_err)) return false;
+	int naux = 2;
+	if (getenv("DSP_DCT_NAUX")) { naux = atoi(getenv("DSP_DCT_NAUX")); if (naux < 1) naux = 1; if (naux > 4) naux = 4; }
+	P->nscratch = naux;
+	if (P->split_bytes && !rt_malloc(&P->d_split, (size_t)naux * P->split_bytes, g_err)) return false;
+#if DSP_GPU
+	P->naux = naux;
+	if (P->split_bytes && !getenv("DSP_DCT_NO_AUX")) {
+		P->aux_ok = cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+		for (int k = 0; k < naux; k++)
+			P->aux_ok = P->aux_ok && cudaStreamCreateWithFlags(&P->aux[k], cudaStreamNonBlocking) == cudaSuccess &&
+			            cudaEventCreateWithFlags(&P->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+	}
+#endif
 	return true;
 }
 
@@ -504,6 +523,14 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		for (int k = 0; k < 4; k++) no *= c.o.cnt[k];
 		const int M = c.f.n / 16;
 		ok = true;
+		rt_stream pst[4] = {st, st, st, st};
+		long long panel_no = 0;
+#if DSP_GPU
+		if (P->aux_ok) {
+			cudaEventRecord(P->ev_fork, st);
+			for (int k = 0; k < P->naux; k++) { cudaStreamWaitEvent(P->aux[k], P->ev_fork, 0); pst[k] = P->aux[k]; }
+		}
+#endif
 		for (long long oi = 0; oi < no && ok; oi++) {
 			long long rem = oi, ioff = 0, ooff = 0;
 			SplitArgs sa;
@@ -525,6 +552,9 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 				// the inverse walks the panels backwards: a forward+inverse round trip then starts on the columns the
 				// forward pass touched last, which are the ones still resident in L2
 				const int pn = fwd ? pi : npanels - 1 - pi;
+				const int half = (int)(panel_no++ % P->nscratch);
+				rt_stream st = pst[half];                       // shadows the caller's stream for this panel's launches
+				sa.scratch = (char *)P->d_split + (size_t)half * P->split_bytes;
 				sa.pcol0 = pn * pp.sp_P;
 				sa.pcols = c.ncols - sa.pcol0 < pp.sp_P ? c.ncols - sa.pcol0 : pp.sp_P;
 				sa.ntiles = (sa.pcols + sa.tc - 1) / sa.tc;
@@ -551,6 +581,10 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 			}
 		}
 		if (ok) g_launches--;                  // the caller adds one
+#if DSP_GPU
+		if (P->aux_ok)
+			for (int k = 0; k < P->naux; k++) { cudaEventRecord(P->ev_join[k], P->aux[k]); cudaStreamWaitEvent(st, P->ev_join[k], 0); }
+#endif
 	} else {
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
@@ -635,6 +669,10 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->d_work = nullptr;
 	P->d_split = nullptr;
 	P->split_bytes = 0;
+	P->nscratch = 1;
+#if DSP_GPU
+	P->aux_ok = false;
+#endif
 	P->need_acc = false;
 	P->last_stream = 0;
 	P->profiling = false;
@@ -747,6 +785,10 @@ void dsp_dct_destroy(dsp_dct_plan p) {
 	rt_free(p->d_work);
 	rt_free(p->d_split);
 #if DSP_GPU
+	if (p->aux_ok) {
+		cudaEventDestroy(p->ev_fork);
+		for (int k = 0; k < p->naux; k++) { cudaStreamDestroy(p->aux[k]); cudaEventDestroy(p->ev_join[k]); }
+	}
 	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
 #endif
 	delete p;
