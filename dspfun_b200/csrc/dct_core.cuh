@@ -105,6 +105,19 @@ struct Coord {
 // ------------------------------------------------------------------------------------------------ complex helpers
 template <class T> DSP_DEV C2<T> cadd(C2<T> a, C2<T> b) { return C2<T>{a.x + b.x, a.y + b.y}; }
 template <class T> DSP_DEV C2<T> csub(C2<T> a, C2<T> b) { return C2<T>{a.x - b.x, a.y - b.y}; }
+#if defined(__CUDA_ARCH__) && !defined(DSP_NO_F32X2)
+// sm_100 packed fp32: one FADD2 per complex add / subtract (same rounding per component as FADD; the negation of
+// the subtrahend folds into the instruction's operand modifier).  The butterflies are issue-bound, and adds are
+// ~80% of their arithmetic, so this is the cheapest way to retire fewer instructions per sample.
+template <> DSP_DEV C2<float> cadd<float>(C2<float> a, C2<float> b) {
+	const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+	return C2<float>{r.x, r.y};
+}
+template <> DSP_DEV C2<float> csub<float>(C2<float> a, C2<float> b) {
+	const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+	return C2<float>{r.x, r.y};
+}
+#endif
 template <class T> DSP_DEV C2<T> cmul(C2<T> a, C2<T> b) { return C2<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 template <class T> DSP_DEV C2<T> cmulc(C2<T> a, T br, T bi) { return C2<T>{a.x * br - a.y * bi, a.x * bi + a.y * br}; }
 template <class T> DSP_DEV C2<T> mul_mi(C2<T> a) { return C2<T>{a.y, -a.x}; }   // a * (-i)
@@ -491,14 +504,14 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 
 	// ---- copy-in
 	for (int tid = t0; tid < t1; tid++) {
-		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)npairs * gpl; idx += (uint32_t)nthr) {
-			const uint32_t g = idx / gpl, q = idx - g * gpl;
-			const int la = line0 + 2 * (int)g;
-			const bool hasb = (2 * (int)g + 1) < nl;
+		for (int g = 0; g < npairs; g++) {                    // the line decode is per pair, not per vector
+			const int la = line0 + 2 * g;
+			const bool hasb = (2 * g + 1) < nl;
 			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
+		for (uint32_t q = (uint32_t)tid; q < gpl; q += (uint32_t)nthr) {
 			const int e0 = (int)q * VN;
 			T va[VecOf<T>::N], vb[VecOf<T>::N];
 			if (a.vec_in && e0 + VN <= llen) {
@@ -527,15 +540,16 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 			for (int t = 0; t < VN; t++) {
 				const int e = e0 + t;
 				if (e < llen) {
-					const int x = (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
+					const int x = d == 1 ? e : (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
 					ca.set(a.ax_slot, x); ca.ch = ch;
 					cb.set(a.ax_slot, x); cb.ch = ch;
 					const T pa = lop(va[t], ca);
 					const T pb = hasb ? lop(vb[t], cb) : (T)0;
 					const int slot = (fwd && !a.f.dense) ? ((x & 1) ? n - 1 - (x >> 1) : (x >> 1)) : x;
-					s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + Pad<T>::of(slot)] = C2<T>{pa, pb};
+					s[(size_t)(g * d + ch) * (size_t)a.f.npad + Pad<T>::of(slot)] = C2<T>{pa, pb};
 				}
 			}
+		}
 		}
 	}
 	DSP_SYNC();
@@ -546,14 +560,14 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
 	for (int tid = t0; tid < t1; tid++) {
-		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)npairs * gpl; idx += (uint32_t)nthr) {
-			const uint32_t g = idx / gpl, q = idx - g * gpl;
-			const int la = line0 + 2 * (int)g;
-			const bool hasb = (2 * (int)g + 1) < nl;
+		for (int g = 0; g < npairs; g++) {
+			const int la = line0 + 2 * g;
+			const bool hasb = (2 * g + 1) < nl;
 			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
+		for (uint32_t q = (uint32_t)tid; q < gpl; q += (uint32_t)nthr) {
 			const int e0 = (int)q * VN;
 			Vec ra, rb;
 #pragma unroll
@@ -561,8 +575,8 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 				const int e = e0 + t;
 				ra.v[t] = 0; rb.v[t] = 0;
 				if (e >= llen) continue;
-				const int x = (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
-				const C2<T> z = s[(size_t)((int)g * d + ch) * (size_t)a.f.npad + (a.f.dense ? a.f.half : 0) + Pad<T>::of((int)DSP_LDG(pos + x))];
+				const int x = d == 1 ? e : (int)fd_div((uint32_t)e, a.dd), ch = e - x * d;
+				const C2<T> z = s[(size_t)(g * d + ch) * (size_t)a.f.npad + (a.f.dense ? a.f.half : 0) + Pad<T>::of((int)DSP_LDG(pos + x))];
 				ca.set(a.ax_slot, x); ca.ch = ch;
 				cb.set(a.ax_slot, x); cb.ch = ch;
 				ra.v[t] = sop(z.x, ca);
@@ -585,6 +599,7 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 						}
 					}
 			}
+		}
 		}
 	}
 }
@@ -624,6 +639,8 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	if (ncl > a.tc) ncl = a.tc;
 	const int nseq = (ncl + 1) / 2;
 	const uint32_t gpr = (uint32_t)((ncl + VN - 1) / VN);    // vector groups per axis position
+	int gsh = 0;                                             // groups are indexed on a power-of-two pitch >= gpr
+	while ((1u << gsh) < gpr) gsh++;
 	const bool fwd = a.kind == DSP_KIND_REDFT10;
 	Coord cbase = {0, 0, 0, 0, 0};
 	long long ibase, obase;
@@ -631,8 +648,9 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 
 	// ---- copy-in
 	for (int tid = t0; tid < t1; tid++) {
-		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n * gpr; idx += (uint32_t)nthr) {
-			const uint32_t r = idx / gpr, cg = idx - r * gpr;
+		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n << gsh; idx += (uint32_t)nthr) {
+			const uint32_t r = idx >> gsh, cg = idx & ((1u << gsh) - 1u);
+			if (cg >= gpr) continue;
 			const int c0 = (int)cg * VN;                      // column within the tile
 			const T *src = gin + ibase + (long long)r * a.ax_is + col0 + c0;
 			T v[VecOf<T>::N];
@@ -670,8 +688,9 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
 	for (int tid = t0; tid < t1; tid++) {
-		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n * gpr; idx += (uint32_t)nthr) {
-			const uint32_t r = idx / gpr, cg = idx - r * gpr;
+		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n << gsh; idx += (uint32_t)nthr) {
+			const uint32_t r = idx >> gsh, cg = idx & ((1u << gsh) - 1u);
+			if (cg >= gpr) continue;
 			const int c0 = (int)cg * VN;
 			const int slot = (a.f.dense ? a.f.half : 0) + Pad<T>::of((int)DSP_LDG(pos + r));
 			Coord c = cbase;

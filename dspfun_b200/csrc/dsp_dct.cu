@@ -415,10 +415,11 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			if (!set_outer(A.o, lv)) return false;
 			A.ax_slot = ax + 3 - r; A.col_slot = lastax ? 3 : 2;
 			if (lastax) { A.d = 1; A.dd = mk_fd(1); }          // column index == channel index
-			// columns per CTA: as wide as fits ~64 KB (wider rows of the tile = longer contiguous global segments)
+			// columns per CTA: as wide as fits ~75 KB, i.e. three CTAs per SM (wider rows of the tile = longer
+			// contiguous global segments; measured at n = 1080: 16 columns 3.48 ms vs 8 columns 3.93 ms per 256 frames)
 			const int cand[] = {8 * VN, 4 * VN, 2 * VN, VN};
 			int tc = 0;
-			for (int c : cand) if ((size_t)(c / 2) * seqb <= 64 * 1024) { tc = c; break; }
+			for (int c : cand) if ((size_t)(c / 2) * seqb <= 75 * 1024) { tc = c; break; }
 			if (!tc) {
 				tc = (VN >= 4 && 2 * seqb <= kMaxSmem) ? VN : 2;
 				if ((size_t)(tc / 2) * seqb > kMaxSmem) { g_err = "transform length " + std::to_string(P->n[ax]) + " does not fit on chip"; return false; }
@@ -435,9 +436,9 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			pp.grid = (int)g;
 			pp.smem = (size_t)((tc + 1) / 2) * seqb;
 			// long power-of-two axes: two L2-resident sub-passes per column panel (dct_split.cuh)
-			// Measured on B200 (profiles/): the split wins for the forward transform at n = 8192 (0.76 vs 0.88 ms per
-			// 2 planes) and loses for the inverse (its first sub-pass reads 32 strided rows per thread straight from
-			// DRAM and is latency-bound), so it is on for REDFT10, n >= 4096.  DSP_DCT_SPLIT_MIN=<n> forces it for both.
+			// Measured on B200 (profiles/): at n = 8192 the split takes 0.49 ms (forward) / 0.54 ms (inverse) per
+			// 2 planes against 0.88 ms for the one-kernel column pass; at n = 1024 it loses (many small launches), so it
+			// is on for n >= 4096.  DSP_DCT_SPLIT_MIN=<n> moves the threshold and selects the DIF-style inverse.
 			int split_min = 4096;
 			bool split_inv = false;
 			if (getenv("DSP_DCT_SPLIT_MIN")) { split_min = atoi(getenv("DSP_DCT_SPLIT_MIN")); split_inv = true; }
