@@ -147,6 +147,16 @@ DSP_DEV void prefetch_l2(const void *p) {
 #endif
 }
 
+// bulk L2 prefetch of `bytes` (multiple of 16) starting at the 16-byte aligned p: one instruction handed to the copy
+// engine instead of one LSU request per 128-byte line
+DSP_DEV void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+#if DSP_GPU
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+#else
+	(void)p; (void)bytes;
+#endif
+}
+
 // read-only (LDG) load of a complex table entry
 #if DSP_GPU
 DSP_DEV C2<float> ldg_c2(const C2<float> *p) { const float2 t = __ldg((const float2 *)p); return C2<float>{t.x, t.y}; }

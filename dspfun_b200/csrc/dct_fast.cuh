@@ -647,12 +647,24 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 	// just-in-time L2 prefetch: the lines of the CTA that will take this SM's place (about one resident wave ahead)
 	if (a.pf_dist > 0 && a.simple) {
 		const int pl0 = (cta + a.pf_dist) * a.lines_per_cta;
-		const int lines128 = (f.N() * d * (int)sizeof(T) + 127) / 128;
-		for (int tid = t0; tid < t1; tid++)
-			for (int i = tid; i < a.lines_per_cta * lines128; i += nthr) {
-				const int l = pl0 + i / lines128;
-				if (l < a.nlines) prefetch_l2((const char *)gin + ((long long)l * a.ls_in) * (long long)sizeof(T) + (long long)(i % lines128) * 128);
-			}
+		const int lbytes = f.N() * d * (int)sizeof(T);
+		if (a.vec_in && (lbytes & 15) == 0) {
+			// 16-byte aligned lines: bulk prefetches of up to 8 KB, one thread each
+			const int chunks = (lbytes + 8191) / 8192;
+			for (int tid = t0; tid < t1; tid++)
+				for (int i = tid; i < a.lines_per_cta * chunks; i += nthr) {
+					const int l = pl0 + i / chunks, c = i % chunks;
+					const int nb = lbytes - c * 8192 < 8192 ? lbytes - c * 8192 : 8192;
+					if (l < a.nlines) prefetch_l2_bulk((const char *)gin + ((long long)l * a.ls_in) * (long long)sizeof(T) + (long long)c * 8192, (uint32_t)nb);
+				}
+		} else {
+			const int lines128 = (lbytes + 127) / 128;
+			for (int tid = t0; tid < t1; tid++)
+				for (int i = tid; i < a.lines_per_cta * lines128; i += nthr) {
+					const int l = pl0 + i / lines128;
+					if (l < a.nlines) prefetch_l2((const char *)gin + ((long long)l * a.ls_in) * (long long)sizeof(T) + (long long)(i % lines128) * 128);
+				}
+		}
 	}
 
 	if (FWD) {
