@@ -356,17 +356,21 @@ template <class T> struct SmemNat {
 	DSP_DEVM C2<T> get(int k) const { return base[Pad<T>::of(k)]; }
 };
 // two global lines (rows A and B of the pair), element k of channel ch at [k*d + ch]
-template <class T, class Op> struct GlobalRows {
+// PLANAR: d == 1 and both lines present, known at compile time -- with a fixed-length F every k is "i + constant",
+// so the accesses become [base + immediate] instead of a 64-bit address computation each
+template <class T, class Op, bool PLANAR = false> struct GlobalRows {
 	T *pa, *pb;                  // line bases (+ channel); pb = nullptr when the pair has no second line
 	int d, ax_slot;
 	Coord ca, cb;
 	const Op *op;
 	DSP_DEVM void put(int k, T xa, T xb) {
+		if (PLANAR) { pa[k] = (*op)(xa, ca); pb[k] = (*op)(xb, cb); return; }
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		pa[k * d] = (*op)(xa, ca);
 		if (pb) pb[k * d] = (*op)(xb, cb);
 	}
 	DSP_DEVM C2<T> get(int k) {
+		if (PLANAR) return C2<T>{(*op)(pa[k], ca), (*op)(pb[k], cb)};
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		const T xa = (*op)(pa[k * d], ca);
 		const T xb = pb ? (*op)(pb[k * d], cb) : (T)0;
@@ -375,6 +379,19 @@ template <class T, class Op> struct GlobalRows {
 };
 
 DSP_DEV int makhoul(int x, int n) { return (x & 1) ? n - 1 - (x >> 1) : (x >> 1); }
+
+// The outer-pass units of `nseq` sequences: per sequence i = 0 .. M/2 (i = 0 and i = M/2 are half-cost special
+// units, the others butterfly pairs i, M-i), flat over the CTA's threads.  One call site: fn is large.
+// (Tried: general units first, special units on lane 0 of successive warps so that no warp serialises three code
+// paths -- no gain at n = 8192 with two CTAs per SM, a loss at n = 1024 where it adds a second round.)
+template <class Fn>
+DSP_DEV void for_outer_units(int nseq, int M, int tid, int nthr, const Fn &fn) {
+	const uint32_t upseq = (uint32_t)(M / 2 + 1);
+	for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
+		const uint32_t seq = u / upseq;
+		fn((int)seq, (int)(u - seq * upseq));
+	}
+}
 
 // ------------------------------------------------------------------------------------------------ row pass (fast)
 // Moves the CTA's lines between global memory and smem in vector groups, `UNR` groups per thread in flight.
@@ -488,6 +505,64 @@ DSP_DEV void row_move(const RowArgs &a, const F &f, const Op &op, int line0, int
 	}
 }
 
+// The common case of row_move_planar4 (below) with all addressing hoisted: lines at a single stride, both lines of
+// every pair present, no coordinates wanted by the op.  Per group of 8 samples: 2 x LDG.128 (or STG.128), two slot
+// lookups, 4 x STS.64 (LDS.64) -- the general version spends ~100 instructions on the same work (ncu, profiles/).
+template <class T, bool FWD, bool FULL, class Op, class F>
+DSP_DEV void row_move_planar4_lean(const RowArgs &a, const F &f, const Op &op, int line0, int npairs, int tid, int nthr, C2<T> *s) {
+	typedef typename VecOf<T>::type Vec;
+	const int UNR = 8;
+	const int n = f.N(), gpl = n >> 2;
+	const int padM = f.PO(f.NMID(), 1);
+	const Coord c0 = {0, 0, 0, 0, 0};
+	const uint16_t *sigA = f.sig + 2 * tid;                  // sig[2q],     q = tid + k nthr
+	const uint16_t *sigB = f.sig + (n - 2) - 2 * tid;        // sig[n-2-2q]
+	for (int g = 0; g < npairs; g++) {
+		const long long l = line0 + 2 * g;
+		const Vec *pa = (const Vec *)((const T *)a.in + l * a.ls_in) + tid;
+		const Vec *pb = (const Vec *)((const T *)a.in + (l + 1) * a.ls_in) + tid;
+		Vec *qa = (Vec *)((T *)a.out + l * a.ls_out) + tid;
+		Vec *qb = (Vec *)((T *)a.out + (l + 1) * a.ls_out) + tid;
+		C2<T> *sg = s + g * f.NPAD();
+		for (int q0 = 0; q0 < gpl; q0 += nthr * UNR) {
+			Vec ta[UNR], tb[UNR];
+			if (FWD) {
+#pragma unroll
+				for (int u = 0; u < UNR; u++) {
+					const int qq = q0 + u * nthr;
+					if (FULL || qq + tid < gpl) { ta[u] = ldg_stream(pa + qq); tb[u] = ldg_stream(pb + qq); }
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int qq = q0 + u * nthr;
+				if (FULL || qq + tid < gpl) {
+					C2<T> *b0 = sg + (int)DSP_LDG(sigA + 2 * qq), *b1 = sg + (int)DSP_LDG(sigB - 2 * qq);
+					if (FWD) {
+						b0[0]    = C2<T>{op(ta[u].v[0], c0), op(tb[u].v[0], c0)};        // x = 4q
+						b1[padM] = C2<T>{op(ta[u].v[1], c0), op(tb[u].v[1], c0)};        // x = 4q + 1
+						b0[padM] = C2<T>{op(ta[u].v[2], c0), op(tb[u].v[2], c0)};        // x = 4q + 2
+						b1[0]    = C2<T>{op(ta[u].v[3], c0), op(tb[u].v[3], c0)};        // x = 4q + 3
+					} else {
+						const C2<T> z0 = b0[0], z1 = b1[padM], z2 = b0[padM], z3 = b1[0];
+						Vec ra, rb;
+						ra.v[0] = op(z0.x, c0); ra.v[1] = op(z1.x, c0); ra.v[2] = op(z2.x, c0); ra.v[3] = op(z3.x, c0);
+						rb.v[0] = op(-z0.y, c0); rb.v[1] = op(-z1.y, c0); rb.v[2] = op(-z2.y, c0); rb.v[3] = op(-z3.y, c0);
+						qa[qq] = ra;
+						qb[qq] = rb;
+					}
+				}
+			}
+		}
+	}
+}
+
+template <class T, bool FWD, class Op, class F>
+DSP_DEV void row_move_planar4_pick(const RowArgs &a, const F &f, const Op &op, int line0, int npairs, int tid, int nthr, C2<T> *s) {
+	if (((f.N() >> 2) % (nthr * 8)) == 0) row_move_planar4_lean<T, FWD, true, Op, F>(a, f, op, line0, npairs, tid, nthr, s);
+	else row_move_planar4_lean<T, FWD, false, Op, F>(a, f, op, line0, npairs, tid, nthr, s);
+}
+
 // planar float lines (d == 1, 16-byte access legal): one vector group = x in [4q, 4q+4) of lines A and B =
 // elements 2q, 2q+1 (even x) and n-2-2q, n-1-2q (odd x) of the permuted sequence.  sig[e+1] = sig[e] + Pad(M)
 // for even e, so two table lookups place (or fetch) all four complex values.
@@ -500,6 +575,10 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const F &f, const Op &op, int li
 	const int n = f.N();
 	const int lgq = ilog2(n) - 2;                             // log2 (vector groups per line)
 	const int npairs = (nl + 1) / 2;
+	if (a.simple && !Op::kNeedsCoord && !(nl & 1)) {
+		row_move_planar4_pick<T, FWD, Op, F>(a, f, op, line0, npairs, tid, nthr, s);
+		return;
+	}
 	const int total = npairs << lgq;
 	const int padM = f.PO(f.NMID(), 1);
 	for (int i0 = tid; i0 < total; i0 += nthr * UNR) {
@@ -631,18 +710,19 @@ DSP_DEV void row_move_any(const RowArgs &a, const F &f, const Op &op, int line0,
 	else row_move<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 }
 
-template <class T, bool FWD, class LoadOp, class StoreOp, class F>
+// PLANAR (chosen by the planner, lean ops only): d == 1, lines at one stride, every CTA owns whole line pairs,
+// 16-byte access legal -- the moves and the fused outer pass then run with all addressing hoisted.
+template <class T, bool FWD, class LoadOp, class StoreOp, class F, bool PLANAR = false>
 DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
                           int nthr, C2<T> *s) {
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
-	const int d = a.d;
+	const int d = PLANAR ? 1 : a.d;
 	const int line0 = cta * a.lines_per_cta;
 	int nl = a.nlines - line0;
 	if (nl > a.lines_per_cta) nl = a.lines_per_cta;
 	const int npairs = (nl + 1) / 2;
 	const int nseq = npairs * d;
-	const uint32_t upseq = (uint32_t)(f.Mq() / 2 + 1);              // outer-pass units per sequence
 
 	// just-in-time L2 prefetch: the lines of the CTA that will take this SM's place (about one resident wave ahead)
 	if (a.pf_dist > 0 && a.simple) {
@@ -668,7 +748,10 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 	}
 
 	if (FWD) {
-		for (int tid = t0; tid < t1; tid++) row_move_any<T, true, LoadOp>(a, f, lop, line0, nl, tid, nthr, s);
+		for (int tid = t0; tid < t1; tid++) {
+			if (PLANAR) row_move_planar4_pick<T, true, LoadOp>(a, f, lop, line0, npairs, tid, nthr, s);
+			else row_move_any<T, true, LoadOp>(a, f, lop, line0, nl, tid, nthr, s);
+		}
 		DSP_SYNC();
 		contig_pass<T>(s, nseq, f, t0, t1, nthr);
 		for (int q = 0; q < f.NMID(); q++) {
@@ -677,10 +760,18 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 		}
 		// ---- outer pass + post-twiddle + direct global store
 		for (int tid = t0; tid < t1; tid++) {
-			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = f.divHalf(u);
-				const int i = (int)(u - seq * upseq);
-				const int g = (int)seq / d, ch = (int)seq - g * d;
+			if (PLANAR) {
+				for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
+					GlobalRows<T, StoreOp, true> sink;
+					sink.ca = Coord{0, 0, 0, 0, 0}; sink.cb = sink.ca;
+					sink.pa = gout + (long long)(line0 + 2 * seq) * a.ls_out; sink.pb = sink.pa + a.ls_out;
+					sink.d = 1; sink.ax_slot = a.ax_slot; sink.op = &sop;
+					dct2_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, sink);
+				});
+				continue;
+			}
+			for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
+				const int g = seq / d, ch = seq - g * d;
 				const int la = line0 + 2 * g;
 				const bool hasb = (2 * g + 1) < nl;
 				GlobalRows<T, StoreOp> sink;
@@ -692,17 +783,25 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 				sink.pa = gout + oa + ch; sink.pb = hasb ? gout + ob + ch : (T *)0;
 				sink.d = d; sink.ax_slot = a.ax_slot; sink.op = &sop;
 				dct2_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, sink);
-			}
+			});
 		}
 		return;
 	}
 
 	// ---- DCT-III: outer pass reads the (k, n-k) pairs straight from global memory
 	for (int tid = t0; tid < t1; tid++) {
-		for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-			const uint32_t seq = f.divHalf(u);
-			const int i = (int)(u - seq * upseq);
-			const int g = (int)seq / d, ch = (int)seq - g * d;
+		if (PLANAR) {
+			for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
+				GlobalRows<T, LoadOp, true> src;
+				src.ca = Coord{0, 0, 0, 0, 0}; src.cb = src.ca;
+				src.pa = (T *)gin + (long long)(line0 + 2 * seq) * a.ls_in; src.pb = src.pa + a.ls_in;
+				src.d = 1; src.ax_slot = a.ax_slot; src.op = &lop;
+				dct3_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, src);
+			});
+			continue;
+		}
+		for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
+			const int g = seq / d, ch = seq - g * d;
 			const int la = line0 + 2 * g;
 			const bool hasb = (2 * g + 1) < nl;
 			GlobalRows<T, LoadOp> src;
@@ -714,7 +813,7 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 			src.pa = (T *)gin + ia + ch; src.pb = hasb ? (T *)gin + ib + ch : (T *)0;
 			src.d = d; src.ax_slot = a.ax_slot; src.op = &lop;
 			dct3_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, src);
-		}
+		});
 	}
 	DSP_SYNC();
 	for (int q = f.NMID() - 1; q >= 0; q--) {
@@ -722,7 +821,10 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 		DSP_SYNC();
 	}
 	contig_pass<T>(s, nseq, f, t0, t1, nthr);
-	for (int tid = t0; tid < t1; tid++) row_move_any<T, false, StoreOp>(a, f, sop, line0, nl, tid, nthr, s);
+	for (int tid = t0; tid < t1; tid++) {
+		if (PLANAR) row_move_planar4_pick<T, false, StoreOp>(a, f, sop, line0, npairs, tid, nthr, s);
+		else row_move_any<T, false, StoreOp>(a, f, sop, line0, nl, tid, nthr, s);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ column pass (fast)
@@ -916,7 +1018,6 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const F &f, const LoadOp &lop, const
 	int ncl = a.ncols - col0;
 	if (ncl > a.tc) ncl = a.tc;
 	const int nseq = (ncl + 1) / 2;
-	const uint32_t upseq = (uint32_t)(f.Mq() / 2 + 1);
 	Coord cbase = {0, 0, 0, 0, 0};
 	long long ibase, obase;
 	outer_decode(a.o, oidx, ibase, obase, cbase);
@@ -946,24 +1047,20 @@ DSP_DEV void cta_col_fast(const ColArgs &a, const F &f, const LoadOp &lop, const
 			DSP_SYNC();
 		}
 		for (int tid = t0; tid < t1; tid++) {
-			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = f.divHalf(u);
-				const int i = (int)(u - seq * upseq);
+			for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
 				SmemNat<T> sink;
 				sink.base = s + seq * f.NPAD();
 				dct2_outer_unit<T>(SmemBf<T, F>{sink.base, &f}, f, i, sink);
-			}
+			});
 		}
 		DSP_SYNC();
 	} else {
 		for (int tid = t0; tid < t1; tid++) {
-			for (uint32_t u = (uint32_t)tid; u < (uint32_t)nseq * upseq; u += (uint32_t)nthr) {
-				const uint32_t seq = f.divHalf(u);
-				const int i = (int)(u - seq * upseq);
+			for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
 				SmemNat<T> src;
 				src.base = s + seq * f.NPAD();
 				dct3_outer_unit<T>(SmemBf<T, F>{src.base, &f}, f, i, src);
-			}
+			});
 		}
 		DSP_SYNC();
 		for (int q = f.NMID() - 1; q >= 0; q--) {

@@ -275,6 +275,17 @@ struct dsp_dct_plan_s {
 #endif
 	bool need_acc;
 	rt_stream last_stream;
+	// creation parameters, kept so that the host-buffer entry can re-plan sub-batches (chunk pipeline, execute_host)
+	int c_howmany, c_istride, c_idist, c_ostride, c_odist, c_nbatch;
+	long long c_ibdist, c_obdist;
+	int c_ie[3], c_oe[3];
+	bool c_has_ie, c_has_oe;
+	std::vector<dsp_dct_plan_s *> kids;      // one sub-plan per chunk of batch elements
+	std::vector<long long> kid_b0;           // first batch element of each chunk
+	bool kids_failed;
+#if DSP_GPU
+	cudaStream_t kid_st[4];
+#endif
 	// per-pass profiling
 	bool profiling;
 	double samples_per_launch;
@@ -509,7 +520,12 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain && !a.in_u8; a.vec_out = pp.vec_out_layout && aout && !a.out_u8;
 		a.pf_dist = pp.pf_dist;
-		if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		const int nn = pp.ff.n;
+		const bool planar = pp.fast && f32 && !pp.fused && a.d == 1 && a.simple && a.vec_in && a.vec_out && nn >= 256 &&
+		                    nn <= 8192 && (a.lines_per_cta % 2) == 0 && (a.nlines % a.lines_per_cta) == 0 &&
+		                    !getenv("DSP_DCT_NO_FIXED") && !getenv("DSP_DCT_NO_PLANAR");
+		if (planar) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #endif
@@ -678,12 +694,19 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->last_stream = 0;
 	P->profiling = false;
 	P->samples_per_launch = 0;
+	P->c_howmany = howmany; P->c_istride = istride; P->c_idist = idist; P->c_ostride = ostride; P->c_odist = odist;
+	P->c_nbatch = nbatch; P->c_ibdist = ibdist; P->c_obdist = obdist;
+	P->c_has_ie = inembed != nullptr; P->c_has_oe = onembed != nullptr;
+	for (int i = 0; i < 3; i++) { P->c_ie[i] = (inembed && i < rank) ? inembed[i] : 0; P->c_oe[i] = (onembed && i < rank) ? onembed[i] : 0; }
+	P->kids_failed = false;
 	if (!build_plan(P, howmany, inembed, istride, idist, onembed, ostride, odist, nbatch, ibdist, obdist)) {
 		delete P;
 		return nullptr;
 	}
 	return P;
 }
+
+static void destroy_plan(dsp_dct_plan_s *p);
 
 static bool ensure_staging(dsp_dct_plan_s *P, bool inplace) {
 	const size_t ib = P->in_span * (size_t)P->es, ob = P->out_span * (size_t)P->es;
@@ -712,10 +735,79 @@ static bool ensure_staging(dsp_dct_plan_s *P, bool inplace) {
 	return true;
 }
 
+#if DSP_GPU
+// Host-buffer execution of a batch: PCIe is the bound (one copy in, one copy out), and the two directions are
+// independent engines.  The batch is cut into up to four chunks of whole batch elements, each with its own sub-plan
+// and stream: chunk c+1 uploads while chunk c transforms and chunk c-1 downloads.
+static bool ensure_kids(dsp_dct_plan_s *P) {
+	if (!P->kids.empty()) return true;
+	if (P->kids_failed) return false;
+	const int nchunks = P->c_nbatch < 4 ? P->c_nbatch : 4;
+	long long b0 = 0;
+	for (int c = 0; c < nchunks; c++) {
+		const int nb = P->c_nbatch / nchunks + (c < P->c_nbatch % nchunks ? 1 : 0);
+		dsp_dct_plan_s *K = new dsp_dct_plan_s(*P);             // same geometry; owned resources reset below
+		K->passes.clear();
+		K->d_in = K->d_out = nullptr; K->d_in_bytes = K->d_out_bytes = 0;
+		K->d_scalars = nullptr; K->d_signmap = nullptr; K->d_work = nullptr; K->d_split = nullptr;
+		K->split_bytes = 0; K->nscratch = 1; K->aux_ok = false;
+		K->kids.clear(); K->kid_b0.clear(); K->kids_failed = true;  // no recursion
+		K->ev.clear(); K->ev_pass.clear(); K->profiling = false;
+		K->c_nbatch = nb;
+		bool ok = build_plan(K, P->c_howmany, P->c_has_ie ? P->c_ie : nullptr, P->c_istride, P->c_idist,
+		                     P->c_has_oe ? P->c_oe : nullptr, P->c_ostride, P->c_odist, nb, P->c_ibdist, P->c_obdist);
+		ok = ok && rt_ok(cudaStreamCreateWithFlags(&P->kid_st[c], cudaStreamNonBlocking), g_err, "stream create");
+		if (!ok) {
+			destroy_plan(K);
+			for (size_t k = 0; k < P->kids.size(); k++) { destroy_plan(P->kids[k]); cudaStreamDestroy(P->kid_st[k]); }
+			P->kids.clear(); P->kid_b0.clear();
+			P->kids_failed = true;
+			return false;
+		}
+		P->kids.push_back(K);
+		P->kid_b0.push_back(b0);
+		b0 += nb;
+	}
+	return true;
+}
+
+static bool execute_host_chunks(dsp_dct_plan_s *P, void *in, void *out, void *din, void *dout) {
+	const size_t es = (size_t)P->es;
+	for (size_t c = 0; c < P->kids.size(); c++) {
+		dsp_dct_plan_s *K = P->kids[c];
+		// the plain scale factors may have been set after the chunks were planned
+		K->passes.front().lop = P->passes.front().lop;
+		K->passes.back().sop = P->passes.back().sop;
+		const size_t io = (size_t)(P->kid_b0[c] * P->c_ibdist) * es, oo = (size_t)(P->kid_b0[c] * P->c_obdist) * es;
+		rt_stream st = P->kid_st[c];
+		if (!rt_h2d((char *)din + io, (const char *)in + io, K->in_span * es, st, g_err)) return false;
+		if (!run_passes(K, (char *)din + io, (char *)dout + oo, st)) return false;
+		if (!rt_d2h((char *)out + oo, (const char *)dout + oo, K->out_span * es, st, g_err)) return false;
+	}
+	bool ok = true;
+	for (size_t c = 0; c < P->kids.size(); c++) ok = rt_sync(P->kid_st[c], g_err) && ok;
+	return ok;
+}
+
+static bool chunkable(const dsp_dct_plan_s *P) {
+	if (P->c_nbatch < 2 || P->fuse_kind != 0 || P->out_has_gaps || P->profiling || P->need_acc) return false;
+	if (getenv("DSP_DCT_NO_PIPELINE")) return false;
+	const size_t min_mb = getenv("DSP_DCT_PIPELINE_MIN_MB") ? (size_t)atoi(getenv("DSP_DCT_PIPELINE_MIN_MB")) : 32;
+	if (P->in_span * (size_t)P->es < (min_mb << 20)) return false;              // small jobs: latency, not bandwidth
+	// batch elements must not interleave in memory
+	const long long ein = (long long)P->in_span - (long long)(P->c_nbatch - 1) * P->c_ibdist;
+	const long long eout = (long long)P->out_span - (long long)(P->c_nbatch - 1) * P->c_obdist;
+	return P->c_ibdist >= ein && P->c_obdist >= eout && ein > 0 && eout > 0;
+}
+#endif
+
 static bool execute_host(dsp_dct_plan_s *P, void *in, void *out) {
 	const bool inplace = in == out;
 	if (!ensure_staging(P, inplace)) return false;
 	void *din = P->d_in, *dout = inplace ? P->d_in : P->d_out;
+#if DSP_GPU
+	if (chunkable(P) && ensure_kids(P)) return execute_host_chunks(P, in, out, din, dout);
+#endif
 	rt_stream st = 0;
 	if (!rt_h2d(din, in, P->in_span * (size_t)P->es, st, g_err)) return false;
 	if (!inplace && P->out_has_gaps && !rt_h2d(dout, out, P->out_span * (size_t)P->es, st, g_err)) return false;
@@ -728,6 +820,27 @@ static bool ensure_scalars(dsp_dct_plan_s *P) {
 	if (P->d_scalars) return true;
 	if (!rt_malloc((void **)&P->d_scalars, sizeof(double) * 16, g_err)) return false;
 	return rt_zero(P->d_scalars, sizeof(double) * 16, 0, g_err) && rt_sync(0, g_err);
+}
+
+static void destroy_plan(dsp_dct_plan_s *p) {
+#if DSP_GPU
+	for (size_t k = 0; k < p->kids.size(); k++) { cudaStreamSynchronize(p->kid_st[k]); destroy_plan(p->kids[k]); cudaStreamDestroy(p->kid_st[k]); }
+	if (p->aux_ok) for (int k = 0; k < p->naux; k++) cudaStreamSynchronize(p->aux[k]);
+#endif
+	rt_free(p->d_in);
+	rt_free(p->d_out);
+	rt_free(p->d_scalars);
+	rt_free(p->d_signmap);
+	rt_free(p->d_work);
+	rt_free(p->d_split);
+#if DSP_GPU
+	if (p->aux_ok) {
+		cudaEventDestroy(p->ev_fork);
+		for (int k = 0; k < p->naux; k++) { cudaStreamDestroy(p->aux[k]); cudaEventDestroy(p->ev_join[k]); }
+	}
+	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+#endif
+	delete p;
 }
 
 }  // namespace dsp
@@ -779,20 +892,7 @@ void dsp_dct_execute(dsp_dct_plan p) {
 
 void dsp_dct_destroy(dsp_dct_plan p) {
 	if (!p) return;
-	rt_free(p->d_in);
-	rt_free(p->d_out);
-	rt_free(p->d_scalars);
-	rt_free(p->d_signmap);
-	rt_free(p->d_work);
-	rt_free(p->d_split);
-#if DSP_GPU
-	if (p->aux_ok) {
-		cudaEventDestroy(p->ev_fork);
-		for (int k = 0; k < p->naux; k++) { cudaStreamDestroy(p->aux[k]); cudaEventDestroy(p->ev_join[k]); }
-	}
-	for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
-#endif
-	delete p;
+	dsp::destroy_plan(p);
 }
 
 void *dsp_dct_alloc(size_t bytes) {

@@ -21,6 +21,7 @@ DSP_DECL_LAUNCH(launch_row_generic_f32, RowArgs)
 DSP_DECL_LAUNCH(launch_row_generic_f64, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f32, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f64, RowArgs)
+DSP_DECL_LAUNCH(launch_row_fast_f32p, RowArgs)     // planar specialisation (fixed lengths 256..8192, lean ops)
 DSP_DECL_LAUNCH(launch_col_generic_f32, ColArgs)
 DSP_DECL_LAUNCH(launch_col_generic_f64, ColArgs)
 DSP_DECL_LAUNCH(launch_col_fast_f32, ColArgs)

@@ -29,6 +29,7 @@ namespace dsp {
 // NB: the element type and the row/fast flags are template parameters so that every translation unit
 // instantiates distinctly named kernels (same-signature templates in different TUs would be merged by the linker).
 // FAST: bit 0 = fast path, bit 1 = forward (fast kernels are specialised on the transform kind),
+// bit 2 = planar row specialisation (cta_row_fast<PLANAR>; its own TU, KERN_PLANAR),
 // bits 8.. = log2 n when the length is fixed at compile time (FastFixed), 0 = runtime length
 template <class TT, int ROW, int FAST, class L, class S>
 DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int cta, int t0, int t1, int nthr,
@@ -38,7 +39,9 @@ DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S
 		FastFixed<((FAST >> 8) != 0) ? (FAST >> 8) : 8> ff;
 		ff.tw = f.tw; ff.om = f.om; ff.sig = f.sig;
 #if KERN_ROW
-		cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
+		typedef FastFixed<((FAST >> 8) != 0) ? (FAST >> 8) : 8> FF;
+		if (FAST & 4) cta_row_fast<KERN_T, (FAST & 2) != 0, L, S, FF, true>(a, ff, l, s, cta, t0, t1, nthr, smem);
+		else cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
 #else
 		cta_col_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
 #endif
@@ -94,6 +97,24 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 	if (!KERN_FAST) block = kThreads;
 	// lean kernels: the only pointwise stage is a multiply (1 unless dsp_dct_fuse_scale set it)
 	const OpMul<KERN_T> lm = {(KERN_T)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(KERN_T)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
+#ifdef KERN_PLANAR
+	// planar row specialisation: the planner has checked the layout (PassPlan::planar); fixed lengths only
+	{
+		const bool fw = a.kind == DSP_KIND_REDFT10;
+		(void)fused;
+#define DSP_PLANAR_CASE(LG)                                                                                                  \
+	case (1 << LG):                                                                                                          \
+		return fw ? launch_t<KERN_T, KERN_ROW, 7 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err) \
+		          : launch_t<KERN_T, KERN_ROW, 5 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
+		switch (f.n) {
+			DSP_PLANAR_CASE(8) DSP_PLANAR_CASE(9) DSP_PLANAR_CASE(10) DSP_PLANAR_CASE(11) DSP_PLANAR_CASE(12) DSP_PLANAR_CASE(13)
+		default: break;
+		}
+#undef DSP_PLANAR_CASE
+		err = "no planar row kernel for this length";
+		return false;
+	}
+#else
 #if KERN_FAST
 	// lean kernels with the length fixed at compile time for the common sizes (float only: FastFixed pads like float)
 	if (!fused && sizeof(KERN_T) == 4 && !getenv("DSP_DCT_NO_FIXED")) {
@@ -115,6 +136,7 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 #endif
 	if (fused) return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpAny, OpAny>(a, f, lop, sop, grid, block, smem, st, err);
 	return launch_t<KERN_T, KERN_ROW, KERN_FAST, OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
+#endif
 }
 
 }  // namespace dsp

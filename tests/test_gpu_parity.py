@@ -65,6 +65,37 @@ def test_planar_3d_embed(lib, prec, kind):
 
 
 @pytest.mark.parametrize("prec", ["f", "d"])
+def test_host_chunk_pipeline(lib, prec, monkeypatch):
+    """dsp_dct_execute_host cuts a batch into chunks (upload / transform / download overlap): same bits as one stream."""
+    import numpy as np
+    from dspfun_b200 import Plan, REDFT10, REDFT01
+    from oracle import dct as od
+    nb, h, w, d = 5, 96, 128, 3                      # 5 images -> chunks of 2,1,1,1
+    x = np.random.default_rng(11).random((nb, h, w, d)).astype(cases.DT[prec])
+    outs = {}
+    for mode in ("pipeline", "single"):
+        if mode == "pipeline":
+            monkeypatch.setenv("DSP_DCT_PIPELINE_MIN_MB", "0")
+            monkeypatch.delenv("DSP_DCT_NO_PIPELINE", raising=False)
+        else:
+            monkeypatch.setenv("DSP_DCT_NO_PIPELINE", "1")
+        p = Plan.interleaved_2d(prec, h, w, d, REDFT10, nbatch=nb, lib=lib)
+        y = p.execute_host(x.copy())
+        y2 = p.execute_host(x.copy())                # plan reuse
+        p.destroy()
+        q = Plan.interleaved_2d(prec, h, w, d, REDFT01, nbatch=nb, lib=lib).fuse_scale(1.0, 1.0 / (4.0 * h * w))
+        z = q.execute_host(y.copy())
+        q.destroy()
+        assert np.array_equal(y, y2)
+        outs[mode] = (y, z)
+    assert np.array_equal(outs["pipeline"][0], outs["single"][0])
+    assert np.array_equal(outs["pipeline"][1], outs["single"][1])
+    ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 2, axes=(1, 2))
+    assert od.rel_l2(outs["pipeline"][0], ref) < cases.OK[prec]
+    assert od.rel_l2(outs["pipeline"][1], x) < cases.OK[prec]
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
 def test_batched_images_roundtrip(lib, prec):
     cases.check_batched_images(lib, prec, 5, 16, 24, 3)
     cases.check_batched_images(lib, prec, 16, 256, 256, 3)
