@@ -41,8 +41,8 @@ DSP_DEV int split_row(int e, int n) { return e < n / 2 ? 2 * e : 2 * (n - 1 - e)
 
 // ------------------------------------------------------------------------------------------------ sub-pass A
 // idx -> (global row, smem slot) for the four moves of sub-pass A
-template <class T, int W, bool IN, bool GLOBAL_SIDE_IS_IMAGE, class Op>
-DSP_DEV void split_move(const SplitArgs &a, const FastDesc &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
+template <class T, int W, bool IN, bool GLOBAL_SIDE_IS_IMAGE, class Op, class F>
+DSP_DEV void split_move(const SplitArgs &a, const F &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
                         int nthr, C2<T> *s) {
 	typedef VecW<T, W> Vec;
 	const int UNR = 8;
@@ -93,7 +93,7 @@ DSP_DEV void split_move(const SplitArgs &a, const FastDesc &fM, const Op &op, in
 					for (int p = 0; p < W / 2; p++) {
 						v[u][2 * p] = 0; v[u][2 * p + 1] = 0;
 						if (c0 + 2 * p < ncl) {
-							const C2<T> z = s[(c0 / 2 + p) * fM.npad + slot];
+							const C2<T> z = s[(c0 / 2 + p) * fM.NPAD() + slot];
 							v[u][2 * p] = z.x;
 							v[u][2 * p + 1] = negim ? -z.y : z.y;
 						}
@@ -114,7 +114,7 @@ DSP_DEV void split_move(const SplitArgs &a, const FastDesc &fM, const Op &op, in
 				if (IN) {
 #pragma unroll
 					for (int p = 0; p < W / 2; p++)
-						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * fM.npad + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
+						if (c0 + 2 * p < ncl) s[(c0 / 2 + p) * fM.NPAD() + slot] = C2<T>{v[u][2 * p], v[u][2 * p + 1]};
 				} else {
 					T *dst = gout + (long long)grow * rs + cofs + c0;
 					if (vec) {
@@ -138,8 +138,8 @@ struct RowSplitScratch { int base; DSP_DEVM int operator()(int r) const { return
 struct SlotSig { const uint16_t *sig; DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + r); } };
 
 // image-side and scratch-side moves of sub-pass A with the lean path when the tile is full and aligned
-template <class T, bool IN, bool IMAGE, class Op>
-DSP_DEV void split_move_any(const SplitArgs &a, const FastDesc &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
+template <class T, bool IN, bool IMAGE, class Op, class F>
+DSP_DEV void split_move_any(const SplitArgs &a, const F &fM, const Op &op, int j, int col0, int ncl, bool negim, int tid,
                             int nthr, C2<T> *s) {
 	const int W = VecOf<T>::N;
 	if (sizeof(T) == 4 && !Op::kNeedsCoord && lean_ok(ncl, a.tc, nthr, true)) {
@@ -147,10 +147,10 @@ DSP_DEV void split_move_any(const SplitArgs &a, const FastDesc &fM, const Op &op
 		if (IMAGE) {
 			const T *gin = (const T *)a.in + col0;
 			T *gout = (T *)a.out + col0;
-			tile_move_lean<T, IN, Op>(gin, gout, IN ? a.ax_is : a.ax_os, a.M, lg, op, negim, RowSplitImage{j, a.n}, SlotSig{fM.sig}, fM.npad, tid, nthr, s);
+			tile_move_lean<T, IN, Op>(gin, gout, IN ? a.ax_is : a.ax_os, fM.N(), lg, op, negim, RowSplitImage{j, a.n}, SlotSig{fM.sig}, fM.NPAD(), tid, nthr, s);
 		} else {
 			const T *g = (const T *)a.scratch + (col0 - a.pcol0);
-			tile_move_lean<T, IN, Op>(g, (T *)g, a.ax_ss, a.M, lg, op, negim, RowSplitScratch{j * a.M}, SlotNat<T>(), fM.npad, tid, nthr, s);
+			tile_move_lean<T, IN, Op>(g, (T *)g, a.ax_ss, fM.N(), lg, op, negim, RowSplitScratch{j * fM.N()}, SlotNat<T>(), fM.NPAD(), tid, nthr, s);
 		}
 		return;
 	}
@@ -159,8 +159,8 @@ DSP_DEV void split_move_any(const SplitArgs &a, const FastDesc &fM, const Op &op
 
 // CTA = (column tile, sub-FFT j).  FWD: image rows -> M-point DIT FFT -> scratch block j.
 // !FWD: scratch block j -> M-point DIF FFT -> image rows (un-permuted).
-template <class T, bool FWD, class LoadOp, class StoreOp>
-DSP_DEV void cta_split_fft(const SplitArgs &a, const FastDesc &fM, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
+template <class T, bool FWD, class LoadOp, class StoreOp, class F>
+DSP_DEV void cta_split_fft(const SplitArgs &a, const F &fM, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
                            int nthr, C2<T> *s) {
 	const int j = cta / a.ntiles, tile = cta - j * a.ntiles;
 	const int col0 = a.pcol0 + tile * a.tc;
@@ -171,7 +171,7 @@ DSP_DEV void cta_split_fft(const SplitArgs &a, const FastDesc &fM, const LoadOp 
 		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, true, LoadOp>(a, fM, lop, j, col0, ncl, false, tid, nthr, s);
 		DSP_SYNC();
 		contig_pass<T>(s, nseq, fM, t0, t1, nthr);
-		for (int q = 0; q <= fM.nmid; q++) {
+		for (int q = 0; q <= fM.NMID(); q++) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, fM, q, tid, nthr);
 			DSP_SYNC();
 		}
@@ -179,7 +179,7 @@ DSP_DEV void cta_split_fft(const SplitArgs &a, const FastDesc &fM, const LoadOp 
 	} else {
 		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
 		DSP_SYNC();
-		for (int q = fM.nmid; q >= 0; q--) {
+		for (int q = fM.NMID(); q >= 0; q--) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, false>(s, nseq, fM, q, tid, nthr);
 			DSP_SYNC();
 		}
@@ -285,10 +285,10 @@ DSP_DEV void split_pretw(const C2<T> *om, int k, int n, C2<T> *pk, C2<T> *pn) {
 	}
 }
 
-template <class T, class LoadOp>
-DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const LoadOp &lop, int cta, int t0,
+template <class T, class LoadOp, class F>
+DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const F &fM, const FastDesc &fN, const LoadOp &lop, int cta, int t0,
                                int t1, int nthr, C2<T> *s) {
-	const int M = a.M, n = a.n;
+	const int M = fM.N(), n = 16 * fM.N();
 	const int jj = cta / a.ntilesi, tile = cta - jj * a.ntilesi;          // jj = 0..8
 	const int col0 = a.pcol0 + tile * a.tci;
 	const int nq = a.tci / 2;                                             // complex sequences per sub-sequence
@@ -297,7 +297,7 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const Fas
 	const int nseq = paired ? 2 * nq : nq;
 	const int lg = ilog2(a.tci / 4);
 	const C2<T> *om = (const C2<T> *)fN.om;
-	C2<T> *sA = s, *sB = s + nq * fM.npad;
+	C2<T> *sA = s, *sB = s + nq * fM.NPAD();
 	const T *gin = (const T *)a.in + col0;
 	// ---- load both rows of every (k, n-k) pair, pre-twiddle in registers, store to the digit-reversed slots
 	//      (element k' of sub-sequence ja pairs with element kb of sub-sequence jb; for the single sub-sequences 0 and 8
@@ -309,7 +309,7 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const Fas
 	for (int tid = t0; tid < t1; tid++) {
 		const int cg = tid & ((1 << lg) - 1), dk = nthr >> lg;
 		const T *gp = gin + 4 * cg;
-		C2<T> *qa = sA + (2 * cg) * fM.npad, *qb = sBB + (2 * cg) * fM.npad;
+		C2<T> *qa = sA + (2 * cg) * fM.NPAD(), *qb = sBB + (2 * cg) * fM.NPAD();
 		for (int k0 = tid >> lg; k0 < npair; k0 += dk * UNR) {
 			Vec va[UNR], vb[UNR];
 #pragma unroll
@@ -336,9 +336,9 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const Fas
 						const C2<T> xa = C2<T>{lop(va[u].v[2 * p], cz), lop(va[u].v[2 * p + 1], cz)};
 						const C2<T> xb = C2<T>{lop(vb[u].v[2 * p], cz), lop(vb[u].v[2 * p + 1], cz)};
 						C2<T> wk, wn;
-						if (self && k == 0) { qa[p * fM.npad + sk] = C2<T>{xa.x, -xa.y}; continue; }
-						if (2 * k <= n) { dct3_pair<T>(w, xa, xb, wk, wn); qa[p * fM.npad + sk] = wk; if (!self) qb[p * fM.npad + sn] = wn; }
-						else { dct3_pair<T>(w, xb, xa, wk, wn); qb[p * fM.npad + sn] = wk; qa[p * fM.npad + sk] = wn; }
+						if (self && k == 0) { qa[p * fM.NPAD() + sk] = C2<T>{xa.x, -xa.y}; continue; }
+						if (2 * k <= n) { dct3_pair<T>(w, xa, xb, wk, wn); qa[p * fM.NPAD() + sk] = wk; if (!self) qb[p * fM.NPAD() + sn] = wn; }
+						else { dct3_pair<T>(w, xb, xa, wk, wn); qb[p * fM.NPAD() + sn] = wk; qa[p * fM.NPAD() + sk] = wn; }
 					}
 				}
 			}
@@ -347,15 +347,15 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const FastDesc &fM, const Fas
 	DSP_SYNC();
 	// ---- M-point DIT FFTs
 	contig_pass<T>(s, nseq, fM, t0, t1, nthr);
-	for (int q = 0; q <= fM.nmid; q++) {
+	for (int q = 0; q <= fM.NMID(); q++) {
 		for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, fM, q, tid, nthr);
 		DSP_SYNC();
 	}
 	// ---- natural-order results to scratch blocks j (and 16 - j)
 	T *gs = (T *)a.scratch + (col0 - a.pcol0);
 	for (int tid = t0; tid < t1; tid++) {
-		tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{ja * M}, SlotNat<T>(), fM.npad, tid, nthr, sA);
-		if (paired) tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{jb * M}, SlotNat<T>(), fM.npad, tid, nthr, sB);
+		tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{ja * M}, SlotNat<T>(), fM.NPAD(), tid, nthr, sA);
+		if (paired) tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{jb * M}, SlotNat<T>(), fM.NPAD(), tid, nthr, sB);
 	}
 }
 

@@ -2,16 +2,39 @@
 #include "dsp_kernels.h"
 #include "dct_split.cuh"
 #include <vector>
+#include <cstdlib>
+
+#ifndef DSP_SPLIT_MINB
+#define DSP_SPLIT_MINB 3      // M = 256 sub-pass A kernels: 3 CTAs per SM (35 KB tiles, <= 85 registers).  Measured: n = 4096
+                              // column pass 0.345 -> 0.314 ms; at M = 512 (512 CTAs per panel = 1.15 waves of 444) it loses.
+#endif
 
 namespace dsp {
 
+// LGM: log2 of the sub-FFT length M = n/16 when fixed at compile time (FastFixed: every smem offset and loop bound of
+// sub-pass A folds), 0 = runtime length.  The thread count is the constant kThreads for the same reason.
+template <int LGM> struct SubDesc {
+	typedef FastFixed<(LGM ? LGM : 8)> type;
+	DSP_DEVM static type make(const FastDesc &f) { type r; r.tw = f.tw; r.om = f.om; r.sig = f.sig; return r; }
+};
+template <int LGM, bool FWD, class L, class S>
+DSP_DEV void split_fft_body(const SplitArgs &a, const FastDesc &fM, const L &l, const S &s, int cta, int t0, int t1, int nthr, C2<float> *smem) {
+	if (LGM) cta_split_fft<float, FWD, L, S>(a, SubDesc<LGM>::make(fM), l, s, cta, t0, t1, nthr, smem);
+	else cta_split_fft<float, FWD, L, S>(a, fM, l, s, cta, t0, t1, nthr, smem);
+}
+template <int LGM, class L>
+DSP_DEV void split_inv_fft_body(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const L &l, int cta, int t0, int t1, int nthr, C2<float> *smem) {
+	if (LGM) cta_split_inv_fft<float, L>(a, SubDesc<LGM>::make(fM), fN, l, cta, t0, t1, nthr, smem);
+	else cta_split_inv_fft<float, L>(a, fM, fN, l, cta, t0, t1, nthr, smem);
+}
+
 #if DSP_GPU
-template <bool FWD, class L, class S>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int LGM, bool FWD, class L, class S>
+__global__ void __launch_bounds__(kThreads, (LGM == 8) ? DSP_SPLIT_MINB : 2)
 k_split_fft(const __grid_constant__ SplitArgs a, const __grid_constant__ FastDesc fM, const __grid_constant__ L l,
             const __grid_constant__ S s) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	cta_split_fft<float, FWD, L, S>(a, fM, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<float> *)smem);
+	split_fft_body<LGM, FWD, L, S>(a, fM, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, kThreads, (C2<float> *)smem);
 }
 template <bool FWD, class L, class S>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -22,12 +45,12 @@ k_split_outer(const __grid_constant__ SplitArgs a, const __grid_constant__ FastD
 #endif
 
 #if DSP_GPU
-template <class L>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int LGM, class L>
+__global__ void __launch_bounds__(kThreads, (LGM == 8) ? DSP_SPLIT_MINB : 2)
 k_split_inv_fft(const __grid_constant__ SplitArgs a, const __grid_constant__ FastDesc fM, const __grid_constant__ FastDesc fN,
                 const __grid_constant__ L l) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	cta_split_inv_fft<float, L>(a, fM, fN, l, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, (int)blockDim.x, (C2<float> *)smem);
+	split_inv_fft_body<LGM, L>(a, fM, fN, l, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, kThreads, (C2<float> *)smem);
 }
 template <class S>
 __global__ void __launch_bounds__(kThreads, 3)
@@ -37,23 +60,34 @@ k_split_inv_outer(const __grid_constant__ SplitArgs a, const __grid_constant__ F
 #endif
 
 // DIT-style inverse (lean only: full 16-column tiles, plain scale ops)
-bool launch_split_inv_fft_f32(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const OpAny &lop, int grid, size_t smem,
-                              rt_stream st, std::string &err) {
-	const OpMul<float> lm = {(float)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)};
+template <int LGM>
+static bool split_inv_fft_t(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const OpMul<float> &lm, int grid, size_t smem,
+                            rt_stream st, std::string &err) {
 #if DSP_GPU
 	static size_t attr_set = 0;
 	if (smem > 48 * 1024 && smem > attr_set) {
-		if (!rt_ok(cudaFuncSetAttribute(k_split_inv_fft<OpMul<float>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
+		if (!rt_ok(cudaFuncSetAttribute(k_split_inv_fft<LGM, OpMul<float>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
 		attr_set = kMaxSmem;
 	}
-	k_split_inv_fft<OpMul<float>><<<grid, kThreads, smem, st>>>(a, fM, fN, lm);
+	k_split_inv_fft<LGM, OpMul<float>><<<grid, kThreads, smem, st>>>(a, fM, fN, lm);
 	return rt_ok(cudaGetLastError(), err, "split inverse fft launch");
 #else
 	(void)st; (void)err;
 	std::vector<unsigned char> buf(smem + 64);
-	for (int cta = 0; cta < grid; cta++) cta_split_inv_fft<float, OpMul<float>>(a, fM, fN, lm, cta, 0, kThreads, kThreads, (C2<float> *)buf.data());
+	for (int cta = 0; cta < grid; cta++) split_inv_fft_body<LGM, OpMul<float>>(a, fM, fN, lm, cta, 0, kThreads, kThreads, (C2<float> *)buf.data());
 	return true;
 #endif
+}
+
+bool launch_split_inv_fft_f32(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const OpAny &lop, int grid, size_t smem,
+                              rt_stream st, std::string &err) {
+	const OpMul<float> lm = {(float)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)};
+	if (!getenv("DSP_DCT_NO_FIXED")) {
+		if (fM.n == 256) return split_inv_fft_t<8>(a, fM, fN, lm, grid, smem, st, err);
+		if (fM.n == 512) return split_inv_fft_t<9>(a, fM, fN, lm, grid, smem, st, err);
+		if (fM.n == 1024) return split_inv_fft_t<10>(a, fM, fN, lm, grid, smem, st, err);
+	}
+	return split_inv_fft_t<0>(a, fM, fN, lm, grid, smem, st, err);
 }
 
 bool launch_split_inv_outer_f32(const SplitArgs &a, const FastDesc &fN, const OpAny &sop, int nwarps, rt_stream st, std::string &err) {
@@ -70,20 +104,20 @@ bool launch_split_inv_outer_f32(const SplitArgs &a, const FastDesc &fN, const Op
 #endif
 }
 
-template <bool FWD, class L, class S>
+template <int LGM, bool FWD, class L, class S>
 static bool split_fft_t(const SplitArgs &a, const FastDesc &fM, const L &l, const S &s, int grid, size_t smem, rt_stream st, std::string &err) {
 #if DSP_GPU
 	static size_t attr_set = 0;
 	if (smem > 48 * 1024 && smem > attr_set) {
-		if (!rt_ok(cudaFuncSetAttribute(k_split_fft<FWD, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
+		if (!rt_ok(cudaFuncSetAttribute(k_split_fft<LGM, FWD, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
 		attr_set = kMaxSmem;
 	}
-	k_split_fft<FWD, L, S><<<grid, kThreads, smem, st>>>(a, fM, l, s);
+	k_split_fft<LGM, FWD, L, S><<<grid, kThreads, smem, st>>>(a, fM, l, s);
 	return rt_ok(cudaGetLastError(), err, "split fft launch");
 #else
 	(void)st; (void)err;
 	std::vector<unsigned char> buf(smem + 64);
-	for (int cta = 0; cta < grid; cta++) cta_split_fft<float, FWD, L, S>(a, fM, l, s, cta, 0, kThreads, kThreads, (C2<float> *)buf.data());
+	for (int cta = 0; cta < grid; cta++) split_fft_body<LGM, FWD, L, S>(a, fM, l, s, cta, 0, kThreads, kThreads, (C2<float> *)buf.data());
 	return true;
 #endif
 }
@@ -106,10 +140,15 @@ bool launch_split_fft_f32(const SplitArgs &a, const FastDesc &fM, bool fused, co
                           rt_stream st, std::string &err) {
 	const bool fwd = a.kind == DSP_KIND_REDFT10;
 	const OpMul<float> lm = {(float)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(float)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
-	if (fwd) return fused ? split_fft_t<true, OpAny, OpAny>(a, fM, lop, sop, grid, smem, st, err)
-	                      : split_fft_t<true, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
-	return fused ? split_fft_t<false, OpAny, OpAny>(a, fM, lop, sop, grid, smem, st, err)
-	             : split_fft_t<false, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
+	if (fwd && !fused && !getenv("DSP_DCT_NO_FIXED")) {
+		if (fM.n == 256) return split_fft_t<8, true, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
+		if (fM.n == 512) return split_fft_t<9, true, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
+		if (fM.n == 1024) return split_fft_t<10, true, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
+	}
+	if (fwd) return fused ? split_fft_t<0, true, OpAny, OpAny>(a, fM, lop, sop, grid, smem, st, err)
+	                      : split_fft_t<0, true, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
+	return fused ? split_fft_t<0, false, OpAny, OpAny>(a, fM, lop, sop, grid, smem, st, err)
+	             : split_fft_t<0, false, OpMul<float>, OpMul<float>>(a, fM, lm, sm, grid, smem, st, err);
 }
 
 bool launch_split_outer_f32(const SplitArgs &a, const FastDesc &fN, bool fused, const OpAny &lop, const OpAny &sop, int nwarps,
