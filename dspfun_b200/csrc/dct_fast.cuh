@@ -356,21 +356,21 @@ template <class T> struct SmemNat {
 	DSP_DEVM C2<T> get(int k) const { return base[Pad<T>::of(k)]; }
 };
 // two global lines (rows A and B of the pair), element k of channel ch at [k*d + ch]
-// PLANAR: d == 1 and both lines present, known at compile time -- with a fixed-length F every k is "i + constant",
-// so the accesses become [base + immediate] instead of a 64-bit address computation each
-template <class T, class Op, bool PLANAR = false> struct GlobalRows {
+// DD > 0: the interleave d == DD and both lines present, known at compile time -- with a fixed-length F every k is
+// "i + constant", so the accesses become [base + immediate] instead of a 64-bit address computation each
+template <class T, class Op, int DD = 0> struct GlobalRows {
 	T *pa, *pb;                  // line bases (+ channel); pb = nullptr when the pair has no second line
 	int d, ax_slot;
 	Coord ca, cb;
 	const Op *op;
 	DSP_DEVM void put(int k, T xa, T xb) {
-		if (PLANAR) { pa[k] = (*op)(xa, ca); pb[k] = (*op)(xb, cb); return; }
+		if (DD) { pa[k * DD] = (*op)(xa, ca); pb[k * DD] = (*op)(xb, cb); return; }
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		pa[k * d] = (*op)(xa, ca);
 		if (pb) pb[k * d] = (*op)(xb, cb);
 	}
 	DSP_DEVM C2<T> get(int k) {
-		if (PLANAR) return C2<T>{(*op)(pa[k], ca), (*op)(pb[k], cb)};
+		if (DD) return C2<T>{(*op)(pa[k * DD], ca), (*op)(pb[k * DD], cb)};
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		const T xa = (*op)(pa[k * d], ca);
 		const T xb = pb ? (*op)(pb[k * d], cb) : (T)0;
@@ -639,7 +639,7 @@ DSP_DEV void row_move_planar4(const RowArgs &a, const F &f, const Op &op, int li
 
 // channel-interleaved float lines (D = 2..4 channels, 16-byte access legal, n % 4 == 0): one group = x in [4q, 4q+4)
 // of lines A and B = D vectors per line; the slot pattern per channel is the planar one.
-template <class T, int D, bool FWD, class Op, class F>
+template <class T, int D, bool FWD, class Op, class F, bool SIMPLE = false>
 DSP_DEV void row_move_inter4(const RowArgs &a, const F &f, const Op &op, int line0, int nl, int tid, int nthr, C2<T> *s) {
 	typedef typename VecOf<T>::type Vec;
 	const T *gin = (const T *)a.in;
@@ -652,10 +652,10 @@ DSP_DEV void row_move_inter4(const RowArgs &a, const F &f, const Op &op, int lin
 	for (int idx = tid; idx < total; idx += nthr) {
 		const int g = idx >> lgq, q = idx & ((1 << lgq) - 1);
 		const int la = line0 + 2 * g;
-		const bool hasb = 2 * g + 1 < nl;
+		const bool hasb = SIMPLE || 2 * g + 1 < nl;
 		Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 		long long ia, ib = 0, oa, ob = 0;
-		if (a.simple && !Op::kNeedsCoord) { ia = la * a.ls_in; ib = ia + a.ls_in; oa = la * a.ls_out; ob = oa + a.ls_out; }
+		if (SIMPLE || (a.simple && !Op::kNeedsCoord)) { ia = la * a.ls_in; ib = ia + a.ls_in; oa = la * a.ls_out; ob = oa + a.ls_out; }
 		else { outer_decode(a.o, (uint32_t)la, ia, oa, ca); if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb); }
 		T va[4 * D], vb[4 * D];
 		if (FWD) {
@@ -710,14 +710,15 @@ DSP_DEV void row_move_any(const RowArgs &a, const F &f, const Op &op, int line0,
 	else row_move<T, FWD, Op>(a, f, op, line0, nl, tid, nthr, s);
 }
 
-// PLANAR (chosen by the planner, lean ops only): d == 1, lines at one stride, every CTA owns whole line pairs,
-// 16-byte access legal -- the moves and the fused outer pass then run with all addressing hoisted.
-template <class T, bool FWD, class LoadOp, class StoreOp, class F, bool PLANAR = false>
+// DD > 0 (chosen at launch, lean ops only): interleave d == DD (1 planar, 3 RGB) at compile time, lines at one
+// stride, every CTA owns whole line pairs, 16-byte access legal -- the moves and the fused outer pass then run with
+// all addressing hoisted.
+template <class T, bool FWD, class LoadOp, class StoreOp, class F, int DD = 0>
 DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const StoreOp &sop, int cta, int t0, int t1,
                           int nthr, C2<T> *s) {
 	const T *gin = (const T *)a.in;
 	T *gout = (T *)a.out;
-	const int d = PLANAR ? 1 : a.d;
+	const int d = DD ? DD : a.d;
 	const int line0 = cta * a.lines_per_cta;
 	int nl = a.nlines - line0;
 	if (nl > a.lines_per_cta) nl = a.lines_per_cta;
@@ -749,7 +750,8 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 
 	if (FWD) {
 		for (int tid = t0; tid < t1; tid++) {
-			if (PLANAR) row_move_planar4_pick<T, true, LoadOp>(a, f, lop, line0, npairs, tid, nthr, s);
+			if (DD == 1) row_move_planar4_pick<T, true, LoadOp>(a, f, lop, line0, npairs, tid, nthr, s);
+			else if (DD > 1) row_move_inter4<T, (DD > 1 ? DD : 2), true, LoadOp, F, true>(a, f, lop, line0, nl, tid, nthr, s);
 			else row_move_any<T, true, LoadOp>(a, f, lop, line0, nl, tid, nthr, s);
 		}
 		DSP_SYNC();
@@ -760,12 +762,13 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 		}
 		// ---- outer pass + post-twiddle + direct global store
 		for (int tid = t0; tid < t1; tid++) {
-			if (PLANAR) {
+			if (DD) {
 				for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
-					GlobalRows<T, StoreOp, true> sink;
+					GlobalRows<T, StoreOp, DD> sink;
+					const int g = DD == 1 ? seq : seq / (DD ? DD : 1), ch = DD == 1 ? 0 : seq - g * DD;
 					sink.ca = Coord{0, 0, 0, 0, 0}; sink.cb = sink.ca;
-					sink.pa = gout + (long long)(line0 + 2 * seq) * a.ls_out; sink.pb = sink.pa + a.ls_out;
-					sink.d = 1; sink.ax_slot = a.ax_slot; sink.op = &sop;
+					sink.pa = gout + (long long)(line0 + 2 * g) * a.ls_out + ch; sink.pb = sink.pa + a.ls_out;
+					sink.d = DD; sink.ax_slot = a.ax_slot; sink.op = &sop;
 					dct2_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, sink);
 				});
 				continue;
@@ -790,12 +793,13 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 
 	// ---- DCT-III: outer pass reads the (k, n-k) pairs straight from global memory
 	for (int tid = t0; tid < t1; tid++) {
-		if (PLANAR) {
+		if (DD) {
 			for_outer_units(nseq, f.Mq(), tid, nthr, [&](int seq, int i) {
-				GlobalRows<T, LoadOp, true> src;
+				GlobalRows<T, LoadOp, DD> src;
+				const int g = DD == 1 ? seq : seq / (DD ? DD : 1), ch = DD == 1 ? 0 : seq - g * DD;
 				src.ca = Coord{0, 0, 0, 0, 0}; src.cb = src.ca;
-				src.pa = (T *)gin + (long long)(line0 + 2 * seq) * a.ls_in; src.pb = src.pa + a.ls_in;
-				src.d = 1; src.ax_slot = a.ax_slot; src.op = &lop;
+				src.pa = (T *)gin + (long long)(line0 + 2 * g) * a.ls_in + ch; src.pb = src.pa + a.ls_in;
+				src.d = DD; src.ax_slot = a.ax_slot; src.op = &lop;
 				dct3_outer_unit<T>(SmemBf<T, F>{s + seq * f.NPAD(), &f}, f, i, src);
 			});
 			continue;
@@ -822,7 +826,8 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 	}
 	contig_pass<T>(s, nseq, f, t0, t1, nthr);
 	for (int tid = t0; tid < t1; tid++) {
-		if (PLANAR) row_move_planar4_pick<T, false, StoreOp>(a, f, sop, line0, npairs, tid, nthr, s);
+		if (DD == 1) row_move_planar4_pick<T, false, StoreOp>(a, f, sop, line0, npairs, tid, nthr, s);
+		else if (DD > 1) row_move_inter4<T, (DD > 1 ? DD : 2), false, StoreOp, F, true>(a, f, sop, line0, nl, tid, nthr, s);
 		else row_move_any<T, false, StoreOp>(a, f, sop, line0, nl, tid, nthr, s);
 	}
 }

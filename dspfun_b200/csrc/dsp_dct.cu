@@ -521,10 +521,12 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		a.vec_in = pp.vec_in_layout && ain && !a.in_u8; a.vec_out = pp.vec_out_layout && aout && !a.out_u8;
 		a.pf_dist = pp.pf_dist;
 		const int nn = pp.ff.n;
-		const bool planar = pp.fast && f32 && !pp.fused && a.d == 1 && a.simple && a.vec_in && a.vec_out && nn >= 256 &&
-		                    nn <= 8192 && (a.lines_per_cta % 2) == 0 && (a.nlines % a.lines_per_cta) == 0 &&
-		                    !getenv("DSP_DCT_NO_FIXED") && !getenv("DSP_DCT_NO_PLANAR");
-		if (planar) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		// layout-specialised kernels: planar or RGB lines at one stride, whole line pairs in every CTA, 16-byte access
+		const bool spec = pp.fast && f32 && !pp.fused && (a.d == 1 || a.d == 3) && a.simple && a.vec_in && a.vec_out &&
+		                  nn >= 256 && nn <= 8192 && (a.lines_per_cta % 2) == 0 && (a.nlines % 2) == 0 &&
+		                  !getenv("DSP_DCT_NO_FIXED") && !getenv("DSP_DCT_NO_PLANAR");
+		if (spec && a.d == 1) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else if (spec) ok = launch_row_fast_f32i3(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 		else if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);

@@ -22,6 +22,7 @@ DSP_DECL_LAUNCH(launch_row_generic_f64, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f32, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f64, RowArgs)
 DSP_DECL_LAUNCH(launch_row_fast_f32p, RowArgs)     // planar specialisation (fixed lengths 256..8192, lean ops)
+DSP_DECL_LAUNCH(launch_row_fast_f32i3, RowArgs)    // the same for 3 interleaved channels (the image tools' RGB layout)
 DSP_DECL_LAUNCH(launch_col_generic_f32, ColArgs)
 DSP_DECL_LAUNCH(launch_col_generic_f64, ColArgs)
 DSP_DECL_LAUNCH(launch_col_fast_f32, ColArgs)

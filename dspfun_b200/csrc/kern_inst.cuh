@@ -7,6 +7,9 @@
 #ifndef KERN_ROW_MINB
 #define KERN_ROW_MINB 2
 #endif
+#ifndef KERN_DD
+#define KERN_DD 1             // interleave the KERN_PLANAR translation unit is specialised for (1 planar, 3 RGB)
+#endif
 
 namespace dsp {
 
@@ -29,7 +32,7 @@ namespace dsp {
 // NB: the element type and the row/fast flags are template parameters so that every translation unit
 // instantiates distinctly named kernels (same-signature templates in different TUs would be merged by the linker).
 // FAST: bit 0 = fast path, bit 1 = forward (fast kernels are specialised on the transform kind),
-// bit 2 = planar row specialisation (cta_row_fast<PLANAR>; its own TU, KERN_PLANAR),
+// bit 2 = layout-specialised row kernels (their own TUs, KERN_PLANAR), bits 4..6 = their interleave DD (KERN_DD),
 // bits 8.. = log2 n when the length is fixed at compile time (FastFixed), 0 = runtime length
 template <class TT, int ROW, int FAST, class L, class S>
 DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int cta, int t0, int t1, int nthr,
@@ -40,7 +43,7 @@ DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S
 		ff.tw = f.tw; ff.om = f.om; ff.sig = f.sig;
 #if KERN_ROW
 		typedef FastFixed<((FAST >> 8) != 0) ? (FAST >> 8) : 8> FF;
-		if (FAST & 4) cta_row_fast<KERN_T, (FAST & 2) != 0, L, S, FF, true>(a, ff, l, s, cta, t0, t1, nthr, smem);
+		if (FAST & 4) cta_row_fast<KERN_T, (FAST & 2) != 0, L, S, FF, ((FAST >> 4) & 7)>(a, ff, l, s, cta, t0, t1, nthr, smem);
 		else cta_row_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
 #else
 		cta_col_fast<KERN_T, (FAST & 2) != 0, L, S>(a, ff, l, s, cta, t0, t1, nthr, smem);
@@ -104,8 +107,8 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 		(void)fused;
 #define DSP_PLANAR_CASE(LG)                                                                                                  \
 	case (1 << LG):                                                                                                          \
-		return fw ? launch_t<KERN_T, KERN_ROW, 7 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err) \
-		          : launch_t<KERN_T, KERN_ROW, 5 | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
+		return fw ? launch_t<KERN_T, KERN_ROW, 7 | (KERN_DD << 4) | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err) \
+		          : launch_t<KERN_T, KERN_ROW, 5 | (KERN_DD << 4) | (LG << 8), OpMul<KERN_T>, OpMul<KERN_T>>(a, f, lm, sm, grid, block, smem, st, err);
 		switch (f.n) {
 			DSP_PLANAR_CASE(8) DSP_PLANAR_CASE(9) DSP_PLANAR_CASE(10) DSP_PLANAR_CASE(11) DSP_PLANAR_CASE(12) DSP_PLANAR_CASE(13)
 		default: break;
