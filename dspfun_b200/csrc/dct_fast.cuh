@@ -28,6 +28,7 @@ struct FastDesc {
 	int poff[4][16];             // poff[q][j] = Pad(j * Lprev_q) for radix-16 pass q (0..nmid-1 middle, nmid = outer)
 	FastDiv dHalf;               // divide by M/2+1 (outer-pass units per sequence)
 	// accessors shared with FastFixed (the compile-time variant below)
+	enum { kFixed = 0, kN = 0 };
 	DSP_HDM int N() const { return n; }
 	DSP_HDM int Mq() const { return M; }
 	DSP_HDM int R0() const { return r0; }
@@ -43,6 +44,7 @@ struct FastDesc {
 template <int LG> struct FastFixed {
 	const void *tw, *om;
 	const uint16_t *sig;
+	enum { kFixed = 1, kN = 1 << LG };
 	static constexpr int kA = LG - 4;
 	static constexpr int kL0raw = kA % 4, kKraw = (kA - kL0raw) / 4;
 	static constexpr int kL0 = (kL0raw == 0 && kKraw > 0) ? 4 : ((kL0raw == 1 && kKraw > 0) ? 5 : kL0raw);

@@ -133,6 +133,111 @@ DSP_DEV void split_move(const SplitArgs &a, const F &fM, const Op &op, int j, in
 	}
 }
 
+// ---- tile moves of sub-pass A with the sub-FFT length M fixed at compile time (F = FastFixed), 256 threads and
+// full TC-column tiles.  Thread = (column group cg, row phase r0); it walks rows r = r0 + DR u.  Everything that
+// depends on u is a compile-time constant: the general tile_move_lean spends ~20 instructions per row on the row
+// map, a 64-bit multiply and the predicate (ncu source view, profiles/r01_ncu_current_summary.md).
+template <int TC> struct FixedTile {
+	enum { GPR = TC / 4, DR = 256 / GPR };                               // column groups per row, rows per step
+	// Pad(r0 + DR u) - Pad(r0) for r0 < DR <= 64, DR | 256
+	DSP_HDM static constexpr int nat_delta(int u) { return u * (DR + DR / 16) + ((u * DR) >> 8); }
+};
+
+// image rows of sub-FFT j (Makhoul order: element e = 16 r + j sits in row 2e for e < n/2, else 2(n-1-e)+1)
+// -> digit-reversed slots.  First half of the rows ascends in steps of 32 DR image rows, second half descends.
+template <class T, int TC, class Op, class F>
+DSP_DEV void split_image_load_fixed(const T *gtile, long long rs, int j, const Op &op, const F &fM, int tid, C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	typedef FixedTile<TC> G;
+	const int M = F::kN, U = M / G::DR, UNR = U < 8 ? U : 8;
+	const int n = 16 * M;
+	const int cg = tid & (G::GPR - 1), r0 = tid / G::GPR;
+	C2<T> *sq = s + (2 * cg) * fM.NPAD();
+	const uint16_t *sg = fM.sig + r0;
+	const T *p1 = gtile + 4 * cg + (long long)(2 * (16 * r0 + j)) * rs;                                  // u = 0
+	const T *p2 = gtile + 4 * cg + (long long)(2 * (n - 1 - (16 * (r0 + G::DR * (U / 2)) + j)) + 1) * rs; // u = U/2
+	const long long step = (long long)(32 * G::DR) * rs;
+	const Coord cz = {0, 0, 0, 0, 0};
+#pragma unroll
+	for (int ub = 0; ub < U; ub += UNR) {
+		Vec v[UNR];
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int uu = ub + u;
+			v[u] = ldg_stream((const Vec *)(uu < U / 2 ? p1 + uu * step : p2 - (uu - U / 2) * step));
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int slot = (int)DSP_LDG(sg + G::DR * (ub + u));
+			sq[slot] = C2<T>{op(v[u].v[0], cz), op(v[u].v[1], cz)};
+			sq[fM.NPAD() + slot] = C2<T>{op(v[u].v[2], cz), op(v[u].v[3], cz)};
+		}
+	}
+}
+
+// natural-order smem rows -> scratch rows rowbase + r (rowbase = j M)
+template <class T, int TC, class F>
+DSP_DEV void split_scratch_store_fixed(T *gtile, long long ss, int rowbase, const F &fM, int tid, const C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	typedef FixedTile<TC> G;
+	const int M = F::kN, U = M / G::DR;
+	const int cg = tid & (G::GPR - 1), r0 = tid / G::GPR;
+	const C2<T> *sq = s + (2 * cg) * fM.NPAD() + Pad<T>::of(r0);
+	T *p = gtile + 4 * cg + (long long)(rowbase + r0) * ss;
+	const long long step = (long long)G::DR * ss;
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		const C2<T> z0 = sq[G::nat_delta(u)], z1 = sq[fM.NPAD() + G::nat_delta(u)];
+		Vec o;
+		o.v[0] = z0.x; o.v[1] = z0.y; o.v[2] = z1.x; o.v[3] = z1.y;
+		*(Vec *)(p + u * step) = o;
+	}
+}
+
+// sub-pass A'' load of a paired CTA (sub-sequences ja = jj and jb = 16 - jj, 0 < jj < 8) with M fixed: element kp of
+// ja pairs with element kb = M-1-kp of jb (rows k = 16 kp + ja and n - k); pre-twiddle in registers, both results to
+// the digit-reversed slots.  kp = k0 + DR u: rows, table entries and the k <= n/2 case are compile-time in u.
+template <class T, int TC, class Op, class F>
+DSP_DEV void split_inv_load_fixed(const T *gtile, long long rs, int ja, int jb, const Op &lop, const F &fM, const C2<T> *om,
+                                  int tid, C2<T> *sA, C2<T> *sB) {
+	typedef VecW<T, 4> Vec;
+	typedef FixedTile<TC> G;
+	const int M = F::kN, U = M / G::DR, UNR = U < 4 ? U : 4;
+	const int n = 16 * M;
+	const int cg = tid & (G::GPR - 1), k0 = tid / G::GPR;
+	C2<T> *qa = sA + (2 * cg) * fM.NPAD(), *qb = sB + (2 * cg) * fM.NPAD();
+	const T *pa = gtile + 4 * cg + (long long)(16 * k0 + ja) * rs;
+	const T *pb = gtile + 4 * cg + (long long)(16 * (M - 1 - k0) + jb) * rs;
+	const long long step = (long long)(16 * G::DR) * rs;
+	const uint16_t *sgA = fM.sig + k0, *sgB = fM.sig + (M - 1 - k0);
+	const C2<T> *omA = om + (16 * k0 + ja), *omB = om + (n - 16 * k0 - ja);
+	const Coord cz = {0, 0, 0, 0, 0};
+#pragma unroll
+	for (int ub = 0; ub < U; ub += UNR) {
+		Vec va[UNR], vb[UNR];
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			va[u] = ldg_stream((const Vec *)(pa + (ub + u) * step));
+			vb[u] = ldg_stream((const Vec *)(pb - (ub + u) * step));
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int uu = ub + u;
+			const int sk = (int)DSP_LDG(sgA + G::DR * uu), sn = (int)DSP_LDG(sgB - G::DR * uu);
+			const bool low = uu < U / 2;                              // k <= n - k
+			const C2<T> w = low ? ldg_c2(omA + 16 * G::DR * uu) : ldg_c2(omB - 16 * G::DR * uu);
+#pragma unroll
+			for (int p = 0; p < 2; p++) {
+				const C2<T> xa = C2<T>{lop(va[u].v[2 * p], cz), lop(va[u].v[2 * p + 1], cz)};
+				const C2<T> xb = C2<T>{lop(vb[u].v[2 * p], cz), lop(vb[u].v[2 * p + 1], cz)};
+				C2<T> wk, wn;
+				if (low) { dct3_pair<T>(w, xa, xb, wk, wn); qa[p * fM.NPAD() + sk] = wk; qb[p * fM.NPAD() + sn] = wn; }
+				else { dct3_pair<T>(w, xb, xa, wk, wn); qb[p * fM.NPAD() + sn] = wk; qa[p * fM.NPAD() + sk] = wn; }
+			}
+		}
+	}
+}
+
 struct RowSplitImage { int j, n; DSP_DEVM int operator()(int r) const { return split_row(16 * r + j, n); } };
 struct RowSplitScratch { int base; DSP_DEVM int operator()(int r) const { return base + r; } };
 struct SlotSig { const uint16_t *sig; DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + r); } };
@@ -167,15 +272,32 @@ DSP_DEV void cta_split_fft(const SplitArgs &a, const F &fM, const LoadOp &lop, c
 	int ncl = a.pcol0 + a.pcols - col0;
 	if (ncl > a.tc) ncl = a.tc;
 	const int nseq = (ncl + 1) / 2;
+	// fixed-length lean moves: compile-time M, 256 threads, full aligned 32-column tile, coordinate-free op
+	const bool fixed = F::kFixed && sizeof(T) == 4 && nthr == 256 && a.tc == 32 && ncl == 32 && !LoadOp::kNeedsCoord &&
+	                   (F::kN % 64) == 0;
 	if (FWD) {
-		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, true, LoadOp>(a, fM, lop, j, col0, ncl, false, tid, nthr, s);
+		bool done = false;
+		if constexpr (F::kFixed != 0) {
+			if (fixed) {
+				for (int tid = t0; tid < t1; tid++) split_image_load_fixed<T, 32, LoadOp>((const T *)a.in + col0, a.ax_is, j, lop, fM, tid, s);
+				done = true;
+			}
+		}
+		if (!done) for (int tid = t0; tid < t1; tid++) split_move_any<T, true, true, LoadOp>(a, fM, lop, j, col0, ncl, false, tid, nthr, s);
 		DSP_SYNC();
 		contig_pass<T>(s, nseq, fM, t0, t1, nthr);
 		for (int q = 0; q <= fM.NMID(); q++) {
 			for (int tid = t0; tid < t1; tid++) mid_pass<T, true>(s, nseq, fM, q, tid, nthr);
 			DSP_SYNC();
 		}
-		for (int tid = t0; tid < t1; tid++) split_move_any<T, false, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
+		done = false;
+		if constexpr (F::kFixed != 0) {
+			if (fixed) {
+				for (int tid = t0; tid < t1; tid++) split_scratch_store_fixed<T, 32>((T *)a.scratch + (col0 - a.pcol0), a.ax_ss, j * F::kN, fM, tid, s);
+				done = true;
+			}
+		}
+		if (!done) for (int tid = t0; tid < t1; tid++) split_move_any<T, false, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
 	} else {
 		for (int tid = t0; tid < t1; tid++) split_move_any<T, true, false, OpNone>(a, fM, OpNone(), j, col0, ncl, false, tid, nthr, s);
 		DSP_SYNC();
@@ -306,7 +428,14 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const F &fM, const FastDesc &
 	const int UNR = 4;
 	const int npair = paired ? M : (jj == 0 ? M / 2 + 1 : M / 2);
 	C2<T> *sBB = paired ? sB : sA;
+	bool fixed = false;
+	if constexpr (F::kFixed != 0) fixed = sizeof(T) == 4 && nthr == 256 && a.tci == 16 && (F::kN % 128) == 0 && !LoadOp::kNeedsCoord;
+	if constexpr (F::kFixed != 0) {
+		if (fixed && paired)
+			for (int tid = t0; tid < t1; tid++) split_inv_load_fixed<T, 16, LoadOp>(gin, a.ax_is, ja, jb, lop, fM, om, tid, sA, sB);
+	}
 	for (int tid = t0; tid < t1; tid++) {
+		if (fixed && paired) break;
 		const int cg = tid & ((1 << lg) - 1), dk = nthr >> lg;
 		const T *gp = gin + 4 * cg;
 		C2<T> *qa = sA + (2 * cg) * fM.NPAD(), *qb = sBB + (2 * cg) * fM.NPAD();
@@ -353,6 +482,15 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const F &fM, const FastDesc &
 	}
 	// ---- natural-order results to scratch blocks j (and 16 - j)
 	T *gs = (T *)a.scratch + (col0 - a.pcol0);
+	if constexpr (F::kFixed != 0) {
+		if (fixed) {
+			for (int tid = t0; tid < t1; tid++) {
+				split_scratch_store_fixed<T, 16>(gs, a.ax_ss, ja * M, fM, tid, sA);
+				if (paired) split_scratch_store_fixed<T, 16>(gs, a.ax_ss, jb * M, fM, tid, sB);
+			}
+			return;
+		}
+	}
 	for (int tid = t0; tid < t1; tid++) {
 		tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{ja * M}, SlotNat<T>(), fM.NPAD(), tid, nthr, sA);
 		if (paired) tile_move_lean<T, false, OpNone>(gs, gs, a.ax_ss, M, lg, OpNone(), false, RowSplitScratch{jb * M}, SlotNat<T>(), fM.NPAD(), tid, nthr, sB);

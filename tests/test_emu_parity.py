@@ -44,6 +44,13 @@ def test_planar_3d_embed(lib, prec, kind):
     cases.check_planar_3d_embed(lib, prec, (16, 15, 20), (16, 27, 36), kind)
 
 
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(4096, 64, 1), (4096, 40, 1), (8192, 32, 1), (4096, 24, 3)])
+def test_split_column_pass(lib, kind, shape):
+    """long power-of-two columns: the two-sub-pass split path (dct_split.cuh), full fixed-length tiles and ragged ones"""
+    cases.check_interleaved_2d(lib, "f", *shape, kind)
+
+
 @pytest.mark.parametrize("prec", ["f", "d"])
 def test_batched_images_roundtrip(lib, prec):
     cases.check_batched_images(lib, prec, 5, 16, 24, 3)

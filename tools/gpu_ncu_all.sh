@@ -4,6 +4,6 @@ mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e"
 N="ncu --set full --clock-control none --import-source on -f"
 timeout 600 $N -k regex:k_pass -s 6 -c 2 -o gpurun_out/prof_row $B > gpurun_out/ncu_row.log 2>&1
-timeout 600 $N -k regex:'k_split_(fft|outer)' -s 192 -c 2 -o gpurun_out/prof_splitfwd $B > gpurun_out/ncu_splitfwd.log 2>&1
+timeout 600 $N -k regex:k_split_[fo] -s 96 -c 2 -o gpurun_out/prof_splitfwd $B > gpurun_out/ncu_splitfwd.log 2>&1
 timeout 600 $N -k regex:k_split_inv -s 96 -c 2 -o gpurun_out/prof_splitinv $B > gpurun_out/ncu_splitinv.log 2>&1
 ls -la gpurun_out/*.ncu-rep
