@@ -69,3 +69,35 @@ def scan_frames(pixels, index_map, step=1, nframes=None, lib=None):
     frames = [s.frame(i * step, min((i + 1) * step, limit)) for i in range(nframes)]
     s.destroy()
     return frames
+
+
+def shard_range(nframes, rank, world):
+    """Contiguous frame range [f0, f1) of `rank` (the first nframes % world ranks take one frame more)."""
+    base, rem = divmod(nframes, world)
+    f0 = rank * base + min(rank, rem)
+    return f0, f0 + base + (1 if rank < rem else 0)
+
+
+def scan_frames_sharded(pixels, index_map, step=1, nframes=None, rank=None, world=None, lib=None):
+    """The scan main loop split over `world` GPUs, one process per GPU (frames are independent given the
+    coefficient plane and the index map; only the running sum is a prefix dependency, scan.c:454).
+
+    The prefix is linear: sum before frame f0 = DC + IDCT(all coefficients with index < f0*step), so a rank builds
+    its starting sum with ONE extra masked inverse instead of replaying f0 frames -- no data-path collective.
+    Every rank holds the pixels and the index map (a broadcast at start in a real run) and returns
+    (f0, frames of its range).  The prefix inverse adds the f0 partial images in one rounding instead of f0, so a
+    sharded frame agrees with the sequential one to the coefficient tolerance, not bit for bit.
+    """
+    if rank is None or world is None:
+        import torch.distributed as dist
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    limit = int(np.max(index_map)) + 1
+    if not nframes or nframes > limit // step:
+        nframes = (limit + step - 1) // step                       # scan.c:346-347
+    f0, f1 = shard_range(nframes, rank, world)
+    s = Scan(pixels, index_map, lib=lib)
+    if f0 > 0:
+        s.frame(0, min(f0 * step, limit), want=False)              # the prefix: one inverse, frame not fetched
+    frames = [s.frame(i * step, min((i + 1) * step, limit)) for i in range(f0, f1)]
+    s.destroy()
+    return f0, frames

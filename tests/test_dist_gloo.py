@@ -68,3 +68,51 @@ def test_single_rank_uses_one_rank3_plan():
     out = d3.forward(torch.from_numpy(vol.copy()))
     assert od.rel_l2(out.numpy(), od.dctn_fast(vol, [od.REDFT10] * 3)) < 1e-12
     d3.destroy()
+
+
+def _scan_worker(rank, world, port, h, w, d, step, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dspfun_b200 import scan as gscan
+        from tests.emu import emu
+        rng = np.random.default_rng(5)
+        px = rng.random((h, w, d))
+        idx = gscan.order_diagonal(h, w)
+        f0, frames = gscan.scan_frames_sharded(px, idx, step=step, lib=emu.load())     # rank / world from the group
+        q.put((rank, f0, [f.copy() for f in frames]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [(12, 10, 3, 1), (16, 16, 1, 3), (9, 14, 2, 2)])
+def test_scan_sharded_world2(cfg):
+    """scan's frames over 2 ranks with the linear-prefix start == the sequential oracle"""
+    from oracle import pipelines as op
+    from dspfun_b200 import scan as gscan
+    h, w, d, step = cfg
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scan_worker, args=(r, 2, port, h, w, d, step, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    px = np.random.default_rng(5).random((h, w, d))
+    ref, _ = op.scan_frames(px, gscan.order_diagonal(h, w), step=step)
+    got = [f for _, _, fr in res for f in fr]
+    assert res[0][1] == 0 and res[1][1] == len(res[0][2]) and len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert od.rel_l2(g, r) < 1e-12
+    assert od.rel_l2(got[-1], px) < 1e-12                       # the last frame is the image itself
+
+
+def test_scan_shard_ranges_cover():
+    from dspfun_b200.scan import shard_range
+    for n in (1, 5, 16, 17):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))

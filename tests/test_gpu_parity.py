@@ -270,3 +270,21 @@ def test_zoom_config2_spot_check(lib):
         yb = np.cos(np.pi * (j / 2 + 0.5) * u / n); yb[0] = 0.5
         want = yb @ C[:, :, c] @ xb / (n * n)
         assert abs(out[j, i, c] - want) < 2e-5, (j, i, c, out[j, i, c], want)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_scan_sharded_prefix(lib, prec):
+    """frame ranges of 3 'ranks' started from the linear prefix (scan_frames_sharded) == the sequential scan"""
+    from dspfun_b200 import scan as gscan
+    h, w, d, step = 64, 48, 3, 5
+    px = np.random.default_rng(21).random((h, w, d)).astype(cases.DT[prec])
+    idx = gscan.order_diagonal(h, w)
+    seq = gscan.scan_frames(px, idx, step=step, lib=lib)
+    got = []
+    for r in range(3):
+        f0, fr = gscan.scan_frames_sharded(px, idx, step=step, rank=r, world=3, lib=lib)
+        assert f0 == len(got)
+        got += fr
+    assert len(got) == len(seq)
+    for g, sfr in zip(got, seq):
+        assert od.rel_l2(g, sfr) < cases.OK[prec]
