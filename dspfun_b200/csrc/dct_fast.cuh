@@ -996,6 +996,54 @@ DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
 	return aligned && ncl == tc && (tc % 4) == 0 && (gpr & (gpr - 1)) == 0 && (nthr % gpr) == 0;
 }
 
+// ---- the same move with the axis length fixed at compile time (F = FastFixed), 256 threads and a full TC-column
+// tile: thread = (column group cg, row phase r0) walks rows r = r0 + DR u; the global row offsets, the natural-order
+// slots Pad(r0) + nat_delta(u) and the offsets into the slot table are compile-time in u.
+template <int TC> struct FixedTile {
+	enum { GPR = TC / 4, DR = 256 / GPR };                               // column groups per row, rows per step
+	// Pad(r0 + DR u) - Pad(r0) for r0 < DR <= 64, DR | 256, r0 + DR u < 4096
+	DSP_HDM static constexpr int nat_delta(int u) { return u * (DR + DR / 16) + ((u * DR) >> 8); }
+};
+template <class T, int TC, bool IN, bool SCATTER, class Op, class F>
+DSP_DEV void col_tile_fixed(const T *gin, T *gout, long long rs, const Op &op, bool negim, const F &f, int tid, C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	typedef FixedTile<TC> G;
+	const int n = F::kN, U = n / G::DR, UNR = U < 8 ? U : 8;
+	const int cg = tid & (G::GPR - 1), r0 = tid / G::GPR;
+	C2<T> *sq = s + (2 * cg) * f.NPAD();
+	const T *gp = gin + 4 * cg + (long long)r0 * rs;
+	T *gq = gout + 4 * cg + (long long)r0 * rs;
+	const long long step = (long long)G::DR * rs;
+	// SCATTER: slot = sig[makhoul(r)]; r keeps the parity of r0, so the table index moves by +-DR/2 per step
+	const uint16_t *sg = f.sig + makhoul(r0, n);
+	const int sdir = (r0 & 1) ? -(G::DR / 2) : (G::DR / 2);
+	const C2<T> *snat = sq + Pad<T>::of(r0);
+	const Coord cz = {0, 0, 0, 0, 0};
+#pragma unroll
+	for (int ub = 0; ub < U; ub += UNR) {
+		Vec v[UNR];
+		if (IN) {
+#pragma unroll
+			for (int u = 0; u < UNR; u++) v[u] = ldg_stream((const Vec *)(gp + (ub + u) * step));
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int uu = ub + u;
+			C2<T> *p0 = SCATTER ? sq + (int)DSP_LDG(sg + sdir * uu) : (C2<T> *)snat + G::nat_delta(uu);
+			if (IN) {
+				p0[0] = C2<T>{op(v[u].v[0], cz), op(v[u].v[1], cz)};
+				p0[f.NPAD()] = C2<T>{op(v[u].v[2], cz), op(v[u].v[3], cz)};
+			} else {
+				const C2<T> z0 = p0[0], z1 = p0[f.NPAD()];
+				Vec o;
+				o.v[0] = op(z0.x, cz); o.v[1] = op(negim ? -z0.y : z0.y, cz);
+				o.v[2] = op(z1.x, cz); o.v[3] = op(negim ? -z1.y : z1.y, cz);
+				*(Vec *)(gq + uu * step) = o;
+			}
+		}
+	}
+}
+
 // picks the access width: full 16-byte groups when the tile allows it, else 8-byte (float) pairs, else scalar
 template <class T, bool IN, class Op, class F>
 DSP_DEV void col_move_any(const ColArgs &a, const F &f, const Op &op, bool scatter, bool negim, int col0, int ncl,
@@ -1006,6 +1054,18 @@ DSP_DEV void col_move_any(const ColArgs &a, const F &f, const Op &op, bool scatt
 		const T *gin = (const T *)a.in + gbase + col0;
 		T *gout = (T *)a.out + gbase + col0;
 		const long long rs = IN ? a.ax_is : a.ax_os;
+		if constexpr (F::kFixed != 0 && sizeof(T) == 4) {
+			if (nthr == 256 && F::kN <= 4096) {
+#define DSP_COL_FIXED(TC)                                                                                              \
+	if (a.tc == TC && (F::kN % (256 / (TC / 4))) == 0) {                                                               \
+		if (scatter) col_tile_fixed<T, TC, IN, true, Op>(gin, gout, rs, op, negim, f, tid, s);                         \
+		else col_tile_fixed<T, TC, IN, false, Op>(gin, gout, rs, op, negim, f, tid, s);                                \
+		return;                                                                                                        \
+	}
+				DSP_COL_FIXED(32) DSP_COL_FIXED(16)
+#undef DSP_COL_FIXED
+			}
+		}
 		const int lg = ilog2(a.tc / 4);
 		if (scatter) tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lg, op, negim, RowIdent(), SlotSigMakhoul{f.sig, f.N()}, f.NPAD(), tid, nthr, s);
 		else tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lg, op, negim, RowIdent(), SlotNat<T>(), f.NPAD(), tid, nthr, s);

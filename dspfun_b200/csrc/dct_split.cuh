@@ -137,12 +137,6 @@ DSP_DEV void split_move(const SplitArgs &a, const F &fM, const Op &op, int j, in
 // full TC-column tiles.  Thread = (column group cg, row phase r0); it walks rows r = r0 + DR u.  Everything that
 // depends on u is a compile-time constant: the general tile_move_lean spends ~20 instructions per row on the row
 // map, a 64-bit multiply and the predicate (ncu source view, profiles/r01_ncu_current_summary.md).
-template <int TC> struct FixedTile {
-	enum { GPR = TC / 4, DR = 256 / GPR };                               // column groups per row, rows per step
-	// Pad(r0 + DR u) - Pad(r0) for r0 < DR <= 64, DR | 256
-	DSP_HDM static constexpr int nat_delta(int u) { return u * (DR + DR / 16) + ((u * DR) >> 8); }
-};
-
 // image rows of sub-FFT j (Makhoul order: element e = 16 r + j sits in row 2e for e < n/2, else 2(n-1-e)+1)
 // -> digit-reversed slots.  First half of the rows ascends in steps of 32 DR image rows, second half descends.
 template <class T, int TC, class Op, class F>

@@ -51,6 +51,12 @@ def test_split_column_pass(lib, kind, shape):
     cases.check_interleaved_2d(lib, "f", *shape, kind)
 
 
+def test_fixed_length_column_tiles(lib):
+    """batches large enough for 32- and 16-column tiles: the compile-time-length column moves (col_tile_fixed)"""
+    cases.check_batched_images(lib, "f", 10, 256, 1024, 1)      # n = 256, 32-column tiles
+    cases.check_batched_images(lib, "f", 25, 1024, 64, 3)       # n = 1024, 16-column tiles, RGB rows
+
+
 @pytest.mark.parametrize("prec", ["f", "d"])
 def test_batched_images_roundtrip(lib, prec):
     cases.check_batched_images(lib, prec, 5, 16, 24, 3)
