@@ -306,7 +306,10 @@ DSP_DEV void cta_split_fft(const SplitArgs &a, const F &fM, const LoadOp &lop, c
 
 // ------------------------------------------------------------------------------------------------ sub-pass B
 // one column pair of the image: rows k of two adjacent columns, through the fused op
-template <class T, class Op> struct GlobalCols {
+// LEAN (chosen at launch): every pair has both columns, 8-byte access is legal, the op ignores coordinates and the
+// image spans < 2^31 elements, so an access is one 32-bit multiply-add on the pointer instead of a branch, a
+// select and a 64-bit address computation.
+template <class T, class Op, bool LEAN = false> struct GlobalCols {
 	T *p;                        // image + column
 	long long rs;                // row stride (elements)
 	bool hasb, vec;              // second column exists; 8-byte access legal
@@ -314,6 +317,7 @@ template <class T, class Op> struct GlobalCols {
 	Coord ca, cb;
 	const Op *op;
 	DSP_DEVM void put(int k, T xa, T xb) {
+		if (LEAN) { *(C2<T> *)(p + (uint32_t)k * (uint32_t)rs) = C2<T>{(*op)(xa, ca), (*op)(xb, cb)}; return; }
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		const T ya = (*op)(xa, ca), yb = hasb ? (*op)(xb, cb) : (T)0;
 		T *q = p + (long long)k * rs;
@@ -321,6 +325,7 @@ template <class T, class Op> struct GlobalCols {
 		else { q[0] = ya; if (hasb) q[1] = yb; }
 	}
 	DSP_DEVM C2<T> get(int k) {
+		if (LEAN) { const C2<T> v = *(const C2<T> *)(p + (uint32_t)k * (uint32_t)rs); return C2<T>{(*op)(v.x, ca), (*op)(v.y, cb)}; }
 		ca.set(ax_slot, k); cb.set(ax_slot, k);
 		const T *q = p + (long long)k * rs;
 		C2<T> v;
@@ -331,7 +336,7 @@ template <class T, class Op> struct GlobalCols {
 };
 
 // thread = (column pair, unit i): lanes run along the columns, one warp per unit
-template <class T, bool FWD, class LoadOp, class StoreOp>
+template <class T, bool FWD, class LoadOp, class StoreOp, bool LEAN = false>
 DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const LoadOp &lop, const StoreOp &sop, int gwarp, int lane) {
 	const int group = gwarp % a.ngroups, i = gwarp / a.ngroups;
 	if (!FWD && a.pf_warps > 0) {
@@ -365,12 +370,12 @@ DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const Lo
 		cb.set(a.col_slot, x); cb.ch = ch;
 	}
 	if (FWD) {
-		GlobalCols<T, StoreOp> sink;
+		GlobalCols<T, StoreOp, LEAN> sink;
 		sink.p = (T *)a.out + col; sink.rs = a.ax_os; sink.hasb = hasb; sink.vec = hasb && (a.ax_os % 2) == 0 && (((size_t)a.out / sizeof(T) + col) % 2) == 0;
 		sink.ax_slot = a.ax_slot; sink.ca = ca; sink.cb = cb; sink.op = &sop;
 		dct2_outer_unit<T>(bf, fN, i, sink);
 	} else {
-		GlobalCols<T, LoadOp> src;
+		GlobalCols<T, LoadOp, LEAN> src;
 		src.p = (T *)a.in + col; src.rs = a.ax_is; src.hasb = hasb; src.vec = hasb && (a.ax_is % 2) == 0 && (((size_t)a.in / sizeof(T) + col) % 2) == 0;
 		src.ax_slot = a.ax_slot; src.ca = ca; src.cb = cb; src.op = &lop;
 		dct3_outer_unit<T>(bf, fN, i, src);
@@ -491,7 +496,7 @@ DSP_DEV void cta_split_inv_fft(const SplitArgs &a, const F &fM, const FastDesc &
 	}
 }
 
-template <class T, class StoreOp>
+template <class T, class StoreOp, bool LEAN = false>
 DSP_DEV void split_inv_outer_thread(const SplitArgs &a, const FastDesc &fN, const StoreOp &sop, int gwarp, int lane) {
 	const int group = gwarp % a.ngroups, i = gwarp / a.ngroups;
 	if (i >= a.M) return;
@@ -502,15 +507,21 @@ DSP_DEV void split_inv_outer_thread(const SplitArgs &a, const FastDesc &fN, cons
 	const C2<T> *g0 = (const C2<T> *)a.scratch + pair + (long long)i * (a.ax_ss / 2);
 	const long long js = (long long)a.M * (a.ax_ss / 2);
 	C2<T> v[16], w[16];
+	if (LEAN) {                                                 // the scratch panel is far below 2^31 elements
+		const uint32_t js32 = (uint32_t)a.M * (uint32_t)(a.ax_ss / 2);
 #pragma unroll
-	for (int j = 0; j < 16; j++) v[j] = g0[j * js];
+		for (int j = 0; j < 16; j++) v[j] = g0[(uint32_t)j * js32];
+	} else {
+#pragma unroll
+		for (int j = 0; j < 16; j++) v[j] = g0[j * js];
+	}
 	if (i != 0) {
 		tw_powers<T>((const C2<T> *)fN.tw, i, w);
 #pragma unroll
 		for (int j = 1; j < 16; j++) v[j] = cmul(v[j], w[j]);
 	}
 	Dft<T, 16>::run(v);
-	GlobalCols<T, StoreOp> sink;
+	GlobalCols<T, StoreOp, LEAN> sink;
 	sink.p = (T *)a.out + col; sink.rs = a.ax_os; sink.hasb = hasb;
 	sink.vec = hasb && (a.ax_os % 2) == 0 && (((size_t)a.out / sizeof(T) + col) % 2) == 0;
 	sink.ax_slot = a.ax_slot; sink.op = &sop;

@@ -2,6 +2,7 @@
 #include "dsp_kernels.h"
 #include "dct_split.cuh"
 #include <vector>
+#include <cstdint>
 #include <cstdlib>
 
 #ifndef DSP_SPLIT_MINB
@@ -36,11 +37,11 @@ k_split_fft(const __grid_constant__ SplitArgs a, const __grid_constant__ FastDes
 	extern __shared__ __align__(16) unsigned char smem[];
 	split_fft_body<LGM, FWD, L, S>(a, fM, l, s, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, kThreads, (C2<float> *)smem);
 }
-template <bool FWD, class L, class S>
+template <bool FWD, class L, class S, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 2)
 k_split_outer(const __grid_constant__ SplitArgs a, const __grid_constant__ FastDesc fN, const __grid_constant__ L l,
               const __grid_constant__ S s) {
-	split_outer_thread<float, FWD, L, S>(a, fN, l, s, (int)blockIdx.x * (kThreads / 32) + (int)threadIdx.x / 32, (int)threadIdx.x % 32);
+	split_outer_thread<float, FWD, L, S, LEAN>(a, fN, l, s, (int)blockIdx.x * (kThreads / 32) + (int)threadIdx.x / 32, (int)threadIdx.x % 32);
 }
 #endif
 
@@ -52,12 +53,18 @@ k_split_inv_fft(const __grid_constant__ SplitArgs a, const __grid_constant__ Fas
 	extern __shared__ __align__(16) unsigned char smem[];
 	split_inv_fft_body<LGM, L>(a, fM, fN, l, (int)blockIdx.x, (int)threadIdx.x, (int)threadIdx.x + 1, kThreads, (C2<float> *)smem);
 }
-template <class S>
+template <class S, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 3)
 k_split_inv_outer(const __grid_constant__ SplitArgs a, const __grid_constant__ FastDesc fN, const __grid_constant__ S s) {
-	split_inv_outer_thread<float, S>(a, fN, s, (int)blockIdx.x * (kThreads / 32) + (int)threadIdx.x / 32, (int)threadIdx.x % 32);
+	split_inv_outer_thread<float, S, LEAN>(a, fN, s, (int)blockIdx.x * (kThreads / 32) + (int)threadIdx.x / 32, (int)threadIdx.x % 32);
 }
 #endif
+
+// image side of sub-pass B: whole column pairs, 8-byte aligned rows, < 2^31 elements (GlobalCols<LEAN>)
+static bool outer_lean(const SplitArgs &a, const void *img, long long rs) {
+	return (a.pcol0 % 2) == 0 && (a.pcols % 2) == 0 && (rs % 2) == 0 && ((uintptr_t)img % 8) == 0 &&
+	       (long long)a.n * rs < (1ll << 31) && !getenv("DSP_DCT_NO_FIXED");
+}
 
 // DIT-style inverse (lean only: full 16-column tiles, plain scale ops)
 template <int LGM>
@@ -92,14 +99,19 @@ bool launch_split_inv_fft_f32(const SplitArgs &a, const FastDesc &fM, const Fast
 
 bool launch_split_inv_outer_f32(const SplitArgs &a, const FastDesc &fN, const OpAny &sop, int nwarps, rt_stream st, std::string &err) {
 	const OpMul<float> sm = {(float)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
+	const bool lean = outer_lean(a, a.out, a.ax_os);
 #if DSP_GPU
 	const int wpb = kThreads / 32;
-	k_split_inv_outer<OpMul<float>><<<(nwarps + wpb - 1) / wpb, kThreads, 0, st>>>(a, fN, sm);
+	if (lean) k_split_inv_outer<OpMul<float>, true><<<(nwarps + wpb - 1) / wpb, kThreads, 0, st>>>(a, fN, sm);
+	else k_split_inv_outer<OpMul<float>, false><<<(nwarps + wpb - 1) / wpb, kThreads, 0, st>>>(a, fN, sm);
 	return rt_ok(cudaGetLastError(), err, "split inverse outer launch");
 #else
 	(void)st; (void)err;
 	for (int w = 0; w < nwarps; w++)
-		for (int lane = 0; lane < 32; lane++) split_inv_outer_thread<float, OpMul<float>>(a, fN, sm, w, lane);
+		for (int lane = 0; lane < 32; lane++) {
+			if (lean) split_inv_outer_thread<float, OpMul<float>, true>(a, fN, sm, w, lane);
+			else split_inv_outer_thread<float, OpMul<float>, false>(a, fN, sm, w, lane);
+		}
 	return true;
 #endif
 }
@@ -122,16 +134,16 @@ static bool split_fft_t(const SplitArgs &a, const FastDesc &fM, const L &l, cons
 #endif
 }
 
-template <bool FWD, class L, class S>
+template <bool FWD, class L, class S, bool LEAN>
 static bool split_outer_t(const SplitArgs &a, const FastDesc &fN, const L &l, const S &s, int nwarps, rt_stream st, std::string &err) {
 #if DSP_GPU
 	const int wpb = kThreads / 32;
-	k_split_outer<FWD, L, S><<<(nwarps + wpb - 1) / wpb, kThreads, 0, st>>>(a, fN, l, s);
+	k_split_outer<FWD, L, S, LEAN><<<(nwarps + wpb - 1) / wpb, kThreads, 0, st>>>(a, fN, l, s);
 	return rt_ok(cudaGetLastError(), err, "split outer launch");
 #else
 	(void)st; (void)err;
 	for (int w = 0; w < nwarps; w++)
-		for (int lane = 0; lane < 32; lane++) split_outer_thread<float, FWD, L, S>(a, fN, l, s, w, lane);
+		for (int lane = 0; lane < 32; lane++) split_outer_thread<float, FWD, L, S, LEAN>(a, fN, l, s, w, lane);
 	return true;
 #endif
 }
@@ -155,10 +167,12 @@ bool launch_split_outer_f32(const SplitArgs &a, const FastDesc &fN, bool fused, 
                             rt_stream st, std::string &err) {
 	const bool fwd = a.kind == DSP_KIND_REDFT10;
 	const OpMul<float> lm = {(float)(lop.kind == OP_SCALE ? lop.p[0] : 1.0)}, sm = {(float)(sop.kind == OP_SCALE ? sop.p[0] : 1.0)};
-	if (fwd) return fused ? split_outer_t<true, OpAny, OpAny>(a, fN, lop, sop, nwarps, st, err)
-	                      : split_outer_t<true, OpMul<float>, OpMul<float>>(a, fN, lm, sm, nwarps, st, err);
-	return fused ? split_outer_t<false, OpAny, OpAny>(a, fN, lop, sop, nwarps, st, err)
-	             : split_outer_t<false, OpMul<float>, OpMul<float>>(a, fN, lm, sm, nwarps, st, err);
+	if (fwd && !fused && outer_lean(a, a.out, a.ax_os))
+		return split_outer_t<true, OpMul<float>, OpMul<float>, true>(a, fN, lm, sm, nwarps, st, err);
+	if (fwd) return fused ? split_outer_t<true, OpAny, OpAny, false>(a, fN, lop, sop, nwarps, st, err)
+	                      : split_outer_t<true, OpMul<float>, OpMul<float>, false>(a, fN, lm, sm, nwarps, st, err);
+	return fused ? split_outer_t<false, OpAny, OpAny, false>(a, fN, lop, sop, nwarps, st, err)
+	             : split_outer_t<false, OpMul<float>, OpMul<float>, false>(a, fN, lm, sm, nwarps, st, err);
 }
 
 }  // namespace dsp
