@@ -134,9 +134,8 @@ DSP_DEV VecOf<double>::type ldg_stream(const VecOf<double>::type *p) {
 	asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
 	return r;
 }
-#else
-template <class V> DSP_DEV V ldg_stream(const V *p) { return *p; }
 #endif
+template <class V> DSP_DEV V ldg_stream(const V *p) { return *p; }      // any other vector type: plain load
 
 // L2 prefetch of the 128-byte line holding p (no data returned; the transfer overlaps whatever runs next)
 DSP_DEV void prefetch_l2(const void *p) {
@@ -265,6 +264,45 @@ template <class T, int R> struct DftOdd {
 	}
 };
 
+// composite radix R = R1 R2 in registers: x[R2 a + b] -> R1-point DFTs over a, twiddle W_R^{bq}, R2-point DFTs over
+// b -> y[q + R1 p].  Merging 3*5 and 3*3 saves one full shared-memory pass each (1080 = 15*9*8, 1920 = 15*8*16).
+template <class T, int R1, int R2> struct DftComp {
+	DSP_DEVM static void run(C2<T> *v, const T *cs, const T *sn) {
+		const int R = R1 * R2;
+		C2<T> t[R2][R1];
+#pragma unroll
+		for (int b = 0; b < R2; b++) {
+			C2<T> u[R1];
+#pragma unroll
+			for (int a = 0; a < R1; a++) u[a] = v[R2 * a + b];
+			Dft<T, R1>::run(u);
+#pragma unroll
+			for (int q = 0; q < R1; q++) t[b][q] = u[q];
+		}
+#pragma unroll
+		for (int b = 1; b < R2; b++)
+#pragma unroll
+			for (int q = 1; q < R1; q++) t[b][q] = cmulc(t[b][q], cs[(b * q) % R], -sn[(b * q) % R]);
+#pragma unroll
+		for (int q = 0; q < R1; q++) {
+			C2<T> u[R2];
+#pragma unroll
+			for (int b = 0; b < R2; b++) u[b] = t[b][q];
+			Dft<T, R2>::run(u);
+#pragma unroll
+			for (int p = 0; p < R2; p++) v[q + R1 * p] = u[p];
+		}
+	}
+};
+#define DSP_DEFINE_COMP(R, R1, R2, CS, SN)                                            \
+	template <class T> struct Dft<T, R> {                                             \
+		DSP_DEVM static void run(C2<T> *v) {                                           \
+			const T cs[R] = CS;                                                       \
+			const T sn[R] = SN;                                                       \
+			DftComp<T, R1, R2>::run(v, cs, sn);                                       \
+		}                                                                             \
+	};
+
 #define DSP_DEFINE_ODD(R, CS, SN)                                                     \
 	template <class T> struct Dft<T, R> {                                             \
 		DSP_DEVM static void run(C2<T> *v) {                                           \
@@ -277,6 +315,7 @@ template <class T, int R> struct DftOdd {
 #include "dct_oddtabs.inc"
 #undef DSP_L
 #undef DSP_DEFINE_ODD
+#undef DSP_DEFINE_COMP
 
 // ------------------------------------------------------------------------------------------------ DIF passes
 // In-place decimation-in-frequency pass p: sub-length L, radix R, M = L/R.  Butterfly (blk, i) reads
@@ -323,6 +362,8 @@ DSP_DEV void fft_dif(C2<T> *s, int nseq, const FftDesc &f, int t0, int t1, int n
 			case 5:  radix_pass<T, 5>(s, nseq, f, p, L, tid, nthr); break;
 			case 7:  radix_pass<T, 7>(s, nseq, f, p, L, tid, nthr); break;
 			case 8:  radix_pass<T, 8>(s, nseq, f, p, L, tid, nthr); break;
+			case 9:  radix_pass<T, 9>(s, nseq, f, p, L, tid, nthr); break;
+			case 15: radix_pass<T, 15>(s, nseq, f, p, L, tid, nthr); break;
 			case 11: radix_pass<T, 11>(s, nseq, f, p, L, tid, nthr); break;
 			case 13: radix_pass<T, 13>(s, nseq, f, p, L, tid, nthr); break;
 			case 16: radix_pass<T, 16>(s, nseq, f, p, L, tid, nthr); break;
@@ -472,6 +513,124 @@ DSP_DEV void outer_decode(const Outer &o, uint32_t l, long long &ioff, long long
 	c.set(o.slot[0], (int)l0); c.set(o.slot[1], (int)l1); c.set(o.slot[2], (int)l2); c.set(o.slot[3], (int)l3);
 }
 
+// ------------------------------------------------------------------------------------------------ lean tile moves
+DSP_DEV int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+// Makhoul's permutation: position of x[j] in the even/odd-reordered sequence
+DSP_DEV int makhoul(int x, int n) { return (x & 1) ? n - 1 - (x >> 1) : (x >> 1); }
+
+// W consecutive elements of T as one global access (W * sizeof(T) in {8, 16} bytes)
+template <class T, int W> struct alignas(W * sizeof(T)) VecW { T v[W]; };
+#if DSP_GPU
+DSP_DEV VecW<float, 4> ldg_stream(const VecW<float, 4> *p) {
+	VecW<float, 4> r;
+	asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+	return r;
+}
+DSP_DEV VecW<float, 2> ldg_stream(const VecW<float, 2> *p) {
+	VecW<float, 2> r;
+	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+	return r;
+}
+DSP_DEV VecW<double, 2> ldg_stream(const VecW<double, 2> *p) {
+	VecW<double, 2> r;
+	asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+	return r;
+}
+#endif
+
+
+// Lean tile move for the common case -- float, full 16-byte groups, a power-of-two number of groups per row that
+// divides the thread count, and a pointwise stage that ignores coordinates (OpMul): each thread keeps one column
+// group and walks down the rows, so the only per-row work is the row / slot mapping.
+//   rowmap(r)  -> global row of tile row r      slotmap(r) -> padded smem slot of tile row r
+template <class T, bool IN, class Op, class RowMap, class SlotMap>
+DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int lg, const Op &op, bool negim, const RowMap &rowmap,
+                            const SlotMap &slotmap, int npad, int tid, int nthr, C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	const int UNR = 8;
+	const int cg = tid & ((1 << lg) - 1), dr = nthr >> lg;
+	C2<T> *sq = s + (2 * cg) * npad;
+	const T *gp = gin + 4 * cg;
+	T *gq = gout + 4 * cg;
+	const Coord cz = {0, 0, 0, 0, 0};
+	for (int r0 = tid >> lg; r0 < nrows; r0 += dr * UNR) {
+		Vec v[UNR];
+		if (IN) {
+#pragma unroll
+			for (int u = 0; u < UNR; u++) {
+				const int r = r0 + u * dr;
+				if (r < nrows) v[u] = ldg_stream((const Vec *)(gp + (long long)rowmap(r) * rs));
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < UNR; u++) {
+			const int r = r0 + u * dr;
+			if (r < nrows) {
+				const int slot = slotmap(r);
+				if (IN) {
+					sq[slot] = C2<T>{op(v[u].v[0], cz), op(v[u].v[1], cz)};
+					sq[npad + slot] = C2<T>{op(v[u].v[2], cz), op(v[u].v[3], cz)};
+				} else {
+					const C2<T> z0 = sq[slot], z1 = sq[npad + slot];
+					Vec o;
+					o.v[0] = op(z0.x, cz); o.v[1] = op(negim ? -z0.y : z0.y, cz);
+					o.v[2] = op(z1.x, cz); o.v[3] = op(negim ? -z1.y : z1.y, cz);
+					*(Vec *)(gq + (long long)rowmap(r) * rs) = o;
+				}
+			}
+		}
+	}
+}
+struct RowIdent { DSP_DEVM int operator()(int r) const { return r; } };
+template <class T> struct SlotNat { DSP_DEVM int operator()(int r) const { return Pad<T>::of(r); } };
+DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
+	const int gpr = tc / 4;
+	return aligned && ncl == tc && (tc % 4) == 0 && (gpr & (gpr - 1)) == 0 && (nthr % gpr) == 0;
+}
+
+// slot maps of the generic engine: natural-order input of the DIF passes, digit-reversed output via pos2 / pos3
+template <class T> struct SlotMakhoulNat { int n; DSP_DEVM int operator()(int r) const { return Pad<T>::of(makhoul(r, n)); } };
+template <class T> struct SlotTab { const uint16_t *pos; DSP_DEVM int operator()(int r) const { return Pad<T>::of((int)DSP_LDG(pos + r)); } };
+
+// Row moves of the generic engine for planar float lines (d == 1, 16-byte access, whole line pairs, coordinate-free
+// op): one vector group = x in [4q, 4q+4) of lines A and B.  IN && FWD: Makhoul scatter to natural-order slots;
+// IN && !FWD: natural order; !IN: gather through pos (pos2 / pos3, one 8-byte table load per group).
+template <class T, bool IN, bool FWD, class Op>
+DSP_DEV void row_move_generic_lean(const T *gin, T *gout, long long ls, int line0, int npairs, int n, int npad, const uint16_t *pos,
+                                   const Op &op, int tid, int nthr, C2<T> *s) {
+	typedef VecW<T, 4> Vec;
+	struct alignas(8) U4 { uint16_t v[4]; };
+	const int gpl = n >> 2;
+	const Coord cz = {0, 0, 0, 0, 0};
+	for (int g = 0; g < npairs; g++) {
+		const long long l = line0 + 2 * g;
+		const Vec *pa = (const Vec *)(gin + l * ls), *pb = (const Vec *)(gin + (l + 1) * ls);
+		Vec *qa = (Vec *)(gout + l * ls), *qb = (Vec *)(gout + (l + 1) * ls);
+		C2<T> *sg = s + (size_t)g * (size_t)npad;
+		for (int q = tid; q < gpl; q += nthr) {
+			if (IN) {
+				const Vec ta = ldg_stream(pa + q), tb = ldg_stream(pb + q);
+				int sl[4];
+				if (FWD) { sl[0] = Pad<T>::of(2 * q); sl[2] = Pad<T>::of(2 * q + 1); sl[1] = Pad<T>::of(n - 1 - 2 * q); sl[3] = Pad<T>::of(n - 2 - 2 * q); }
+				else { sl[0] = Pad<T>::of(4 * q); sl[1] = Pad<T>::of(4 * q + 1); sl[2] = Pad<T>::of(4 * q + 2); sl[3] = Pad<T>::of(4 * q + 3); }
+#pragma unroll
+				for (int t = 0; t < 4; t++) sg[sl[t]] = C2<T>{op(ta.v[t], cz), op(tb.v[t], cz)};
+			} else {
+				const U4 pp = *(const U4 *)(pos + 4 * q);
+				Vec ra, rb;
+#pragma unroll
+				for (int t = 0; t < 4; t++) {
+					const C2<T> z = sg[Pad<T>::of((int)pp.v[t])];
+					ra.v[t] = op(z.x, cz);
+					rb.v[t] = op(FWD ? z.y : -z.y, cz);
+				}
+				qa[q] = ra;
+				qb[q] = rb;
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ row pass
 // Transform along the contiguous axis.  A "line" is n*d contiguous elements: d interleaved sequences of
 // length n (d = 1 planar, d = 3 for dspfun's RGB images).  Lines (2g, 2g+1) of the CTA's range ride together.
@@ -512,8 +671,16 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 	const uint32_t gpl = (uint32_t)((llen + VN - 1) / VN);   // vector groups per line
 	const bool fwd = a.kind == DSP_KIND_REDFT10;
 
+	const bool lean = sizeof(T) == 4 && d == 1 && a.simple && a.vec_in && a.vec_out && !LoadOp::kNeedsCoord &&
+	                  !StoreOp::kNeedsCoord && !a.f.dense && !(nl & 1) && (n & 3) == 0;
+
 	// ---- copy-in
 	for (int tid = t0; tid < t1; tid++) {
+		if (lean) {
+			if (fwd) row_move_generic_lean<T, true, true, LoadOp>(gin, gout, a.ls_in, line0, npairs, n, a.f.npad, a.f.pos2, lop, tid, nthr, s);
+			else row_move_generic_lean<T, true, false, LoadOp>(gin, gout, a.ls_in, line0, npairs, n, a.f.npad, a.f.pos3, lop, tid, nthr, s);
+			continue;
+		}
 		for (int g = 0; g < npairs; g++) {                    // the line decode is per pair, not per vector
 			const int la = line0 + 2 * g;
 			const bool hasb = (2 * g + 1) < nl;
@@ -570,6 +737,11 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
 	for (int tid = t0; tid < t1; tid++) {
+		if (lean) {
+			if (fwd) row_move_generic_lean<T, false, true, StoreOp>(gin, gout, a.ls_out, line0, npairs, n, a.f.npad, pos, sop, tid, nthr, s);
+			else row_move_generic_lean<T, false, false, StoreOp>(gin, gout, a.ls_out, line0, npairs, n, a.f.npad, pos, sop, tid, nthr, s);
+			continue;
+		}
 		for (int g = 0; g < npairs; g++) {
 			const int la = line0 + 2 * g;
 			const bool hasb = (2 * g + 1) < nl;
@@ -656,8 +828,19 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	long long ibase, obase;
 	outer_decode(a.o, oidx, ibase, obase, cbase);
 
+	// full aligned float tiles with a coordinate-free op: the lean tile moves (one column group per thread)
+	const bool lean = sizeof(T) == 4 && !LoadOp::kNeedsCoord && !StoreOp::kNeedsCoord && !a.f.dense &&
+	                  lean_ok(ncl, a.tc, nthr, a.vec_in && a.vec_out);
+	const int lg = lean ? ilog2(a.tc / 4) : 0;
+
 	// ---- copy-in
 	for (int tid = t0; tid < t1; tid++) {
+		if (lean) {
+			const T *gi = gin + ibase + col0;
+			if (fwd) tile_move_lean<T, true, LoadOp>(gi, (T *)0, a.ax_is, n, lg, lop, false, RowIdent(), SlotMakhoulNat<T>{n}, a.f.npad, tid, nthr, s);
+			else tile_move_lean<T, true, LoadOp>(gi, (T *)0, a.ax_is, n, lg, lop, false, RowIdent(), SlotNat<T>(), a.f.npad, tid, nthr, s);
+			continue;
+		}
 		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n << gsh; idx += (uint32_t)nthr) {
 			const uint32_t r = idx >> gsh, cg = idx & ((1u << gsh) - 1u);
 			if (cg >= gpr) continue;
@@ -698,6 +881,10 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	// ---- copy-out
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
 	for (int tid = t0; tid < t1; tid++) {
+		if (lean) {
+			tile_move_lean<T, false, StoreOp>((const T *)0, gout + obase + col0, a.ax_os, n, lg, sop, !fwd, RowIdent(), SlotTab<T>{pos}, a.f.npad, tid, nthr, s);
+			continue;
+		}
 		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n << gsh; idx += (uint32_t)nthr) {
 			const uint32_t r = idx >> gsh, cg = idx & ((1u << gsh) - 1u);
 			if (cg >= gpr) continue;

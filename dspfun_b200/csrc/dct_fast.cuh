@@ -105,7 +105,6 @@ template <class T> DSP_DEV C2<T> cmul_conj(C2<T> a, C2<T> b) {   // a * conj(b)
 }
 
 // ------------------------------------------------------------------------------------------------ inner passes
-DSP_DEV int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 template <class T, int R, class F>
 DSP_DEV void contig_pass_r(C2<T> *s, int nseq, const F &f, int tid, int nthr) {
@@ -380,7 +379,6 @@ template <class T, class Op, int DD = 0> struct GlobalRows {
 	}
 };
 
-DSP_DEV int makhoul(int x, int n) { return (x & 1) ? n - 1 - (x >> 1) : (x >> 1); }
 
 // The outer-pass units of `nseq` sequences: per sequence i = 0 .. M/2 (i = 0 and i = M/2 are half-cost special
 // units, the others butterfly pairs i, M-i), flat over the CTA's threads.  One call site: fn is large.
@@ -835,26 +833,6 @@ DSP_DEV void cta_row_fast(const RowArgs &a, const F &f, const LoadOp &lop, const
 }
 
 // ------------------------------------------------------------------------------------------------ column pass (fast)
-// W consecutive elements of T as one global access (W * sizeof(T) in {8, 16} bytes)
-template <class T, int W> struct alignas(W * sizeof(T)) VecW { T v[W]; };
-#if DSP_GPU
-DSP_DEV VecW<float, 4> ldg_stream(const VecW<float, 4> *p) {
-	VecW<float, 4> r;
-	asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
-	return r;
-}
-DSP_DEV VecW<float, 2> ldg_stream(const VecW<float, 2> *p) {
-	VecW<float, 2> r;
-	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
-	return r;
-}
-DSP_DEV VecW<double, 2> ldg_stream(const VecW<double, 2> *p) {
-	VecW<double, 2> r;
-	asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
-	return r;
-}
-#endif
-
 // Moves the CTA's column tile between global memory and smem in groups of W columns, UNR groups per thread in
 // flight.  IN: global -> lop -> slot ; !IN: slot -> (re, +-im) -> sop -> global.  `scatter` selects
 // sig[makhoul(r)] vs Pad(r).  `vec`: W-wide accesses are legal (alignment + the tile is a whole number of groups).
@@ -943,58 +921,10 @@ DSP_DEV void col_move(const ColArgs &a, const F &f, const Op &op, bool scatter, 
 	}
 }
 
-// Lean tile move for the common case -- float, full 16-byte groups, a power-of-two number of groups per row that
-// divides the thread count, and a pointwise stage that ignores coordinates (OpMul): each thread keeps one column
-// group and walks down the rows, so the only per-row work is the row / slot mapping.
-//   rowmap(r)  -> global row of tile row r      slotmap(r) -> padded smem slot of tile row r
-template <class T, bool IN, class Op, class RowMap, class SlotMap>
-DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int lg, const Op &op, bool negim, const RowMap &rowmap,
-                            const SlotMap &slotmap, int npad, int tid, int nthr, C2<T> *s) {
-	typedef VecW<T, 4> Vec;
-	const int UNR = 8;
-	const int cg = tid & ((1 << lg) - 1), dr = nthr >> lg;
-	C2<T> *sq = s + (2 * cg) * npad;
-	const T *gp = gin + 4 * cg;
-	T *gq = gout + 4 * cg;
-	const Coord cz = {0, 0, 0, 0, 0};
-	for (int r0 = tid >> lg; r0 < nrows; r0 += dr * UNR) {
-		Vec v[UNR];
-		if (IN) {
-#pragma unroll
-			for (int u = 0; u < UNR; u++) {
-				const int r = r0 + u * dr;
-				if (r < nrows) v[u] = ldg_stream((const Vec *)(gp + (long long)rowmap(r) * rs));
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < UNR; u++) {
-			const int r = r0 + u * dr;
-			if (r < nrows) {
-				const int slot = slotmap(r);
-				if (IN) {
-					sq[slot] = C2<T>{op(v[u].v[0], cz), op(v[u].v[1], cz)};
-					sq[npad + slot] = C2<T>{op(v[u].v[2], cz), op(v[u].v[3], cz)};
-				} else {
-					const C2<T> z0 = sq[slot], z1 = sq[npad + slot];
-					Vec o;
-					o.v[0] = op(z0.x, cz); o.v[1] = op(negim ? -z0.y : z0.y, cz);
-					o.v[2] = op(z1.x, cz); o.v[3] = op(negim ? -z1.y : z1.y, cz);
-					*(Vec *)(gq + (long long)rowmap(r) * rs) = o;
-				}
-			}
-		}
-	}
-}
-struct RowIdent { DSP_DEVM int operator()(int r) const { return r; } };
-template <class T> struct SlotNat { DSP_DEVM int operator()(int r) const { return Pad<T>::of(r); } };
 struct SlotSigMakhoul {                                       // DCT-II input / DCT-III output of a whole axis
 	const uint16_t *sig; int n;
 	DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + makhoul(r, n)); }
 };
-DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
-	const int gpr = tc / 4;
-	return aligned && ncl == tc && (tc % 4) == 0 && (gpr & (gpr - 1)) == 0 && (nthr % gpr) == 0;
-}
 
 // ---- the same move with the axis length fixed at compile time (F = FastFixed), 256 threads and a full TC-column
 // tile: thread = (column group cg, row phase r0) walks rows r = r0 + DR u; the global row offsets, the natural-order

@@ -55,9 +55,18 @@ static FastDiv mk_fd(uint32_t d) {
 // which keeps every pass's smem access pattern a power-of-two stride under the bank-skew padding.
 static bool factorize(int n, std::vector<int> &fac) {
 	fac.clear();
-	static const int odd[] = {13, 11, 7, 5, 3};
+	static const int odd[] = {13, 11, 7};
 	for (int r : odd)
 		while (n % r == 0) { fac.push_back(r); n /= r; }
+	// 3s and 5s pair up into the composite radices 15 and 9 (one shared-memory pass instead of two)
+	int c3 = 0, c5 = 0;
+	while (n % 5 == 0) { c5++; n /= 5; }
+	while (n % 3 == 0) { c3++; n /= 3; }
+	const bool merge = !getenv("DSP_DCT_NO_MERGE");
+	while (merge && c5 > 0 && c3 > 0) { fac.push_back(15); c5--; c3--; }
+	while (merge && c3 >= 2) { fac.push_back(9); c3 -= 2; }
+	while (c5-- > 0) fac.push_back(5);
+	while (c3-- > 0) fac.push_back(3);
 	int e = 0;
 	while (n % 2 == 0) { e++; n /= 2; }
 	if (n != 1) return false;

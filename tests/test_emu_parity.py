@@ -51,6 +51,14 @@ def test_split_column_pass(lib, kind, shape):
     cases.check_interleaved_2d(lib, "f", *shape, kind)
 
 
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(8, 1080, 1), (6, 1920, 1), (540, 16, 1), (20, 360, 1), (1080, 36, 1)])
+def test_mixed_radix_video_sizes(lib, kind, shape):
+    """motion's frame sizes: merged radices 15 / 9 and the lean planar moves of the generic engine"""
+    cases.check_interleaved_2d(lib, "f", *shape, kind)
+    cases.check_interleaved_2d(lib, "d", *shape, kind)
+
+
 def test_fixed_length_column_tiles(lib):
     """batches large enough for 32- and 16-column tiles: the compile-time-length column moves (col_tile_fixed)"""
     cases.check_batched_images(lib, "f", 10, 256, 1024, 1)      # n = 256, 32-column tiles
