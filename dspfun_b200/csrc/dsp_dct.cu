@@ -372,7 +372,8 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		pp.axis = ax;
 		// the contiguous-axis (row) kernel keeps all d interleaved sequences of a line on chip; a wide interleave
 		// (e.g. a temporal transform over [D][H*W] with stride H*W) is a strided axis over d contiguous columns instead
-		const bool wide = d > 4;
+		// ... and so is an interleaved line too long for all its channels to sit on chip together (e.g. 8192 RGB doubles)
+		const bool wide = d > 4 || (d > 1 && (size_t)t->npad * 2 * (size_t)P->es * (size_t)d > kMaxSmem);
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
 		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0; pp.sp_smem_inv = 0; pp.sp_force_inv = false;
@@ -490,8 +491,8 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
 		// one CTA per SM (big tile): run it with 512 threads; otherwise 256 and rely on several CTAs per SM
-		pp.block = (pp.fast && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;
-		if (pp.fast && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
+		pp.block = (pp.fast && !pp.row && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;      // (row kernels are built for 256)
+		if (pp.fast && !pp.row && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
 		{
 			// one resident wave ahead: CTAs per SM by shared memory (<= 2 by registers for the fast kernels) x 148 SMs
 			int per_sm = (int)((kMaxSmem) / (pp.smem ? pp.smem : 1));

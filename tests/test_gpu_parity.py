@@ -32,7 +32,7 @@ def test_interleaved_2d(lib, prec, kind, shape):
 
 @pytest.mark.parametrize("prec", ["f", "d"])
 @pytest.mark.parametrize("shape", [(512, 512, 3), (1024, 1024, 3), (1080, 1920, 1), (540, 960, 3), (2048, 4096, 1),
-                                   (4096, 2048, 3), (8192, 512, 1), (512, 8192, 1)])
+                                   (4096, 2048, 3), (8192, 512, 1), (512, 8192, 1), (64, 8192, 3)])
 def test_reference_config_shapes(lib, prec, shape):
     cases.check_interleaved_2d(lib, prec, *shape, REDFT10)
     cases.check_interleaved_2d(lib, prec, *shape, REDFT01, seed=9)
