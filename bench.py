@@ -180,7 +180,7 @@ def run_motion3d(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.load()
     D, H, W = MOTION3D
-    d3 = Dist3D(D, H, W, "f")
+    d3 = Dist3D(D, H, W, "f", exchange=os.environ.get("DSP_DIST_EXCHANGE", "auto"))
     g = torch.Generator(device="cuda").manual_seed(3 + rank)
     slab = torch.rand((D // world, H, W), device="cuda", dtype=torch.float32, generator=g)
     ref = slab[0].clone()
@@ -247,7 +247,10 @@ def run_motion3d(args):
             "data": "synthetic",
             "config": {"workload": "motion3d", "shape": [D, H, W], "bytes_total": samples * 4,
                        "l2_policy": "inputs larger than L2 (%.0f MB per GPU)" % (samples * 4 / world / 1e6),
-                       "parallelism": "frame slabs; all-to-all transpose around the temporal transform" if world > 1 else "single GPU, one rank-3 plan"},
+                       "parallelism": ("frame slabs; exchange around the temporal transform: " +
+                                       ("fused into the preceding pass (stores into peer-mapped buffers over NVLink)" if d3.mode == "peer"
+                                        else "pack + NCCL all-to-all")) if world > 1 else "single GPU, one rank-3 plan",
+                       "exchange": d3.mode if world > 1 else None},
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": (16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9) / peak,
                          "traffic": None, "peak_source": peak_src},
@@ -488,5 +491,18 @@ def main():
         dist.destroy_process_group()
 
 
+def _clean_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at the
+    first collective), so fd 1 is pointed at stderr for the whole run and `print` keeps the real stdout."""
+    try:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real, "w", buffering=1)
+    except OSError:
+        pass
+
+
 if __name__ == "__main__":
+    _clean_stdout()
     main()

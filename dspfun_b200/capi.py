@@ -22,7 +22,8 @@ LIB_PATH = os.environ.get("DSPFUN_B200_LIB") or os.path.join(_HERE, "libdspdct.s
 SYMBOLS = [
     "dsp_dct_plan_many", "dsp_dct_plan_many_batched", "dsp_dct_plan_2d", "dsp_dct_execute", "dsp_dct_execute_host",
     "dsp_dct_execute_dev", "dsp_dct_destroy", "dsp_dct_alloc", "dsp_dct_free", "dsp_dct_cleanup",
-    "dsp_dct_last_error", "dsp_dct_launch_count", "dsp_dct_fuse_scale", "dsp_dct_fuse_spec", "dsp_dct_spec_dc",
+    "dsp_dct_last_error", "dsp_dct_launch_count", "dsp_dct_fuse_scale", "dsp_dct_set_output_segments", "dsp_dct_fuse_spec",
+    "dsp_dct_spec_dc",
     "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy",
@@ -92,6 +93,8 @@ def bind(path):
     lib.dsp_dct_launch_count.restype = ctypes.c_ulonglong
     lib.dsp_dct_fuse_scale.restype = ci
     lib.dsp_dct_fuse_scale.argtypes = [vp, cd, cd]
+    lib.dsp_dct_set_output_segments.restype = ci
+    lib.dsp_dct_set_output_segments.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.c_longlong, ctypes.c_longlong]
     lib.dsp_dct_fuse_spec.restype = ci
     lib.dsp_dct_fuse_spec.argtypes = [vp, ctypes.POINTER(SpecParams)]
     lib.dsp_dct_spec_dc.restype = ci

@@ -542,7 +542,7 @@ DSP_DEV VecW<double, 2> ldg_stream(const VecW<double, 2> *p) {
 // Lean tile move for the common case -- float, full 16-byte groups, a power-of-two number of groups per row that
 // divides the thread count, and a pointwise stage that ignores coordinates (OpMul): each thread keeps one column
 // group and walks down the rows, so the only per-row work is the row / slot mapping.
-//   rowmap(r)  -> global row of tile row r      slotmap(r) -> padded smem slot of tile row r
+//   rowmap.off(r, rs) -> element offset of tile row r (rs = row stride)      slotmap(r) -> padded smem slot of row r
 template <class T, bool IN, class Op, class RowMap, class SlotMap>
 DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int lg, const Op &op, bool negim, const RowMap &rowmap,
                             const SlotMap &slotmap, int npad, int tid, int nthr, C2<T> *s) {
@@ -559,7 +559,7 @@ DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int 
 #pragma unroll
 			for (int u = 0; u < UNR; u++) {
 				const int r = r0 + u * dr;
-				if (r < nrows) v[u] = ldg_stream((const Vec *)(gp + (long long)rowmap(r) * rs));
+				if (r < nrows) v[u] = ldg_stream((const Vec *)(gp + rowmap.off(r, rs)));
 			}
 		}
 #pragma unroll
@@ -575,13 +575,22 @@ DSP_DEV void tile_move_lean(const T *gin, T *gout, long long rs, int nrows, int 
 					Vec o;
 					o.v[0] = op(z0.x, cz); o.v[1] = op(negim ? -z0.y : z0.y, cz);
 					o.v[2] = op(z1.x, cz); o.v[3] = op(negim ? -z1.y : z1.y, cz);
-					*(Vec *)(gq + (long long)rowmap(r) * rs) = o;
+					*(Vec *)(gq + rowmap.off(r, rs)) = o;
 				}
 			}
 		}
 	}
 }
-struct RowIdent { DSP_DEVM int operator()(int r) const { return r; } };
+struct RowIdent { DSP_DEVM long long off(int r, long long rs) const { return (long long)r * rs; } };
+// segmented output: rows [g S, (g+1) S) live at element offset seg[g] (from the pass's output pointer) with the same
+// row stride -- the peer GPUs' buffers of the slab-sharded 3-D transform (ColArgs::seg_rows, dsp_dct_set_output_segments)
+struct RowSeg {
+	int S; FastDiv dS; const long long *seg;
+	DSP_DEVM long long off(int r, long long rs) const {
+		const int g = (int)fd_div((uint32_t)r, dS);
+		return seg[g] + (long long)(r - g * S) * rs;
+	}
+};
 template <class T> struct SlotNat { DSP_DEVM int operator()(int r) const { return Pad<T>::of(r); } };
 DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
 	const int gpr = tc / 4;
@@ -804,6 +813,12 @@ struct ColArgs {
 	void *out;
 	int vec_in, vec_out;
 	int pf_dist;                 // > 0: prefetch the input tile of CTA (cta + pf_dist) into L2 while this one computes
+	// segmented output (0 = off): axis positions [g seg_rows, (g+1) seg_rows) are stored at out + seg_off[g] (+ the
+	// outer offset, + (position - g seg_rows) * ax_os): the last local pass of the slab-sharded 3-D transform writes
+	// straight into the peer GPUs' buffers over NVLink (full aligned float tiles only; checked when it is set)
+	int seg_rows;
+	FastDiv dseg;
+	long long seg_off[8];
 };
 
 template <class T, class LoadOp, class StoreOp>
@@ -882,7 +897,8 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 	const uint16_t *pos = fwd ? a.f.pos2 : a.f.pos3;
 	for (int tid = t0; tid < t1; tid++) {
 		if (lean) {
-			tile_move_lean<T, false, StoreOp>((const T *)0, gout + obase + col0, a.ax_os, n, lg, sop, !fwd, RowIdent(), SlotTab<T>{pos}, a.f.npad, tid, nthr, s);
+			if (a.seg_rows > 0) tile_move_lean<T, false, StoreOp>((const T *)0, gout + obase + col0, a.ax_os, n, lg, sop, !fwd, RowSeg{a.seg_rows, a.dseg, a.seg_off}, SlotTab<T>{pos}, a.f.npad, tid, nthr, s);
+			else tile_move_lean<T, false, StoreOp>((const T *)0, gout + obase + col0, a.ax_os, n, lg, sop, !fwd, RowIdent(), SlotTab<T>{pos}, a.f.npad, tid, nthr, s);
 			continue;
 		}
 		for (uint32_t idx = (uint32_t)tid; idx < (uint32_t)n << gsh; idx += (uint32_t)nthr) {

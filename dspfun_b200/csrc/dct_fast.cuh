@@ -984,6 +984,12 @@ DSP_DEV void col_move_any(const ColArgs &a, const F &f, const Op &op, bool scatt
 		const T *gin = (const T *)a.in + gbase + col0;
 		T *gout = (T *)a.out + gbase + col0;
 		const long long rs = IN ? a.ax_is : a.ax_os;
+		if (!IN && a.seg_rows > 0) {                          // segmented output rows (peer buffers): general lean move
+			const int lgs = ilog2(a.tc / 4);
+			if (scatter) tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lgs, op, negim, RowSeg{a.seg_rows, a.dseg, a.seg_off}, SlotSigMakhoul{f.sig, f.N()}, f.NPAD(), tid, nthr, s);
+			else tile_move_lean<T, IN, Op>(gin, gout, rs, f.N(), lgs, op, negim, RowSeg{a.seg_rows, a.dseg, a.seg_off}, SlotNat<T>(), f.NPAD(), tid, nthr, s);
+			return;
+		}
 		if constexpr (F::kFixed != 0 && sizeof(T) == 4) {
 			if (nthr == 256 && F::kN <= 4096) {
 #define DSP_COL_FIXED(TC)                                                                                              \

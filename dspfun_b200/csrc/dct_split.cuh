@@ -232,8 +232,8 @@ DSP_DEV void split_inv_load_fixed(const T *gtile, long long rs, int ja, int jb, 
 	}
 }
 
-struct RowSplitImage { int j, n; DSP_DEVM int operator()(int r) const { return split_row(16 * r + j, n); } };
-struct RowSplitScratch { int base; DSP_DEVM int operator()(int r) const { return base + r; } };
+struct RowSplitImage { int j, n; DSP_DEVM long long off(int r, long long rs) const { return (long long)split_row(16 * r + j, n) * rs; } };
+struct RowSplitScratch { int base; DSP_DEVM long long off(int r, long long rs) const { return (long long)(base + r) * rs; } };
 struct SlotSig { const uint16_t *sig; DSP_DEVM int operator()(int r) const { return (int)DSP_LDG(sig + r); } };
 
 // image-side and scratch-side moves of sub-pass A with the lean path when the tile is full and aligned
@@ -390,7 +390,6 @@ DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const Lo
 //        pair (j, 16-j) of a 16-column tile: 2 x 8 sequences x M.  G_j goes to scratch block j.
 //   B'') F[i + M m] = sum_j W_n^{ij} W_16^{jm} G_j[i]: one plain radix-16 DIT butterfly per thread, lanes along the
 //        columns, output sample e = i + M m stored (re, -im) to image row split_row(e).
-struct RowSubseq { int j; DSP_DEVM int operator()(int r) const { return 16 * r + j; } };
 
 // pre-twiddle of one (k, n-k) pair held in two smem slots (pk holds X[k], pn holds X[n-k]; any order of k vs n/2)
 template <class T>

@@ -249,6 +249,9 @@ struct PassPlan {
 	int sp_P, sp_tc;
 	size_t sp_smem, sp_smem_inv;
 	bool sp_force_inv;                       // DSP_DCT_SPLIT_MIN given: use the DIF-style split inverse (experiments)
+	// segmented output of the last pass (dsp_dct_set_output_segments): absolute device bases, one per segment
+	int seg_n;
+	void *seg_base[8];
 };
 
 }  // namespace dsp
@@ -377,6 +380,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
 		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0; pp.sp_smem_inv = 0; pp.sp_force_inv = false;
+		pp.seg_n = 0;
 		memset(&pp.ffM, 0, sizeof(pp.ffM));
 		memset(&pp.ff, 0, sizeof(pp.ff));
 		if (pp.fast) fill_fast(pp.ff, t);
@@ -619,6 +623,15 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
 		a.pf_dist = pp.pf_dist;
+		if (pp.seg_n > 0) {
+			// segment bases become element offsets from this execute's output pointer; 16-byte alignment keeps the lean move
+			for (int g = 0; g < pp.seg_n; g++) {
+				const long long db = (const char *)pp.seg_base[g] - (const char *)out;
+				if (db % 16) { g_err = "output segment bases must be 16-byte aligned relative to the output pointer"; return false; }
+				a.seg_off[g] = db / P->es;
+			}
+			if (!a.vec_in || !a.vec_out) { g_err = "segmented output needs 16-byte aligned buffers"; return false; }
+		}
 		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
 		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
@@ -980,6 +993,38 @@ int dsp_dct_fuse_scale(dsp_dct_plan p, double load_scale, double store_scale) {
 	// a plain multiply rides in the lean kernels (no OpAny dispatch needed)
 	if (load_scale != 1.0) { f.lop.kind = OP_SCALE; f.lop.p[0] = load_scale; }
 	if (store_scale != 1.0) { l.sop.kind = OP_SCALE; l.sop.p[0] = store_scale; }
+	return 0;
+}
+
+int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *const *bases, long long outer_stride,
+                                long long row_stride) {
+	g_err.clear();
+	if (!p) { g_err = "null plan"; return 1; }
+	PassPlan &l = p->passes.back();
+	if (nseg == 0) { l.seg_n = 0; l.ca.seg_rows = 0; return 0; }
+	if (!bases || nseg < 1 || nseg > 8 || seg_rows < 1) { g_err = "segments: 1..8 segments of >= 1 rows"; return 1; }
+	if (l.row || l.split || p->prec != 'f') { g_err = "segmented output needs a float plan whose last pass is a one-kernel strided-axis pass"; return 1; }
+	ColArgs &c = l.ca;
+	if (c.f.n != nseg * seg_rows) { g_err = "segments must tile the last axis exactly"; return 1; }
+	const int gpr = c.tc / 4;
+	if ((c.tc % 4) || (gpr & (gpr - 1)) || (l.block % gpr) || (c.ncols % c.tc) || !l.vec_in_layout || !l.vec_out_layout || c.f.dense || l.fused) {
+		g_err = "segmented output needs full, 16-byte aligned column tiles and no fused stage";
+		return 1;
+	}
+	if (outer_stride) {
+		int live = 0, at = -1;
+		for (int k = 0; k < 4; k++) if (c.o.cnt[k] > 1) { live++; at = k; }
+		if (live > 1) { g_err = "outer stride override needs a single outer level"; return 1; }
+		if (at >= 0) c.o.os[at] = outer_stride;
+	}
+	if (row_stride) {
+		if (row_stride % 4) { g_err = "row stride override must keep 16-byte alignment"; return 1; }
+		c.ax_os = row_stride;
+	}
+	c.seg_rows = seg_rows;
+	c.dseg = mk_fd((uint32_t)seg_rows);
+	l.seg_n = nseg;
+	for (int g = 0; g < nseg; g++) l.seg_base[g] = bases[g];
 	return 0;
 }
 

@@ -9,6 +9,15 @@ Decomposition: rank r owns frames [r D/G, (r+1) D/G) of the [D][H
 The flattened h*w index is partitioned (not rows), so chroma planes whose height does not divide by G still shard.
 With G = 1 the same object runs one rank-3 plan.  The reference has no distributed path; its single buffer
 (`coeffs`, motion.c:500) is what the slabs partition.
+
+Two exchange modes:
+  * "nccl" : pack + `all_to_all_single` + local pass (the baseline; also what the gloo CPU tests exercise).
+  * "peer" : the exchange is FUSED into the transform.  The receive buffers live in symmetric memory
+    (torch.distributed._symmetric_memory: every rank maps every peer's buffer), and the last local pass before the
+    exchange stores each run of its output axis straight into the owning GPU's buffer over NVLink
+    (dsp_dct_set_output_segments): forward, the h-pass of frame d writes rows [g H/G, (g+1) H/G) into rank g's
+    [D][HW/G] array; inverse, the temporal pass writes frames [g D/G, (g+1) D/G) into rank g's slab.  No pack kernel,
+    no separate collective: one device-side barrier before and after.  Needs H % G == 0, float, CUDA tensors.
 """
 import numpy as np
 import torch
@@ -23,7 +32,7 @@ def _ptr(t):
 
 
 class Dist3D:
-    def __init__(self, D, H, W, prec="f", group=None, lib=None):
+    def __init__(self, D, H, W, prec="f", group=None, lib=None, exchange="auto", device=None):
         self.D, self.H, self.W = int(D), int(H), int(W)
         self.prec = prec
         self.tdt = torch.float32 if prec == "f" else torch.float64
@@ -46,6 +55,37 @@ class Dist3D:
             self.fwdt = Plan(prec, [D], [capi.REDFT10], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
             self.invt = Plan(prec, [D], [capi.REDFT01], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
         self.a2a_bytes = 0
+        self.mode = "nccl"
+        if G > 1 and exchange in ("auto", "peer"):
+            try:
+                self._setup_peer(device)
+                self.mode = "peer"
+            except Exception as e:                      # no symmetric memory / layout not eligible: keep the NCCL path
+                if exchange == "peer":
+                    raise
+                self.peer_error = repr(e)
+
+    def _setup_peer(self, device):
+        """Symmetric receive buffers + segmented output of the two passes that precede an exchange."""
+        import torch.distributed._symmetric_memory as symm_mem
+        if self.prec != "f" or self.H % self.G:
+            raise ValueError("peer exchange needs float data and H divisible by the number of ranks")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        G, D, Dl, Pl, H, W = self.G, self.D, self.Dl, self.Pl, self.H, self.W
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.cols_buf = symm_mem.empty((D * Pl,), dtype=self.tdt, device=device)       # [D][Pl]
+        self.slab_buf = symm_mem.empty((Dl * H * W,), dtype=self.tdt, device=device)   # [Dl][H][W]
+        self.h_cols = symm_mem.rendezvous(self.cols_buf, grp)
+        self.h_slab = symm_mem.rendezvous(self.slab_buf, grp)
+        es = self.cols_buf.element_size()
+        Hg = H // G
+        # forward: frame dl of this rank, rows [g Hg, (g+1) Hg) -> rank g's cols[rank Dl + dl][(h - g Hg) W + w]
+        self.fwd2.set_output_segments(Hg, [self.h_cols.buffer_ptrs[g] + self.rank * Dl * Pl * es for g in range(G)],
+                                      outer_stride=Pl)
+        # inverse: temporal output frame d in [g Dl, (g+1) Dl) -> rank g's slab[d - g Dl][rank Pl + col]
+        self.invt.set_output_segments(Dl, [self.h_slab.buffer_ptrs[g] + self.rank * Pl * es for g in range(G)],
+                                      row_stride=H * W)
 
     # -- exchange ------------------------------------------------------------------------------------------------
     def _all_to_all(self, out, inp):
@@ -77,6 +117,15 @@ class Dist3D:
             self.fwd3.execute_dev(_ptr(slab), _ptr(slab), st)
             return slab
         G, Dl, Pl = self.G, self.Dl, self.Pl
+        if self.mode == "peer":
+            # (the returned array is the plan-owned symmetric buffer: valid until the next forward())
+            self.h_cols.barrier(channel=0)                      # every peer is done with its previous cols
+            self.fwd2.execute_dev(_ptr(slab), _ptr(slab), st)   # last pass stores into the peers' cols
+            self.h_cols.barrier(channel=0)                      # all runs have landed
+            cols = self.cols_buf.view(self.D, Pl)
+            self.fwdt.execute_dev(_ptr(cols), _ptr(cols), st)
+            self.a2a_bytes += slab.numel() * slab.element_size() * (G - 1) // G
+            return cols
         self.fwd2.execute_dev(_ptr(slab), _ptr(slab), st)
         send = slab.view(Dl, G, Pl).permute(1, 0, 2).contiguous()          # [G][Dl][Pl]
         recv = torch.empty_like(send)
@@ -93,6 +142,14 @@ class Dist3D:
             self.inv3.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
             return coeffs
         G, Dl, Pl = self.G, self.Dl, self.Pl
+        if self.mode == "peer":
+            self.h_slab.barrier(channel=1)
+            self.invt.execute_dev(_ptr(coeffs), _ptr(coeffs), st)   # stores frames into the owning ranks' slabs
+            self.h_slab.barrier(channel=1)
+            slab = self.slab_buf.view(Dl, self.H, self.W)
+            self.inv2.execute_dev(_ptr(slab), _ptr(slab), st)
+            self.a2a_bytes += coeffs.numel() * coeffs.element_size() * (G - 1) // G
+            return slab
         self.invt.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
         send = coeffs.view(G, Dl, Pl)                                       # chunk g = frames of rank g
         recv = torch.empty_like(send)

@@ -47,6 +47,13 @@ class Plan:
         self._check(self.lib.dsp_dct_fuse_scale(self._h, float(load_scale), float(store_scale)))
         return self
 
+    def set_output_segments(self, seg_rows, bases, outer_stride=0, row_stride=0):
+        """Last pass stores run g of `seg_rows` axis positions at device pointer bases[g] (include/dsp_dct.h)."""
+        arr = (ctypes.c_void_p * len(bases))(*[int(b) for b in bases])
+        self._check(self.lib.dsp_dct_set_output_segments(self._h, len(bases), int(seg_rows), arr, int(outer_stride),
+                                                          int(row_stride)))
+        return self
+
     def fuse_spec(self, scaletype, signtype, rangetype, gain):
         sp = capi.SpecParams(int(scaletype), int(signtype), int(rangetype), float(gain))
         self._check(self.lib.dsp_dct_fuse_spec(self._h, ctypes.byref(sp)))

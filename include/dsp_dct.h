@@ -113,6 +113,15 @@ int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out);
  * scan/scan.c:296-298 (coeffs /= w*h*4) is store_scale = 1/(4wh) on the forward plan. */
 int dsp_dct_fuse_scale(dsp_dct_plan p, double load_scale, double store_scale);
 
+/* Segmented output of the plan's LAST pass (no reference counterpart: it replaces the pack + all-to-all of the
+ * slab-sharded motion volume).  The last axis transformed (length n = nseg * seg_rows) is cut into nseg
+ * runs of seg_rows positions; run g is stored at bases[g] (device pointers, typically peer-mapped buffers of the
+ * other GPUs) with the plan's output row stride (row_stride elements when non-zero), plus the plan's outer offset --
+ * whose stride becomes outer_stride elements when that is non-zero.  Float plans whose last pass is a one-kernel strided-axis pass over full,
+ * 16-byte aligned column tiles; returns non-zero (dsp_dct_last_error) otherwise.  nseg = 0 turns it off. */
+int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *const *bases, long long outer_stride,
+                                long long row_stride);
+
 enum { DSP_SPEC_SCALE_LOG = 0, DSP_SPEC_SCALE_LINEAR = 1 };
 enum { DSP_SPEC_SIGN_ABS = 0, DSP_SPEC_SIGN_SHIFT = 1, DSP_SPEC_SIGN_SATURATE = 2, DSP_SPEC_SIGN_RETAIN = 3 };
 enum { DSP_SPEC_RANGE_ONE = 0, DSP_SPEC_RANGE_DC = 1, DSP_SPEC_RANGE_DCS = 2 };

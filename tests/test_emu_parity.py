@@ -96,3 +96,41 @@ def test_rejects_loudly(lib):
         with pytest.raises(capi.DspDctError) as e:
             Plan(lib=lib, **args)
         assert str(e.value)
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_segmented_output_of_last_pass(lib, kind):
+    """dsp_dct_set_output_segments: the last pass scatters runs of axis positions to separate buffers (the peer
+    buffers of the slab-sharded 3-D transform), for the batched 2-D plan and for the wide-interleave temporal plan"""
+    from oracle import dct as od
+    ork = od.REDFT10 if kind == REDFT10 else od.REDFT01
+    rng = np.random.default_rng(4)
+    # batched 2-D plan, last pass along h (forward) -- rows h split in two, frame stride (h/2) w in the destinations
+    B, h, w = 3, 16, 32
+    x = rng.random((B, h, w)).astype(np.float32)
+    ref = od.dctn_fast(x.astype(np.float64), [ork] * 2, axes=(1, 2))
+    if kind == REDFT10:
+        p = Plan.interleaved_2d("f", h, w, 1, kind, nbatch=B, lib=lib)
+        segs = [np.full((B, h // 2, w), -1.0, np.float32) for _ in range(2)]
+        p.set_output_segments(h // 2, [a.ctypes.data for a in segs], outer_stride=(h // 2) * w)
+        buf = x.copy()
+        p.execute_dev(buf.ctypes.data, buf.ctypes.data, None)
+        p.destroy()
+        got = np.concatenate(segs, axis=1)
+        assert od.rel_l2(got, ref) < cases.OK["f"]
+    # temporal plan over [D][P] (stride P): frames d split in two runs
+    D, P = 32, 64
+    v = rng.random((D, P)).astype(np.float32)
+    refv = od.dctn_fast(v.astype(np.float64), [ork], axes=(0,))
+    q = Plan("f", [D], [kind], P, None, P, 1, None, P, 1, lib=lib)
+    segs = [np.full((D // 2, P), -1.0, np.float32) for _ in range(2)]
+    q.set_output_segments(D // 2, [a.ctypes.data for a in segs])
+    buf = v.copy()
+    q.execute_dev(buf.ctypes.data, buf.ctypes.data, None)
+    q.destroy()
+    assert od.rel_l2(np.concatenate(segs, axis=0), refv) < cases.OK["f"]
+    # a plan whose last pass is a row pass refuses
+    r = Plan.interleaved_2d("f", h, w, 1, REDFT01, lib=lib)
+    with pytest.raises(capi.DspDctError):
+        r.set_output_segments(h // 2, [segs[0].ctypes.data, segs[1].ctypes.data])
+    r.destroy()
