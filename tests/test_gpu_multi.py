@@ -1,0 +1,71 @@
+"""GPU suite, needs >= 2 GPUs (skipped otherwise): the slab-sharded 3-D transform with the exchange fused into the
+preceding pass (peer-mapped symmetric buffers over NVLink) against the NCCL all-to-all path and the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, D, H, W, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dspfun_b200.dist3d import Dist3D
+        from oracle import dct as od
+        vol = np.random.default_rng(7).random((D, H, W)).astype(np.float32)
+        Dl, Pl = D // world, H * W // world
+        ref = od.dctn_fast(vol.astype(np.float64), [od.REDFT10] * 3).reshape(D, H * W)[:, rank * Pl:(rank + 1) * Pl]
+        res = {}
+        for mode in ("peer", "nccl"):
+            d3 = Dist3D(D, H, W, prec="f", exchange=mode)
+            assert d3.mode == mode
+            slab = torch.from_numpy(vol[rank * Dl:(rank + 1) * Dl].copy()).cuda()
+            cols = d3.forward(slab)
+            e_fwd = od.rel_l2(cols.cpu().numpy(), ref)
+            back = d3.inverse(cols) / (8.0 * D * H * W)
+            e_inv = od.rel_l2(back.cpu().numpy(), vol[rank * Dl:(rank + 1) * Dl])
+            # a second round trip reuses the symmetric buffers
+            cols2 = d3.forward(back.clone())
+            e_fwd2 = od.rel_l2(cols2.cpu().numpy(), ref)
+            res[mode] = (e_fwd, e_inv, e_fwd2, cols2.cpu().numpy().copy())
+            torch.cuda.synchronize()
+            dist.barrier()
+            d3.destroy()
+        same = np.array_equal(res["peer"][3], res["nccl"][3])
+        q.put((rank, res["peer"][:3], res["nccl"][:3], same))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(16, 24, 32), (32, 540, 960)])
+def test_peer_fused_exchange_world2(shape):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    D, H, W = shape
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, D, H, W, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, peer, nccl, same in res:
+        assert max(peer) < 1e-5 and max(nccl) < 1e-5, (rank, peer, nccl)
+        assert same, "peer-fused and NCCL exchanges must give identical coefficients"
