@@ -41,6 +41,11 @@ bool launch_split_outer_f32(const SplitArgs &a, const FastDesc &fN, bool fused, 
 bool launch_split_inv_fft_f32(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const OpAny &lop, int grid, size_t smem,
                               rt_stream st, std::string &err);
 bool launch_split_inv_outer_f32(const SplitArgs &a, const FastDesc &fN, const OpAny &sop, int nwarps, rt_stream st, std::string &err);
+// double: the forward split and the DIF-style inverse (sub-pass B first) -- the generic, element-type agnostic moves
+bool launch_split_fft_f64(const SplitArgs &a, const FastDesc &fM, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,
+                          rt_stream st, std::string &err);
+bool launch_split_outer_f64(const SplitArgs &a, const FastDesc &fN, bool fused, const OpAny &lop, const OpAny &sop, int nwarps,
+                            rt_stream st, std::string &err);
 
 bool launch_zoom_basis(char prec, void *basis, int nvec, int ncomp, int type, double num, double den, double offset, int len,
                        rt_stream st, std::string &err);

@@ -49,6 +49,8 @@ def test_planar_3d_embed(lib, prec, kind):
 def test_split_column_pass(lib, kind, shape):
     """long power-of-two columns: the two-sub-pass split path (dct_split.cuh), full fixed-length tiles and ragged ones"""
     cases.check_interleaved_2d(lib, "f", *shape, kind)
+    if shape[0] == 4096:
+        cases.check_interleaved_2d(lib, "d", *shape, kind)     # double: forward split + DIF-style inverse split
 
 
 @pytest.mark.parametrize("kind", [REDFT10, REDFT01])
