@@ -78,19 +78,26 @@ class ClockSampler:
         except Exception:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
-    def _poll(self):
+    def sample_now(self):
+        """One NVML sample from the calling thread (the timed loops call it half way through their enqueue, so at
+        least one sample is taken while the GPU is busy even if the polling thread is starved)."""
+        if not self.nvml:
+            return
         nv, h = self.nvml
-        while not self._stop.is_set():
+        try:
+            mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
             try:
-                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                try:
-                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((float(mhz), int(bits)))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
-                pass
-            time.sleep(0.001)
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append((float(mhz), int(bits)))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self.sample_now()
+            time.sleep(0.0005)
 
     def start(self):
         try:
@@ -208,8 +215,10 @@ def run_motion3d(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         x = step(x)
+        if rank == 0 and i == args.steps // 2:
+            sampler.sample_now()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -392,8 +401,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step()
+        if rank == 0 and i == args.steps // 2:
+            sampler.sample_now()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
