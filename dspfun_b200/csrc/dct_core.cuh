@@ -601,6 +601,18 @@ DSP_DEV bool lean_ok(int ncl, int tc, int nthr, bool aligned) {
 template <class T> struct SlotMakhoulNat { int n; DSP_DEVM int operator()(int r) const { return Pad<T>::of(makhoul(r, n)); } };
 template <class T> struct SlotTab { const uint16_t *pos; DSP_DEVM int operator()(int r) const { return Pad<T>::of((int)DSP_LDG(pos + r)); } };
 
+// Threads of a CTA over (line pair, vector group): `gp2` threads (a power of two >= the groups per line, capped at the
+// CTA) share one pair, nthr / gp2 pairs are moved at a time -- short lines (e.g. the 8-point transforms of a block
+// DCT) would otherwise leave all but a handful of threads idle in a pair-by-pair walk.
+struct PairThreads {
+	int gp2, ngrp, grp, ql;
+	DSP_DEVM PairThreads(int gpl, int tid, int nthr) {
+		gp2 = 1;
+		while (gp2 < gpl && gp2 < nthr) gp2 <<= 1;
+		ngrp = nthr / gp2; grp = tid / gp2; ql = tid - grp * gp2;
+	}
+};
+
 // Row moves of the generic engine for planar float lines (d == 1, 16-byte access, whole line pairs, coordinate-free
 // op): one vector group = x in [4q, 4q+4) of lines A and B.  IN && FWD: Makhoul scatter to natural-order slots;
 // IN && !FWD: natural order; !IN: gather through pos (pos2 / pos3, one 8-byte table load per group).
@@ -611,12 +623,13 @@ DSP_DEV void row_move_generic_lean(const T *gin, T *gout, long long ls, int line
 	struct alignas(8) U4 { uint16_t v[4]; };
 	const int gpl = n >> 2;
 	const Coord cz = {0, 0, 0, 0, 0};
-	for (int g = 0; g < npairs; g++) {
+	const PairThreads pt(gpl, tid, nthr);
+	for (int g = pt.grp; g < npairs; g += pt.ngrp) {
 		const long long l = line0 + 2 * g;
 		const Vec *pa = (const Vec *)(gin + l * ls), *pb = (const Vec *)(gin + (l + 1) * ls);
 		Vec *qa = (Vec *)(gout + l * ls), *qb = (Vec *)(gout + (l + 1) * ls);
 		C2<T> *sg = s + (size_t)g * (size_t)npad;
-		for (int q = tid; q < gpl; q += nthr) {
+		for (int q = pt.ql; q < gpl; q += pt.gp2) {
 			if (IN) {
 				const Vec ta = ldg_stream(pa + q), tb = ldg_stream(pb + q);
 				int sl[4];
@@ -690,14 +703,15 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 			else row_move_generic_lean<T, true, false, LoadOp>(gin, gout, a.ls_in, line0, npairs, n, a.f.npad, a.f.pos3, lop, tid, nthr, s);
 			continue;
 		}
-		for (int g = 0; g < npairs; g++) {                    // the line decode is per pair, not per vector
+		const PairThreads pt((int)gpl, tid, nthr);
+		for (int g = pt.grp; g < npairs; g += pt.ngrp) {      // the line decode is per pair, not per vector
 			const int la = line0 + 2 * g;
 			const bool hasb = (2 * g + 1) < nl;
 			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
-		for (uint32_t q = (uint32_t)tid; q < gpl; q += (uint32_t)nthr) {
+		for (uint32_t q = (uint32_t)pt.ql; q < gpl; q += (uint32_t)pt.gp2) {
 			const int e0 = (int)q * VN;
 			T va[VecOf<T>::N], vb[VecOf<T>::N];
 			if (a.vec_in && e0 + VN <= llen) {
@@ -751,14 +765,15 @@ DSP_DEV void cta_row_pass(const RowArgs &a, const LoadOp &lop, const StoreOp &so
 			else row_move_generic_lean<T, false, false, StoreOp>(gin, gout, a.ls_out, line0, npairs, n, a.f.npad, pos, sop, tid, nthr, s);
 			continue;
 		}
-		for (int g = 0; g < npairs; g++) {
+		const PairThreads pt((int)gpl, tid, nthr);
+		for (int g = pt.grp; g < npairs; g += pt.ngrp) {
 			const int la = line0 + 2 * g;
 			const bool hasb = (2 * g + 1) < nl;
 			Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
 			long long ia, oa, ib = 0, ob = 0;
 			outer_decode(a.o, (uint32_t)la, ia, oa, ca);
 			if (hasb) outer_decode(a.o, (uint32_t)la + 1, ib, ob, cb);
-		for (uint32_t q = (uint32_t)tid; q < gpl; q += (uint32_t)nthr) {
+		for (uint32_t q = (uint32_t)pt.ql; q < gpl; q += (uint32_t)pt.gp2) {
 			const int e0 = (int)q * VN;
 			Vec ra, rb;
 #pragma unroll

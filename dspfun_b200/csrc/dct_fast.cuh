@@ -409,7 +409,8 @@ DSP_DEV void row_move(const RowArgs &a, const F &f, const Op &op, int line0, int
 	const int gpl = (llen + VN - 1) / VN;
 	const int npairs = (nl + 1) / 2;
 	const bool vec = (FWD ? a.vec_in : a.vec_out) && (llen % VN) == 0;
-	for (int g = 0; g < npairs; g++) {
+	const PairThreads pt(gpl, tid, nthr);
+	for (int g = pt.grp; g < npairs; g += pt.ngrp) {
 		const int la = line0 + 2 * g;
 		const bool hasb = (2 * g + 1) < nl;
 		Coord ca = {0, 0, 0, 0, 0}, cb = {0, 0, 0, 0, 0};
@@ -419,14 +420,14 @@ DSP_DEV void row_move(const RowArgs &a, const F &f, const Op &op, int line0, int
 		const T *pa = gin + ia, *pb = gin + ib;
 		T *qa = gout + oa, *qb = gout + ob;
 		C2<T> *sg = s + g * d * f.NPAD();
-		for (int q0 = tid; q0 < gpl; q0 += nthr * UNR) {
+		for (int q0 = pt.ql; q0 < gpl; q0 += pt.gp2 * UNR) {
 			T va[UNR][VecOf<T>::N], vb[UNR][VecOf<T>::N];
 			if (FWD) {
 				// ---- all loads of the batch first
 #pragma unroll
 				for (int u = 0; u < UNR; u++) {
-					const int e0 = (q0 + u * nthr) * VN;
-					if (q0 + u * nthr < gpl) {
+					const int e0 = (q0 + u * pt.gp2) * VN;
+					if (q0 + u * pt.gp2 < gpl) {
 						if (vec) {
 							const Vec ta = ldg_stream((const Vec *)(pa + e0));
 #pragma unroll
@@ -455,8 +456,8 @@ DSP_DEV void row_move(const RowArgs &a, const F &f, const Op &op, int line0, int
 			}
 #pragma unroll
 			for (int u = 0; u < UNR; u++) {
-				const int e0 = (q0 + u * nthr) * VN;
-				if (q0 + u * nthr < gpl) {
+				const int e0 = (q0 + u * pt.gp2) * VN;
+				if (q0 + u * pt.gp2 < gpl) {
 #pragma unroll
 					for (int t = 0; t < VN; t++) {
 						const int e = e0 + t;
@@ -515,28 +516,30 @@ DSP_DEV void row_move_planar4_lean(const RowArgs &a, const F &f, const Op &op, i
 	const int n = f.N(), gpl = n >> 2;
 	const int padM = f.PO(f.NMID(), 1);
 	const Coord c0 = {0, 0, 0, 0, 0};
-	const uint16_t *sigA = f.sig + 2 * tid;                  // sig[2q],     q = tid + k nthr
-	const uint16_t *sigB = f.sig + (n - 2) - 2 * tid;        // sig[n-2-2q]
-	for (int g = 0; g < npairs; g++) {
+	const PairThreads pt(gpl, tid, nthr);                    // short lines: several pairs at a time
+	const int ql = pt.ql, gp2 = pt.gp2;
+	const uint16_t *sigA = f.sig + 2 * ql;                   // sig[2q],     q = ql + k gp2
+	const uint16_t *sigB = f.sig + (n - 2) - 2 * ql;         // sig[n-2-2q]
+	for (int g = pt.grp; g < npairs; g += pt.ngrp) {
 		const long long l = line0 + 2 * g;
-		const Vec *pa = (const Vec *)((const T *)a.in + l * a.ls_in) + tid;
-		const Vec *pb = (const Vec *)((const T *)a.in + (l + 1) * a.ls_in) + tid;
-		Vec *qa = (Vec *)((T *)a.out + l * a.ls_out) + tid;
-		Vec *qb = (Vec *)((T *)a.out + (l + 1) * a.ls_out) + tid;
+		const Vec *pa = (const Vec *)((const T *)a.in + l * a.ls_in) + ql;
+		const Vec *pb = (const Vec *)((const T *)a.in + (l + 1) * a.ls_in) + ql;
+		Vec *qa = (Vec *)((T *)a.out + l * a.ls_out) + ql;
+		Vec *qb = (Vec *)((T *)a.out + (l + 1) * a.ls_out) + ql;
 		C2<T> *sg = s + g * f.NPAD();
-		for (int q0 = 0; q0 < gpl; q0 += nthr * UNR) {
+		for (int q0 = 0; q0 < gpl; q0 += gp2 * UNR) {
 			Vec ta[UNR], tb[UNR];
 			if (FWD) {
 #pragma unroll
 				for (int u = 0; u < UNR; u++) {
-					const int qq = q0 + u * nthr;
-					if (FULL || qq + tid < gpl) { ta[u] = ldg_stream(pa + qq); tb[u] = ldg_stream(pb + qq); }
+					const int qq = q0 + u * gp2;
+					if (FULL || qq + ql < gpl) { ta[u] = ldg_stream(pa + qq); tb[u] = ldg_stream(pb + qq); }
 				}
 			}
 #pragma unroll
 			for (int u = 0; u < UNR; u++) {
-				const int qq = q0 + u * nthr;
-				if (FULL || qq + tid < gpl) {
+				const int qq = q0 + u * gp2;
+				if (FULL || qq + ql < gpl) {
 					C2<T> *b0 = sg + (int)DSP_LDG(sigA + 2 * qq), *b1 = sg + (int)DSP_LDG(sigB - 2 * qq);
 					if (FWD) {
 						b0[0]    = C2<T>{op(ta[u].v[0], c0), op(tb[u].v[0], c0)};        // x = 4q

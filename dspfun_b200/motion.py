@@ -65,3 +65,85 @@ class Motion:
             self.destroy()
         except Exception:
             pass
+
+
+class MotionTiled:
+    """Every block of a plane volume in one go: `motion -b WxHxD` with block == scaled (no resampling), the reference
+    README's 8x8x8 + --quant example (motion/README.md:75-77, block loop motion/motion.c:591-615).
+
+    The reference walks the blocks one by one and runs an 8x8x8 FFTW plan on each; here the whole [D][H][W] volume is
+    transformed block-wise by three plans, one per axis, each a single launch over the volume:
+        w: rank-1 length bw, howmany = (W/bw) H D contiguous segments            (dist = bw)
+        h: rank-1 length bh, stride W, W adjacent columns, batch over (H/bh) D bands (band stride bh W)
+        d: rank-1 length bd, stride H W, H W adjacent columns, batch over D/bd slabs
+    The blocks are independent, so a multi-GPU run shards the volume along d in whole blocks with no collective
+    (SURVEY 8e).  The per-coefficient stages between the transforms (normalise, quantise, de-normalise, clamp / round:
+    motion.c:644-647, 740-751, 757-776) are plain element-wise tensor expressions on the device here, evaluated in
+    double like the fused per-block path; filters other than --quant stay with `Motion` (block at a time).
+    Works on torch tensors: CUDA with the product library, CPU with the emulation library (tests).
+    """
+
+    def __init__(self, dims, block, quant=0.0, float_pixels=False, lib=None):
+        import torch
+        self.torch = torch
+        self.lib = lib if lib is not None else capi.load()
+        self.dims = D, H, W = tuple(int(v) for v in dims)
+        self.block = bd, bh, bw = tuple(int(v) for v in block)
+        if D % bd or H % bh or W % bw:
+            raise ValueError("the volume must be a whole number of blocks (the reference pads the last block with zeros)")
+        from .plan import Plan
+        self.quant, self.float_pixels = float(quant), bool(float_pixels)
+        self.coeffs_coded = 0
+
+        def plans(kind):
+            return (Plan("f", [bw], [kind], (W // bw) * H * D, None, 1, bw, None, 1, bw, lib=self.lib),
+                    Plan("f", [bh], [kind], W, None, W, 1, None, W, 1, (H // bh) * D, bh * W, bh * W, lib=self.lib),
+                    Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib))
+        self.fwd = plans(capi.REDFT10)
+        self.inv = plans(capi.REDFT01)[::-1]
+        self._nf = None
+
+    def _norm_factor(self, device):
+        """nf[z][y][x] = 2 sqrt2 / prod(sqrt2 where the in-block index is 0)   (motion.c:644-647), double, broadcastable"""
+        if self._nf is None or self._nf[0].device != device:
+            t = self.torch
+            s2 = 2.0 ** 0.5
+            vs = []
+            for n, b in zip(self.dims, self.block):
+                idx = t.arange(n, device=device) % b
+                vs.append(t.where(idx > 0, t.tensor(1.0, dtype=t.float64, device=device), t.tensor(s2, dtype=t.float64, device=device)))
+            D, H, W = self.dims
+            self._nf = (vs[0].view(D, 1, 1), vs[1].view(1, H, 1), vs[2].view(1, 1, W))
+        z, y, x = self._nf
+        return (2.0 * 2.0 ** 0.5) / (z * y * x)
+
+    def process(self, pels):
+        """pels: [D][H][W] torch tensor, uint8 (or float32 in [0,1] with float_pixels).  Returns the processed volume."""
+        t = self.torch
+        assert tuple(pels.shape) == self.dims and pels.is_contiguous()
+        bd, bh, bw = self.block
+        stream = t.cuda.current_stream().cuda_stream if pels.is_cuda else None
+        c = pels.to(t.float64)
+        c = (c * 255.0 if self.float_pixels else c).to(t.float32).contiguous()                  # motion.c:618-637
+        for p in self.fwd:
+            p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :641 for every block
+        nf = self._norm_factor(c.device)
+        a = (c.to(t.float64) * nf).to(t.float32)                                                # :644-647
+        if self.quant:
+            q = np.float32(self.quant * 8.0 * np.sqrt(np.float64(bd * bh * bw)))                # :570
+            a = (t.round(a.to(t.float64) / float(q)) * float(q)).to(t.float32)                  # :740-744
+            self.coeffs_coded += int(t.count_nonzero(a).item())
+        c = (a.to(t.float64) / nf).to(t.float32).contiguous()                                   # :748-751
+        for p in self.inv:
+            p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :753
+        pel = c.to(t.float64) * (1.0 / np.sqrt(np.float64(bd * bh * bw * 8))) ** 2             # :757,767 (sf = 1)
+        if self.float_pixels:
+            return (pel / 255.0).to(t.float32)                                                  # :773
+        r = t.floor(pel.abs() + 0.5) * t.sign(pel)                                              # lround
+        return t.where(pel > 255, t.tensor(255.0, dtype=t.float64, device=pel.device),
+                       t.where(pel < 0, t.tensor(0.0, dtype=t.float64, device=pel.device), r)).to(t.uint8)   # :776
+
+    def destroy(self):
+        for p in tuple(getattr(self, "fwd", ())) + tuple(getattr(self, "inv", ())):
+            p.destroy()
+        self.fwd = self.inv = ()

@@ -285,3 +285,36 @@ def check_zoom(lib, prec, h, w, seed=8, **kw):
     err = od.rel_l2(got, want)
     assert err < OK[prec], (kw, err)
     return path, got, want
+
+
+def check_motion_tiled(lib, dims, block, quant=0.0, seed=12, device="cpu"):
+    """MotionTiled (all blocks of a volume through three per-axis plans) == the reference block loop, block by block:
+    8-bit output identical except where the reference's unrounded pel sits on a rounding tie; coded counts equal."""
+    import torch
+    from dspfun_b200.motion import MotionTiled
+    D, H, W = dims
+    bd, bh, bw = block
+    v = np.random.default_rng(seed).integers(16, 236, dims).astype(np.uint8)
+    mt = MotionTiled(dims, block, quant=quant, lib=lib)
+    out = mt.process(torch.from_numpy(v.copy()).to(device)).cpu().numpy()
+    # sharding along d in whole blocks needs no exchange: the two halves processed separately give the same pels
+    if (D // bd) % 2 == 0:
+        half = MotionTiled((D // 2, H, W), block, quant=quant, lib=lib)
+        lo = half.process(torch.from_numpy(v[:D // 2].copy()).to(device)).cpu().numpy()
+        hi = half.process(torch.from_numpy(v[D // 2:].copy()).to(device)).cpu().numpy()
+        half.destroy()
+        assert np.array_equal(np.concatenate([lo, hi]), out)
+    coded = 0
+    for z in range(0, D, bd):
+        for y in range(0, H, bh):
+            for x in range(0, W, bw):
+                sl = (slice(z, z + bd), slice(y, y + bh), slice(x, x + bw))
+                o, c, pel = pl.motion_block(v[sl].copy(), block, quant=quant)
+                coded += c
+                diff = out[sl] != o
+                if diff.any():
+                    frac = np.abs(pel - np.floor(pel))[diff]
+                    assert np.all(np.abs(frac - 0.5) < 1e-3), "8-bit mismatch away from a rounding tie"
+    if quant:
+        assert abs(mt.coeffs_coded - coded) <= max(2, coded // 10000)       # a coefficient on a quantiser tie may flip
+    mt.destroy()

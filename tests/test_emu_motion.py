@@ -34,3 +34,11 @@ def test_resample_by_spectral_pad_and_crop(lib):
 def test_float_pixels(lib):
     cases.check_motion(lib, (4, 8, 16), float_pixels=True)
     cases.check_motion(lib, (4, 8, 16), scaled=(4, 12, 16), float_pixels=True, quant=0.01)
+
+
+def test_all_blocks_of_a_volume_at_once(lib):
+    """motion -b 8x8x8 (+ --quant): three per-axis plans over the whole volume instead of a plan per block"""
+    cases.check_motion_tiled(lib, (16, 16, 24), (8, 8, 8))
+    cases.check_motion_tiled(lib, (16, 16, 24), (8, 8, 8), quant=0.05)
+    cases.check_motion_tiled(lib, (8, 32, 16), (4, 16, 8), quant=0.02)
+    cases.check_motion_tiled(lib, (2, 24, 40), (1, 8, 8))                   # depth-1 blocks: a 2-D block DCT per frame

@@ -288,3 +288,9 @@ def test_scan_sharded_prefix(lib, prec):
     assert len(got) == len(seq)
     for g, sfr in zip(got, seq):
         assert od.rel_l2(g, sfr) < cases.OK[prec]
+
+
+def test_motion_all_blocks_of_a_volume_at_once(lib, torch_cuda):
+    cases.check_motion_tiled(lib, (16, 64, 96), (8, 8, 8), device="cuda")
+    cases.check_motion_tiled(lib, (16, 64, 96), (8, 8, 8), quant=0.05, device="cuda")
+    cases.check_motion_tiled(lib, (4, 64, 128), (1, 16, 16), quant=0.02, device="cuda")
