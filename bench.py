@@ -79,8 +79,9 @@ class ClockSampler:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def sample_now(self):
-        """One NVML sample from the calling thread (the timed loops call it half way through their enqueue, so at
-        least one sample is taken while the GPU is busy even if the polling thread is starved)."""
+        """One NVML sample from the calling thread (the timed loops call it right after their last enqueue, while the
+        GPU is still busy, so at least one sample is taken under load even if the polling thread is starved; an NVML
+        call can take milliseconds, so it must never sit between two enqueues)."""
         if not self.nvml:
             return
         nv, h = self.nvml
@@ -215,11 +216,11 @@ def run_motion3d(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
+    for _ in range(args.steps):
         x = step(x)
-        if rank == 0 and i == args.steps // 2:
-            sampler.sample_now()
     e1.record()
+    if rank == 0:
+        sampler.sample_now()     # everything is enqueued, the GPU is still working: a sample under load, no stall
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(lib.dsp_dct_launch_count() - l0)
@@ -401,11 +402,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
+    for _ in range(args.steps):
         step()
-        if rank == 0 and i == args.steps // 2:
-            sampler.sample_now()
     e1.record()
+    if rank == 0:
+        sampler.sample_now()     # everything is enqueued, the GPU is still working: a sample under load, no stall
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(lib.dsp_dct_launch_count() - l0)
