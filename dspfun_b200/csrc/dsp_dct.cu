@@ -21,8 +21,8 @@
 #include <thread>
 #endif
 
-// The power-of-two fast path is instantiated for float only by default (double falls back to the generic
-// mixed-radix engine); build with -DDSP_FAST_F64=1 and the kern_*_fast_f64.cu units to enable it for double.
+// The power-of-two fast path is built for float and double (the Makefile passes -DDSP_FAST_F64=1 and adds the
+// kern_*_fast_f64.cu / kern_split_f64.cu units); with DSP_FAST_F64=0 double runs on the generic mixed-radix engine.
 #ifndef DSP_FAST_F64
 #define DSP_FAST_F64 0
 #endif
