@@ -38,8 +38,8 @@ struct OpAny {
 	int scaletype, signtype, rangetype;
 	int d, w, h, flag;
 	int lo, hi;
-	double p[4];             // OP_SCALE: p[0] = factor.  OP_SPEC/ISPEC: p[0] = gain, p[1] = norm (2wh)
-	double q[4];             // OP_ISPEC: log1p(max[z]) or max[z] per channel; OP_SPEC (range one): the same
+	double p[4];             // OP_SCALE: p[0] = factor.  OP_SPEC/ISPEC: p[0] = gain, p[1] = norm (2wh); ISPEC: p[2] = 1/gain, p[3] = 255/254
+	double q[4];             // OP_ISPEC: log1p(max[z]) or max[z] per channel; OP_SPEC: q[0] = 1/norm, q[1] = 254/255
 	double dc[4];            // OP_ISPEC preserve_dc values
 	int a3[3], b3[3], e3[3]; // OP_MOTION_COEFF: active box, band-pass begin / end (d, h, w order)
 	double m[8];             // OP_MOTION_*: damp, boost, threshold min, max, quantizer, grey offset, output scale, -
@@ -72,13 +72,20 @@ struct OpAny {
 			if (y == 0 && x == 0) ((double *)aux)[ch] = (double)f / ((double)w * (double)h * 4.0);   // spec.c:66-68
 			if (y == 0) f = (T)((I)f / SQRT2);                                                       // :70-71
 			if (x == 0) f = (T)((I)f / SQRT2);                                                       // :72-74
-			f = (T)((I)f / p[1]);                                                                    // :76-78
+			// The double divisions of the reference's `intermediate` chain are multiplications by reciprocals prepared
+			// once (q[0] = 1/(2wh), q[1] = 254/255, the resolved 1/log1p(max[z])): the quotients differ from true division
+			// by at most an ulp of double before they are rounded to `coeff`, and the stage is FP64-issue bound.
+			f = (T)((I)f * q[0]);                                                                    // :76-78
 			f = (T)((I)f * p[0]);                                                                    // :89-90
-			const I sc = DSP_LDG((const double *)aux_c + ch);     // log1p(max[z]) or max[z], resolved on device
-			if (scaletype == 0) f = (T)(copysign(log1p(fabs((I)f)), (I)f) / sc);                     // :110-117
-			else                f = (T)(f / (T)sc);                                                  // :118-121
+			if (scaletype == 0) {
+				const I rsc = DSP_LDG((const double *)aux_c + 8 + ch);                               // 1 / log1p(max[z])
+				f = (T)(copysign(log1p(fabs((I)f)), (I)f) * rsc);                                    // :110-117
+			} else {
+				const I sc = DSP_LDG((const double *)aux_c + ch);                                    // max[z], resolved on device
+				f = (T)(f / (T)sc);                                                                  // :118-121
+			}
 			if (signtype == 0) f = (T)fabs((I)f);                                                    // :126-128
-			else if (signtype == 1) f = (T)(((I)f / 2.0 + 0.5) * 254 / 255);                         // :130-132
+			else if (signtype == 1) f = (T)(((I)f * 0.5 + 0.5) * q[1]);                              // :130-132
 			else if (signtype == 2) { if (y != 0 || x != 0) f = signbit((I)f) ? (T)0 : (T)1; }        // :134-136
 			return f;
 		}
@@ -91,13 +98,13 @@ struct OpAny {
 					const int sm = (int)DSP_LDG((const unsigned char *)aux_c + ((size_t)y * w + x) * d + ch) - 128;
 					f = (T)copysign((I)f, (I)sm);
 				}
-			} else if (signtype == 1) f = (T)(((I)f * 255.0 / 254 - 0.5) * 2);                       // :100-103
+			} else if (signtype == 1) f = (T)(((I)f * p[3] - 0.5) * 2);                              // :100-103 (p[3] = 255/254)
 			else if (signtype == 2) { if (!pix0) f = f * 2 - 1; }                                     // :104-107
 			if (scaletype == 0) {                                                                    // :136-143
 				const T prod = f * (T)q[ch];
 				f = (T)copysign(expm1(fabs((I)prod)), (I)f);
 			} else f = f * (T)q[ch];                                                                 // :144-147
-			f = (T)((I)f / p[0]);                                                                    // :150-151
+			f = (T)((I)f * p[2]);                                                                    // :150-151 (p[2] = 1/gain)
 			if (y == 0) f = (T)((I)f * SQRT2);                                                       // :153-154
 			if (x == 0) f = (T)((I)f * SQRT2);                                                       // :155-157
 			f = f / 2;                                                                               // :158-159
@@ -181,6 +188,7 @@ DSP_DEV void spec_resolve_range(const OpAny &op, const double *acc, double *scal
 		T m = mx[z];
 		if (op.scaletype == 0) m = (T)log1p((I)m);     // mc(log1p): rounded to coeff
 		scale_z[z] = (double)m;
+		scale_z[8 + z] = 1.0 / (double)m;              // OP_SPEC multiplies (d_scalars[12..15])
 	}
 }
 

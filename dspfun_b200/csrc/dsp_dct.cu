@@ -1057,6 +1057,7 @@ int dsp_dct_fuse_spec(dsp_dct_plan p, const dsp_spec_params *sp) {
 	op.scaletype = sp->scaletype; op.signtype = sp->signtype; op.rangetype = sp->rangetype;
 	op.d = p->d; op.w = w; op.h = h;
 	op.p[0] = sp->gain; op.p[1] = 2.0 * (double)w * (double)h;
+	op.q[0] = 1.0 / op.p[1]; op.q[1] = 254.0 / 255.0;          // reciprocals for the per-coefficient chain
 	op.aux_c = p->d_scalars + 4;
 	op.aux = p->d_scalars + 8;
 	colp.sop = op; colp.fused = true;
@@ -1091,7 +1092,7 @@ int dsp_dct_fuse_ispec(dsp_dct_plan p, const dsp_ispec_params *ip) {
 	op.kind = OP_ISPEC;
 	op.scaletype = ip->scaletype; op.signtype = ip->signtype;
 	op.d = p->d; op.w = w; op.h = h;
-	op.p[0] = ip->gain;
+	op.p[0] = ip->gain; op.p[2] = 1.0 / ip->gain; op.p[3] = 255.0 / 254.0;   // reciprocals for the per-coefficient chain
 	op.flag = ip->preserve_dc;
 	for (int z = 0; z < 4; z++) {
 		// spec/ispec.c:138: max[z] = log1p(max[z]) stored back into coeff precision
