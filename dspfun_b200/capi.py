@@ -26,7 +26,8 @@ SYMBOLS = [
     "dsp_dct_spec_dc",
     "dsp_dct_fuse_ispec", "dsp_dct_profile", "dsp_dct_num_passes", "dsp_dct_pass_stat_get",
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
-    "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy",
+    "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
+    "dsp_block_store_u8",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
 ]
 
@@ -93,6 +94,10 @@ def bind(path):
     lib.dsp_dct_launch_count.restype = ctypes.c_ulonglong
     lib.dsp_dct_fuse_scale.restype = ci
     lib.dsp_dct_fuse_scale.argtypes = [vp, cd, cd]
+    lib.dsp_block_quant.restype = ci
+    lib.dsp_block_quant.argtypes = [ctypes.c_char, vp, ci, ci, ci, ci, ci, ci, cd, vp, vp]
+    lib.dsp_block_store_u8.restype = ci
+    lib.dsp_block_store_u8.argtypes = [ctypes.c_char, vp, vp, ctypes.c_longlong, cd, vp]
     lib.dsp_dct_set_output_segments.restype = ci
     lib.dsp_dct_set_output_segments.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.c_longlong, ctypes.c_longlong]
     lib.dsp_dct_fuse_spec.restype = ci

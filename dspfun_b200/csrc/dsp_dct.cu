@@ -1042,6 +1042,25 @@ int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *co
 	return 0;
 }
 
+int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer,
+                    unsigned long long *d_count, void *stream) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || !d_coeffs || D < 1 || H < 1 || W < 1 || bd < 1 || bh < 1 || bw < 1) { g_err = "block quant: bad arguments"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	const bool ok = launch_block_quant(prec, d_coeffs, (long long)D * H * W, H, W, bd, bh, bw, quantizer, d_count, (rt_stream)stream, g_err);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
+}
+
+int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || !d_coeffs || !d_pels || n < 1) { g_err = "block store: bad arguments"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	const bool ok = launch_block_store_u8(prec, d_coeffs, d_pels, n, scale, (rt_stream)stream, g_err);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
+}
+
 int dsp_dct_fuse_spec(dsp_dct_plan p, const dsp_spec_params *sp) {
 	g_err.clear();
 	if (!p || !sp) { g_err = "null plan or params"; return 1; }

@@ -31,6 +31,9 @@ DSP_DECL_LAUNCH(launch_col_fast_f64, ColArgs)
 
 bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int row_bytes, rt_stream st, std::string &err);
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
+bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,
+                        unsigned long long *count, rt_stream st, std::string &err);
+bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err);
 
 struct SplitArgs;
 bool launch_split_fft_f32(const SplitArgs &a, const FastDesc &fM, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,

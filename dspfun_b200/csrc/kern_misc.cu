@@ -1,5 +1,6 @@
 // kern_misc.cu -- small helper kernels
 #include "dsp_kernels.h"
+#include <math.h>
 
 namespace dsp {
 
@@ -47,6 +48,94 @@ bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *
 	(void)st; (void)err;
 	if (prec == 'f') spec_resolve_range<float>(op, acc, scale_z);
 	else spec_resolve_range<double>(op, acc, scale_z);
+	return true;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ block-tiled motion
+// The coefficient stage of `motion -b BWxBHxBD --quant` over a whole block-tiled volume (motion/motion.c:644-647
+// normalise, :740-744 quantise + count, :748-751 de-normalise), in place, and the 8-bit store (:757-776).
+// One pass each; the in-block indices come from the flat element index.
+struct BlockQuantArgs {
+	long long n;                 // D * H * W
+	int H, W, bd, bh, bw;
+	double nf[4];                // 2 sqrt2 / sqrt2^k for k = number of zero in-block indices
+	double quantizer;            // 0 = no quantisation (the normalise / de-normalise rounding still applies)
+	unsigned long long *count;   // device counter of non-zero quantised coefficients (may be null)
+};
+
+template <class T>
+DSP_DEV int block_quant_elem(const BlockQuantArgs &a, T *c, long long i) {
+	const long long row = i / a.W;
+	const int x = (int)(i - row * a.W);
+	const long long zz = row / a.H;
+	const int y = (int)(row - zz * a.H);
+	const int k = ((x % a.bw) == 0) + ((y % a.bh) == 0) + (((int)(zz % a.bd)) == 0);
+	const double nf = a.nf[k];
+	T f = (T)((double)c[i] * nf);
+	int nz = 0;
+	if (a.quantizer != 0.0) {
+		f = (T)(round((double)f / a.quantizer) * a.quantizer);
+		nz = f != 0;
+	}
+	c[i] = (T)((double)f / nf);
+	return nz;
+}
+
+template <class T>
+DSP_DEV unsigned char block_store_elem(T c, double scale) {
+	const double pel = (double)c * scale;
+	return (unsigned char)(pel > 255.0 ? 255.0 : pel < 0.0 ? 0.0 : (double)lround(pel));
+}
+
+#if DSP_GPU
+template <class T> __global__ void k_block_quant(BlockQuantArgs a, T *c) {
+	unsigned long long local = 0;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x)
+		local += (unsigned long long)block_quant_elem<T>(a, c, i);
+	if (a.count) {
+		for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+		if ((threadIdx.x & 31) == 0 && local) atomicAdd(a.count, local);
+	}
+}
+template <class T> __global__ void k_block_store_u8(const T *c, unsigned char *pels, long long n, double scale) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+		pels[i] = block_store_elem<T>(c[i], scale);
+}
+#endif
+
+bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,
+                        unsigned long long *count, rt_stream st, std::string &err) {
+	BlockQuantArgs a;
+	a.n = n; a.H = H; a.W = W; a.bd = bd; a.bh = bh; a.bw = bw; a.quantizer = quantizer; a.count = count;
+	const long double s2 = 1.41421356237309504880168872420969808L;
+	long double den = 1.0L;
+	for (int k = 0; k < 4; k++) { a.nf[k] = (double)((2.0L * s2) / den); den *= s2; }
+#if DSP_GPU
+	const int grid = 148 * 16;
+	if (prec == 'f') k_block_quant<float><<<grid, 256, 0, st>>>(a, (float *)coeffs);
+	else k_block_quant<double><<<grid, 256, 0, st>>>(a, (double *)coeffs);
+	return rt_ok(cudaGetLastError(), err, "block quant launch");
+#else
+	(void)st; (void)err;
+	unsigned long long total = 0;
+	for (long long i = 0; i < n; i++)
+		total += (unsigned long long)(prec == 'f' ? block_quant_elem<float>(a, (float *)coeffs, i) : block_quant_elem<double>(a, (double *)coeffs, i));
+	if (count) *count += total;
+	return true;
+#endif
+}
+
+bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err) {
+#if DSP_GPU
+	const int grid = 148 * 16;
+	if (prec == 'f') k_block_store_u8<float><<<grid, 256, 0, st>>>((const float *)coeffs, pels, n, scale);
+	else k_block_store_u8<double><<<grid, 256, 0, st>>>((const double *)coeffs, pels, n, scale);
+	return rt_ok(cudaGetLastError(), err, "block store launch");
+#else
+	(void)st; (void)err;
+	for (long long i = 0; i < n; i++)
+		pels[i] = prec == 'f' ? block_store_elem<float>(((const float *)coeffs)[i], scale) : block_store_elem<double>(((const double *)coeffs)[i], scale);
 	return true;
 #endif
 }

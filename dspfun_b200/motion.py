@@ -77,9 +77,10 @@ class MotionTiled:
         h: rank-1 length bh, stride W, W adjacent columns, batch over (H/bh) D bands (band stride bh W)
         d: rank-1 length bd, stride H W, H W adjacent columns, batch over D/bd slabs
     The blocks are independent, so a multi-GPU run shards the volume along d in whole blocks with no collective
-    (SURVEY 8e).  The per-coefficient stages between the transforms (normalise, quantise, de-normalise, clamp / round:
-    motion.c:644-647, 740-751, 757-776) are plain element-wise tensor expressions on the device here, evaluated in
-    double like the fused per-block path; filters other than --quant stay with `Motion` (block at a time).
+    (SURVEY 8e).  The per-coefficient stages between and after the transforms (normalise, quantise, de-normalise;
+    clamp / round / 8-bit store: motion.c:644-647, 740-751, 757-776) are one pass each (dsp_block_quant,
+    dsp_block_store_u8), evaluated in double like the fused per-block path; filters other than --quant stay with
+    `Motion` (block at a time).
     Works on torch tensors: CUDA with the product library, CPU with the emulation library (tests).
     """
 
@@ -101,47 +102,36 @@ class MotionTiled:
                     Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib))
         self.fwd = plans(capi.REDFT10)
         self.inv = plans(capi.REDFT01)[::-1]
-        self._nf = None
-
-    def _norm_factor(self, device):
-        """nf[z][y][x] = 2 sqrt2 / prod(sqrt2 where the in-block index is 0)   (motion.c:644-647), double, broadcastable"""
-        if self._nf is None or self._nf[0].device != device:
-            t = self.torch
-            s2 = 2.0 ** 0.5
-            vs = []
-            for n, b in zip(self.dims, self.block):
-                idx = t.arange(n, device=device) % b
-                vs.append(t.where(idx > 0, t.tensor(1.0, dtype=t.float64, device=device), t.tensor(s2, dtype=t.float64, device=device)))
-            D, H, W = self.dims
-            self._nf = (vs[0].view(D, 1, 1), vs[1].view(1, H, 1), vs[2].view(1, 1, W))
-        z, y, x = self._nf
-        return (2.0 * 2.0 ** 0.5) / (z * y * x)
 
     def process(self, pels):
         """pels: [D][H][W] torch tensor, uint8 (or float32 in [0,1] with float_pixels).  Returns the processed volume."""
         t = self.torch
         assert tuple(pels.shape) == self.dims and pels.is_contiguous()
+        D, H, W = self.dims
         bd, bh, bw = self.block
         stream = t.cuda.current_stream().cuda_stream if pels.is_cuda else None
-        c = pels.to(t.float64)
-        c = (c * 255.0 if self.float_pixels else c).to(t.float32).contiguous()                  # motion.c:618-637
+        if self.float_pixels:
+            c = (pels.to(t.float64) * 255.0).to(t.float32).contiguous()                         # motion.c:618-637
+        else:
+            c = pels.to(t.float32).contiguous()                                                 # (8-bit values are exact)
         for p in self.fwd:
             p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :641 for every block
-        nf = self._norm_factor(c.device)
-        a = (c.to(t.float64) * nf).to(t.float32)                                                # :644-647
-        if self.quant:
-            q = np.float32(self.quant * 8.0 * np.sqrt(np.float64(bd * bh * bw)))                # :570
-            a = (t.round(a.to(t.float64) / float(q)) * float(q)).to(t.float32)                  # :740-744
-            self.coeffs_coded += int(t.count_nonzero(a).item())
-        c = (a.to(t.float64) / nf).to(t.float32).contiguous()                                   # :748-751
+        # normalise, quantise + count, de-normalise: one pass (dsp_block_quant, :644-647, :740-751)
+        q = float(np.float32(self.quant * 8.0 * np.sqrt(np.float64(bd * bh * bw)))) if self.quant else 0.0   # :570
+        cnt = t.zeros(1, dtype=t.int64, device=c.device)
+        if self.lib.dsp_block_quant(b"f", c.data_ptr(), D, H, W, bd, bh, bw, q, cnt.data_ptr(), stream) != 0:
+            raise capi.DspDctError(capi.last_error(self.lib))
         for p in self.inv:
             p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :753
-        pel = c.to(t.float64) * (1.0 / np.sqrt(np.float64(bd * bh * bw * 8))) ** 2             # :757,767 (sf = 1)
+        scale = float((1.0 / np.sqrt(np.float64(bd * bh * bw * 8))) ** 2)                       # :757,767 (sf = 1)
+        if self.quant:
+            self.coeffs_coded += int(cnt.item())
         if self.float_pixels:
-            return (pel / 255.0).to(t.float32)                                                  # :773
-        r = t.floor(pel.abs() + 0.5) * t.sign(pel)                                              # lround
-        return t.where(pel > 255, t.tensor(255.0, dtype=t.float64, device=pel.device),
-                       t.where(pel < 0, t.tensor(0.0, dtype=t.float64, device=pel.device), r)).to(t.uint8)   # :776
+            return (c.to(t.float64) * scale / 255.0).to(t.float32)                              # :773
+        out = t.empty(self.dims, dtype=t.uint8, device=c.device)
+        if self.lib.dsp_block_store_u8(b"f", c.data_ptr(), out.data_ptr(), D * H * W, scale, stream) != 0:   # :776
+            raise capi.DspDctError(capi.last_error(self.lib))
+        return out
 
     def destroy(self):
         for p in tuple(getattr(self, "fwd", ())) + tuple(getattr(self, "inv", ())):

@@ -194,6 +194,17 @@ int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned
 int dsp_motion_block_dev(dsp_motion m, const void *d_pels_in, void *d_pels_out, void *stream);
 void dsp_motion_destroy(dsp_motion m);
 
+/* ---- motion over a block-tiled volume (`motion -b BWxBHxBD [--quant q]` with block == scaled): the block DCTs are
+ * three per-axis dsp_dct plans over the whole [D][H][W] volume (dspfun_b200/motion.py: MotionTiled builds them);
+ * these two entry points are the stages between and after them, one pass each over device memory.
+ *   dsp_block_quant    : in place: c *= nf (motion.c:644-647), c = round(c / quantizer) * quantizer and count the
+ *                        non-zero results into *d_count (:740-744; quantizer = 0 skips this step), c /= nf (:748-751),
+ *                        with nf from the in-block indices of each element.
+ *   dsp_block_store_u8 : pel = c * scale, clamp to [0, 255], lround, 8-bit store (:757-776). */
+int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer,
+                    unsigned long long *d_count, void *stream);
+int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream);
+
 /* ---- zoom: DCT-domain resampling of an RGB image (zoom/zoom.c:263-266 forward plan, :36-68 scaled basis,
  * :361-375 synthesis).  create: REDFT10 x REDFT10 of the [h][w][3] interleaved pixels, kept on the GPU.
  * frame: one output view.  Scale is num/den per axis; (vx, vy) the view offset in output samples; (vw, vh) the
