@@ -19,6 +19,7 @@ _LIB = None
 def load():
     global _LIB
     if _LIB is None:
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "dspfun_b200", "csrc"), "emu"], check=True)
+        subprocess.run(["make", "-s", "-j%d" % max(2, min(16, os.cpu_count() or 2)), "-C",
+                        os.path.join(ROOT, "dspfun_b200", "csrc"), "emu"], check=True)
         _LIB = capi.bind(EMU_PATH)
     return _LIB
