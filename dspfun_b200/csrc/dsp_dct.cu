@@ -1437,6 +1437,29 @@ int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out) {
 		return ok ? 0 : 1;
 	}
 
+	// ---- fast path: interpolated basis with an integer scaled size == four phase-shifted REDFT01 x REDFT01 (kern_zoom.cu)
+	const bool interp_fft = zp->basis == 0 && sw == floor(sw) && sh == floor(sh) && sw >= 1 && sh >= 1 && vw <= (int)sw &&
+	                        vh <= (int)sh && cw <= (int)sw && ch <= (int)sh && !getenv("DSP_ZOOM_NO_SHIFT");
+	if (interp_fft) {
+		const int Nw = (int)sw, Nh = (int)sh;
+		const double dx = zp->vx + (xn / xd - 1.0) / 2.0, dy = zp->vy + (yn / yd - 1.0) / 2.0;
+		const size_t pbytes = 4 * (size_t)Nh * Nw * 3 * es;
+		if (!zoom_reserve(&z->d_pad, &z->pad_bytes, pbytes)) return 1;
+		if (!rt_zero(z->d_pad, pbytes, 0, g_err)) return 1;
+		if (!launch_zoom_shift_build(z->prec, z->d_coeffs, z->d_pad, W, Nh, Nw, ch, cw, dx, dy, 0, g_err)) return 1;
+		const int n[2] = {Nh, Nw}, k01[2] = {DSP_DCT_REDFT01, DSP_DCT_REDFT01};
+		dsp_dct_plan inv = dsp_dct_plan_many_batched(z->prec, 2, n, 3, z->d_pad, nullptr, 3, 1, z->d_pad, nullptr, 3, 1, k01, 0, 4,
+		                                             (ptrdiff_t)Nh * Nw * 3, (ptrdiff_t)Nh * Nw * 3);
+		if (!inv) return 1;
+		bool ok = dsp_dct_execute_dev(inv, z->d_pad, z->d_pad, nullptr) == 0 &&
+		          launch_zoom_shift_combine(z->prec, z->d_pad, z->d_out, Nh, Nw, vh, vw, inv_wh / 4.0, 0, g_err) &&
+		          rt_d2h(out, z->d_out, (size_t)vh * vw * 3 * es, 0, g_err) && rt_sync(0, g_err);
+		dsp_dct_destroy(inv);
+		g_launches += 2;
+		z->last_path = 2;
+		return ok ? 0 : 1;
+	}
+
 	// ---- general path: scaled bases (zoom.c:347-358) and the separable synthesis (zoom.c:361-375)
 	if (!zoom_reserve(&z->d_xb, &z->xb_bytes, (size_t)vw * cw * es) || !zoom_reserve(&z->d_yb, &z->yb_bytes, (size_t)vh * ch * es) ||
 	    !zoom_reserve(&z->d_tmp, &z->tmp_bytes, (size_t)ch * vw * es))

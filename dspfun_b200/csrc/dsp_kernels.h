@@ -52,6 +52,10 @@ bool launch_split_outer_f64(const SplitArgs &a, const FastDesc &fN, bool fused, 
 
 bool launch_zoom_basis(char prec, void *basis, int nvec, int ncomp, int type, double num, double den, double offset, int len,
                        rt_stream st, std::string &err);
+bool launch_zoom_shift_build(char prec, const void *coef, void *planes, int W, int Nh, int Nw, int ch, int cw, double dx, double dy,
+                             rt_stream st, std::string &err);
+bool launch_zoom_shift_combine(char prec, const void *planes, void *out, int Nh, int Nw, int vh, int vw, double alpha, rt_stream st,
+                               std::string &err);
 bool launch_zoom_gemm(char prec, int M, int N, int K, const void *A, long long ar, long long ac, const void *B, long long br,
                       long long bc, void *Cm, long long cr, long long cc, double alpha, rt_stream st, std::string &err);
 

@@ -121,6 +121,99 @@ static bool zoom_gemm_t(int M, int N, int K, const void *A, long long ar, long l
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------ shifted-DCT path
+// Interpolated basis with an integer scaled size N' = N s: the sample angle is pi u (i + 1/2 + delta) / N' with
+// delta = offset + (s - 1)/2, and cos(alpha + phi) = cos alpha cos phi - sin alpha sin phi turns the synthesis into
+// REDFT01s of length N':   sum_u C_u cos(.) = 1/2 [ T(A)[i] - (-1)^i T(G)[i] ],
+//   A_u = C_u cos(phi_u),  G_m = C_{N'-m} sin(phi_{N'-m})  (sin(pi (N'-m)(i+1/2)/N') = (-1)^i cos(pi m (i+1/2)/N')),
+// phi_u = pi u delta / N'.  In two dimensions: four planes (AA, AG, GA, GG), four REDFT01 x REDFT01, one combine.
+DSP_DEV void zoom_sincospi(double x, double &s, double &c) {
+#if DSP_GPU
+	sincospi(x, &s, &c);
+#else
+	const double r = x - 2.0 * floor(x / 2.0);
+	s = sin(3.14159265358979323846264338327950288 * r);
+	c = cos(3.14159265358979323846264338327950288 * r);
+#endif
+}
+
+// element (v, u, ch) of the coefficient plane -> its four destinations
+template <class T>
+DSP_DEV void zoom_shift_build_elem(const T *coef, T *planes, int W, int Nh, int Nw, int cw, double dx, double dy, long long idx) {
+	const int ch = (int)(idx % 3);
+	const long long vu = idx / 3;
+	const int u = (int)(vu % cw), v = (int)(vu / cw);
+	const double C = (double)coef[((size_t)v * W + u) * 3 + ch];
+	double sx = 0, cx = 1, sy = 0, cy = 1;
+	if (u) zoom_sincospi((double)u * dx / (double)Nw, sx, cx);
+	if (v) zoom_sincospi((double)v * dy / (double)Nh, sy, cy);
+	const size_t plane = (size_t)Nh * Nw * 3;
+	planes[((size_t)v * Nw + u) * 3 + ch] = (T)(C * cy * cx);                                        // AA
+	if (u) planes[plane + ((size_t)v * Nw + (Nw - u)) * 3 + ch] = (T)(C * cy * sx);                  // AG
+	if (v) planes[2 * plane + ((size_t)(Nh - v) * Nw + u) * 3 + ch] = (T)(C * sy * cx);              // GA
+	if (u && v) planes[3 * plane + ((size_t)(Nh - v) * Nw + (Nw - u)) * 3 + ch] = (T)(C * sy * sx);  // GG
+}
+
+template <class T>
+DSP_DEV void zoom_shift_combine_elem(const T *planes, T *out, int Nh, int Nw, int vw, double alpha, long long idx) {
+	const int ch = (int)(idx % 3);
+	const long long ji = idx / 3;
+	const int i = (int)(ji % vw), j = (int)(ji / vw);
+	const size_t plane = (size_t)Nh * Nw * 3, at = ((size_t)j * Nw + i) * 3 + ch;
+	const double si = (i & 1) ? -1.0 : 1.0, sj = (j & 1) ? -1.0 : 1.0;
+	const double r = (double)planes[at] - si * (double)planes[plane + at] - sj * (double)planes[2 * plane + at] +
+	                 si * sj * (double)planes[3 * plane + at];
+	out[idx] = (T)(alpha * r);
+}
+
+#if DSP_GPU
+template <class T>
+__global__ void k_zoom_shift_build(const T *coef, T *planes, int W, int Nh, int Nw, int cw, double dx, double dy, long long total) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+		zoom_shift_build_elem<T>(coef, planes, W, Nh, Nw, cw, dx, dy, i);
+}
+template <class T>
+__global__ void k_zoom_shift_combine(const T *planes, T *out, int Nh, int Nw, int vw, double alpha, long long total) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+		zoom_shift_combine_elem<T>(planes, out, Nh, Nw, vw, alpha, i);
+}
+#endif
+
+template <class T>
+static bool zoom_shift_build_t(const void *coef, void *planes, int W, int Nh, int Nw, int ch, int cw, double dx, double dy, rt_stream st, std::string &err) {
+	const long long total = (long long)ch * cw * 3;
+#if DSP_GPU
+	k_zoom_shift_build<T><<<148 * 8, 256, 0, st>>>((const T *)coef, (T *)planes, W, Nh, Nw, cw, dx, dy, total);
+	return rt_ok(cudaGetLastError(), err, "zoom shift build launch");
+#else
+	(void)st; (void)err;
+	for (long long i = 0; i < total; i++) zoom_shift_build_elem<T>((const T *)coef, (T *)planes, W, Nh, Nw, cw, dx, dy, i);
+	return true;
+#endif
+}
+template <class T>
+static bool zoom_shift_combine_t(const void *planes, void *out, int Nh, int Nw, int vh, int vw, double alpha, rt_stream st, std::string &err) {
+	const long long total = (long long)vh * vw * 3;
+#if DSP_GPU
+	k_zoom_shift_combine<T><<<148 * 8, 256, 0, st>>>((const T *)planes, (T *)out, Nh, Nw, vw, alpha, total);
+	return rt_ok(cudaGetLastError(), err, "zoom shift combine launch");
+#else
+	(void)st; (void)err;
+	for (long long i = 0; i < total; i++) zoom_shift_combine_elem<T>((const T *)planes, (T *)out, Nh, Nw, vw, alpha, i);
+	return true;
+#endif
+}
+bool launch_zoom_shift_build(char prec, const void *coef, void *planes, int W, int Nh, int Nw, int ch, int cw, double dx, double dy,
+                             rt_stream st, std::string &err) {
+	return prec == 'f' ? zoom_shift_build_t<float>(coef, planes, W, Nh, Nw, ch, cw, dx, dy, st, err)
+	                   : zoom_shift_build_t<double>(coef, planes, W, Nh, Nw, ch, cw, dx, dy, st, err);
+}
+bool launch_zoom_shift_combine(char prec, const void *planes, void *out, int Nh, int Nw, int vh, int vw, double alpha, rt_stream st,
+                               std::string &err) {
+	return prec == 'f' ? zoom_shift_combine_t<float>(planes, out, Nh, Nw, vh, vw, alpha, st, err)
+	                   : zoom_shift_combine_t<double>(planes, out, Nh, Nw, vh, vw, alpha, st, err);
+}
+
 bool launch_zoom_basis(char prec, void *basis, int nvec, int ncomp, int type, double num, double den, double offset, int len,
                        rt_stream st, std::string &err) {
 	return prec == 'f' ? zoom_basis_t<float>(basis, nvec, ncomp, type, num, den, offset, len, st, err)

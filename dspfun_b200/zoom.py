@@ -33,7 +33,7 @@ class Zoom:
         out = np.empty((vh.value, vw.value, 3), self.dtype)
         if self.lib.dsp_zoom_frame(self._h, ctypes.byref(zp), out.ctypes.data) != 0:
             raise capi.DspDctError(capi.last_error(self.lib))
-        self.last_path = "inverse-dct" if self.lib.dsp_zoom_last_path(self._h) == 1 else "dense"
+        self.last_path = {1: "inverse-dct", 2: "shifted-dct"}.get(self.lib.dsp_zoom_last_path(self._h), "dense")
         return out
 
     def destroy(self):

@@ -210,7 +210,8 @@ int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, l
  * frame: one output view.  Scale is num/den per axis; (vx, vy) the view offset in output samples; (vw, vh) the
  * view size (0 = the whole scaled image, zoom.c:286-289).  basis: 0 interpolated (default), 1 centered, 2 native.
  * A native basis with integer scaled size and zero offset is a spectral zero-pad / crop and runs as one inverse
- * DCT; every other case runs the reference's separable cosine synthesis as dense contractions.
+ * DCT; the interpolated basis (the default) with an integer scaled size runs as four phase-shifted inverse DCTs;
+ * every other case runs the reference's separable cosine synthesis as dense contractions.
  * out: host buffer [vh][vw][3] of the coefficient type, the values zoom hands to ffapi_setpelf (zoom.c:393-400). */
 typedef struct {
 	int basis;
@@ -222,7 +223,8 @@ typedef struct dsp_zoom_s *dsp_zoom;
 dsp_zoom dsp_zoom_create(char prec, int h, int w, const void *pixels);
 int dsp_zoom_view_size(dsp_zoom z, const dsp_zoom_params *zp, int *vw, int *vh);
 int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out);
-/* which path the last frame took: 1 = inverse-DCT fast path, 0 = dense synthesis */
+/* which path the last frame took: 1 = inverse-DCT fast path (native basis), 2 = four phase-shifted inverse DCTs
+ * (interpolated basis with an integer scaled size, any offset), 0 = dense synthesis */
 int dsp_zoom_last_path(dsp_zoom z);
 void dsp_zoom_destroy(dsp_zoom z);
 
