@@ -136,3 +136,26 @@ def test_segmented_output_of_last_pass(lib, kind):
     with pytest.raises(capi.DspDctError):
         r.set_output_segments(h // 2, [segs[0].ctypes.data, segs[1].ctypes.data])
     r.destroy()
+
+
+def test_size_limits_and_argument_errors(lib):
+    """the loud failures at the edges: lengths beyond the on-chip limit, bad segment geometry, bad block-stage arguments"""
+    import ctypes
+    for n in (70000, 65536):                                   # table index type / shared-memory capacity
+        with pytest.raises(capi.DspDctError) as e:
+            Plan("f", [n], [REDFT10], lib=lib)
+        assert "too large" in str(e.value) or "does not fit" in str(e.value)
+    p = Plan.interleaved_2d("f", 16, 32, 1, REDFT10, nbatch=2, lib=lib)
+    a = np.zeros((2, 8, 32), np.float32)
+    with pytest.raises(capi.DspDctError):                      # 3 x 8 rows do not tile the 16-point axis
+        p.set_output_segments(8, [a.ctypes.data] * 3)
+    with pytest.raises(capi.DspDctError):                      # more than 8 segments
+        p.set_output_segments(1, [a.ctypes.data] * 16)
+    p.set_output_segments(8, [a.ctypes.data, a.ctypes.data], outer_stride=8 * 32)
+    lib.dsp_dct_set_output_segments(p._h, 0, 0, None, 0, 0)    # switching it off again is legal
+    p.destroy()
+    c = np.zeros(64, np.float32)
+    assert lib.dsp_block_quant(b"x", c.ctypes.data, 4, 4, 4, 2, 2, 2, 0.0, None, None) != 0
+    assert lib.dsp_block_quant(b"f", None, 4, 4, 4, 2, 2, 2, 0.0, None, None) != 0
+    assert lib.dsp_block_store_u8(b"f", c.ctypes.data, None, 64, 1.0, None) != 0
+    assert capi.last_error(lib)
