@@ -44,7 +44,8 @@ class SpecParams(ctypes.Structure):
 class PassStat(ctypes.Structure):
     _fields_ = [("is_row", ctypes.c_int), ("axis", ctypes.c_int), ("n", ctypes.c_int), ("grid", ctypes.c_int),
                 ("block", ctypes.c_int), ("smem_bytes", ctypes.c_size_t), ("launches", ctypes.c_int),
-                ("ms_total", ctypes.c_double), ("samples", ctypes.c_double), ("split_panels", ctypes.c_int)]
+                ("ms_total", ctypes.c_double), ("samples", ctypes.c_double), ("split_panels", ctypes.c_int),
+                ("kernel_launches", ctypes.c_int)]
 
 
 class MotionParams(ctypes.Structure):

@@ -90,6 +90,8 @@ struct Outer {
 	long long is[4], os[4];
 	int slot[4];
 	FastDiv d0, d01, d012;       // divide by cnt[0], cnt[0]*cnt[1], cnt[0]*cnt[1]*cnt[2]
+	int base_slot, base;         // chunked launches (L2-resident schedule): the launch covers indices base.. of the outermost
+	                             // level; pointers are pre-offset by the host, coordinates get the base back here
 };
 
 // Logical coordinates of an element.  Named fields + select-based set(): a dynamically indexed array would be
@@ -511,6 +513,10 @@ DSP_DEV void outer_decode(const Outer &o, uint32_t l, long long &ioff, long long
 	ioff = (long long)l0 * o.is[0] + (long long)l1 * o.is[1] + (long long)l2 * o.is[2] + (long long)l3 * o.is[3];
 	ooff = (long long)l0 * o.os[0] + (long long)l1 * o.os[1] + (long long)l2 * o.os[2] + (long long)l3 * o.os[3];
 	c.set(o.slot[0], (int)l0); c.set(o.slot[1], (int)l1); c.set(o.slot[2], (int)l2); c.set(o.slot[3], (int)l3);
+	if (o.base) {
+		c.i0 += o.base_slot == 0 ? o.base : 0; c.i1 += o.base_slot == 1 ? o.base : 0; c.i2 += o.base_slot == 2 ? o.base : 0;
+		c.ch += o.base_slot == 3 ? o.base : 0; c.b += o.base_slot == 4 ? o.base : 0;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ lean tile moves
@@ -892,7 +898,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 				if (c0 + t < ncl) {
 					const int col = col0 + c0 + t;
 					const int x = (int)fd_div((uint32_t)col, a.dd);
-					c.set(a.col_slot, x); c.ch = col - x * a.d;
+					c.ch = col - x * a.d; c.set(a.col_slot, x);   // ch first: with a wide interleave col_slot IS the channel slot
 					v[t] = lop(v[t], c);
 				}
 			}
@@ -938,7 +944,7 @@ DSP_DEV void cta_col_pass(const ColArgs &a, const LoadOp &lop, const StoreOp &so
 				if (c0 + t < ncl) {
 					const int col = col0 + c0 + t;
 					const int x = (int)fd_div((uint32_t)col, a.dd);
-					c.set(a.col_slot, x); c.ch = col - x * a.d;
+					c.ch = col - x * a.d; c.set(a.col_slot, x);   // ch first: with a wide interleave col_slot IS the channel slot
 					res.v[t] = sop(res.v[t], c);
 				}
 			}

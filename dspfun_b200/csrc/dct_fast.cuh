@@ -898,7 +898,7 @@ DSP_DEV void col_move(const ColArgs &a, const F &f, const Op &op, bool scatter, 
 						const int col = col0 + c0 + t;
 						int x = col, ch = 0;
 						if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
-						c.set(a.col_slot, x); c.ch = ch;
+						c.ch = ch; c.set(a.col_slot, x);
 						v[u][t] = op(v[u][t], c);
 					}
 				}

@@ -106,7 +106,7 @@ DSP_DEV void split_move(const SplitArgs &a, const F &fM, const Op &op, int j, in
 							const int col = col0 + c0 + t;
 							int x = col, ch = 0;
 							if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
-							c.set(a.col_slot, x); c.ch = ch;
+							c.ch = ch; c.set(a.col_slot, x);
 							v[u][t] = op(v[u][t], c);
 						}
 					}
@@ -364,10 +364,10 @@ DSP_DEV void split_outer_thread(const SplitArgs &a, const FastDesc &fN, const Lo
 	{
 		int x = col, ch = 0;
 		if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
-		ca.set(a.col_slot, x); ca.ch = ch;
+		ca.ch = ch; ca.set(a.col_slot, x);
 		x = col + 1; ch = 0;
 		if (a.d != 1) { x = (int)fd_div((uint32_t)(col + 1), a.dd); ch = col + 1 - x * a.d; }
-		cb.set(a.col_slot, x); cb.ch = ch;
+		cb.ch = ch; cb.set(a.col_slot, x);
 	}
 	if (FWD) {
 		GlobalCols<T, StoreOp, LEAN> sink;
@@ -528,10 +528,10 @@ DSP_DEV void split_inv_outer_thread(const SplitArgs &a, const FastDesc &fN, cons
 	{
 		int x = col, ch = 0;
 		if (a.d != 1) { x = (int)fd_div((uint32_t)col, a.dd); ch = col - x * a.d; }
-		sink.ca.set(a.col_slot, x); sink.ca.ch = ch;
+		sink.ca.ch = ch; sink.ca.set(a.col_slot, x);
 		x = col + 1; ch = 0;
 		if (a.d != 1) { x = (int)fd_div((uint32_t)(col + 1), a.dd); ch = col + 1 - x * a.d; }
-		sink.cb.set(a.col_slot, x); sink.cb.ch = ch;
+		sink.cb.ch = ch; sink.cb.set(a.col_slot, x);
 	}
 #pragma unroll
 	for (int m = 0; m < 16; m++) sink.put(split_row(i + a.M * m, a.n), v[m].x, -v[m].y);

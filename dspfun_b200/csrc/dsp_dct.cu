@@ -180,7 +180,9 @@ template <class T> static Tables *build_tables(int n) {
 	return t;
 }
 
+static std::mutex g_tab_mu;                // the table cache is shared by plan calls and by execute_host's lazily built chunk plans
 static Tables *get_tables(int n, char prec) {
+	std::lock_guard<std::mutex> tab_lock(g_tab_mu);
 	if (n > 65535) { g_err = "transform length " + std::to_string(n) + " too large"; return nullptr; }
 	auto key = std::make_pair(rt_device(), std::make_pair(n, prec));
 	auto it = g_tables.find(key);
@@ -252,6 +254,12 @@ struct PassPlan {
 	// segmented output of the last pass (dsp_dct_set_output_segments): absolute device bases, one per segment
 	int seg_n;
 	void *seg_base[8];
+	// outermost loop level of the pass (chunked, L2-resident schedule): consecutive passes that share it run chunk by
+	// chunk, so the intermediate of a chunk is still in L2 when the next pass reads it
+	int ch_slot;                             // coordinate slot of that level (-1: the pass has no outer level)
+	long long ch_cnt, ch_is, ch_os, ch_inner;// its count and strides (elements), product of the levels below it
+	bool seg_saved;                          // strides below hold the plan's own values while an override is active
+	long long seg_os[4], seg_ax_os;
 };
 
 }  // namespace dsp
@@ -305,6 +313,7 @@ struct dsp_dct_plan_s {
 	std::vector<cudaEvent_t> ev;             // 2 events per pass per recorded execute
 #endif
 	std::vector<int> ev_pass;
+	std::vector<float> ev_frac;              // share of the pass each recorded launch covered (chunked schedule)
 };
 
 namespace dsp {
@@ -320,7 +329,19 @@ static bool set_outer(Outer &o, std::vector<Level> lv) {
 	o.d0 = mk_fd((uint32_t)o.cnt[0]);
 	o.d01 = mk_fd((uint32_t)((long long)o.cnt[0] * o.cnt[1]));
 	o.d012 = mk_fd((uint32_t)((long long)o.cnt[0] * o.cnt[1] * o.cnt[2]));
+	o.base_slot = -1; o.base = 0;
 	return true;
+}
+
+static void set_chunk_level(PassPlan &pp, const std::vector<Level> &lv) {
+	pp.ch_slot = -1; pp.ch_cnt = 1; pp.ch_is = pp.ch_os = 0; pp.ch_inner = 1;
+	long long inner = 1;
+	for (auto &l : lv) {
+		if (l.cnt <= 1) continue;
+		pp.ch_inner = inner;
+		pp.ch_slot = l.slot; pp.ch_cnt = l.cnt; pp.ch_is = l.is; pp.ch_os = l.os;
+		inner *= l.cnt;
+	}
 }
 
 static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int istride, int idist, const int *onembed,
@@ -380,7 +401,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
 		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0; pp.sp_smem_inv = 0; pp.sp_force_inv = false;
-		pp.seg_n = 0;
+		pp.seg_n = 0; pp.seg_saved = false;
 		memset(&pp.ffM, 0, sizeof(pp.ffM));
 		memset(&pp.ff, 0, sizeof(pp.ff));
 		if (pp.fast) fill_fast(pp.ff, t);
@@ -502,6 +523,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 			}
 		}
 		pp.vec_in_layout = vin; pp.vec_out_layout = vout;
+		set_chunk_level(pp, lv);
 		// one CTA per SM (big tile): run it with 512 threads; otherwise 256 and rely on several CTAs per SM
 		pp.block = (pp.fast && !pp.row && pp.smem > 113 * 1024) ? 2 * kThreads : kThreads;      // (row kernels are built for 256)
 		if (pp.fast && !pp.row && getenv("DSP_DCT_THREADS")) pp.block = atoi(getenv("DSP_DCT_THREADS")) >= 512 ? 512 : 256;
@@ -533,28 +555,38 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 	return true;
 }
 
-static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st) {
+// One pass over indices [c0, c0 + nc) of its outermost loop level (the whole pass when nc == pp.ch_cnt).  `in` / `out`
+// already point at index c0; the coordinates get c0 back through Outer::base.
+static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out, rt_stream st, long long c0, long long nc) {
 	const bool ain = ((uintptr_t)in % 16) == 0, aout = ((uintptr_t)out % 16) == 0;
 	const bool f32 = P->prec == 'f';
+	const bool part = nc < pp.ch_cnt;
 	bool ok = false;
+	int grid = pp.grid, pf_dist = pp.pf_dist;
 	if (pp.row) {
 		RowArgs a = pp.ra;
 		a.in = in; a.out = out;
+		if (part) {
+			a.nlines = (int)(nc * pp.ch_inner);
+			grid = (a.nlines + a.lines_per_cta - 1) / a.lines_per_cta;
+			a.o.base_slot = pp.ch_slot; a.o.base = (int)c0;
+			if (pf_dist >= grid) pf_dist = 0;
+		}
 		a.vec_in = pp.vec_in_layout && ain && !a.in_u8; a.vec_out = pp.vec_out_layout && aout && !a.out_u8;
-		a.pf_dist = pp.pf_dist;
+		a.pf_dist = pf_dist;
 		const int nn = pp.ff.n;
 		// layout-specialised kernels: planar or RGB lines at one stride, whole line pairs in every CTA, 16-byte access
 		const bool spec = pp.fast && f32 && !pp.fused && (a.d == 1 || a.d == 3) && a.simple && a.vec_in && a.vec_out &&
 		                  nn >= 256 && nn <= 8192 && (a.lines_per_cta % 2) == 0 && (a.nlines % 2) == 0 &&
 		                  !getenv("DSP_DCT_NO_FIXED") && !getenv("DSP_DCT_NO_PLANAR");
-		if (spec && a.d == 1) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
-		else if (spec) ok = launch_row_fast_f32i3(a, pp.ff, false, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
-		else if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		if (spec && a.d == 1) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
+		else if (spec) ok = launch_row_fast_f32i3(a, pp.ff, false, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
+		else if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
-		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else if (pp.fast) ok = launch_row_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 #endif
-		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
-		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else ok = f32 ? launch_row_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err)
+		              : launch_row_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 	} else if (pp.split && ain && aout &&
 	           (pp.ca.kind == DSP_KIND_REDFT10 || pp.sp_force_inv || (!pp.fused && (pp.ca.ncols % 16) == 0 && !getenv("DSP_DCT_NO_SPLIT_INV")))) {
 		// per outer index (batch / frame) and per column panel: sub-pass A then B (forward) or B' then A' (inverse)
@@ -562,6 +594,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		const bool fwd = c.kind == DSP_KIND_REDFT10;
 		long long no = 1;
 		for (int k = 0; k < 4; k++) no *= c.o.cnt[k];
+		if (part) no = nc * pp.ch_inner;
 		const int M = c.f.n / 16;
 		ok = true;
 		rt_stream pst[4] = {st, st, st, st};
@@ -580,7 +613,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 				const long long idx = rem % c.o.cnt[k];
 				rem /= c.o.cnt[k];
 				ioff += idx * c.o.is[k]; ooff += idx * c.o.os[k];
-				sa.cbase.set(c.o.slot[k], (int)idx);
+				sa.cbase.set(c.o.slot[k], (int)idx + ((part && c.o.slot[k] == pp.ch_slot) ? (int)c0 : 0));
 			}
 			sa.n = c.f.n; sa.M = M; sa.kind = c.kind; sa.d = c.d; sa.dd = c.dd;
 			sa.ax_is = c.ax_is; sa.ax_os = c.ax_os; sa.ax_ss = pp.sp_P;
@@ -636,7 +669,12 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
 		a.vec_in = pp.vec_in_layout && ain; a.vec_out = pp.vec_out_layout && aout;
-		a.pf_dist = pp.pf_dist;
+		if (part) {
+			grid = (int)((long long)a.ntiles * nc * pp.ch_inner);
+			a.o.base_slot = pp.ch_slot; a.o.base = (int)c0;
+			if (pf_dist >= grid) pf_dist = 0;
+		}
+		a.pf_dist = pf_dist;
 		if (pp.seg_n > 0) {
 			// segment bases become element offsets from this execute's output pointer; 16-byte alignment keeps the lean move
 			for (int g = 0; g < pp.seg_n; g++) {
@@ -646,46 +684,93 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 			}
 			if (!a.vec_in || !a.vec_out) { g_err = "segmented output needs 16-byte aligned buffers"; return false; }
 		}
-		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		if (pp.fast && f32) ok = launch_col_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64
-		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else if (pp.fast) ok = launch_col_fast_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 #endif
-		else ok = f32 ? launch_col_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err)
-		              : launch_col_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, pp.grid, pp.block, pp.smem, st, g_err);
+		else ok = f32 ? launch_col_generic_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err)
+		              : launch_col_generic_f64(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 	}
 	if (ok) g_launches++;
 	return ok;
 }
 
+// L2 budget of the chunked schedule (bytes of one chunk's intermediate).  B200: 126 MB of L2 in two halves; a chunk and
+// the next chunk's input have to sit in it together.  DSP_DCT_L2_CHUNK_MB tunes it, 0 turns the schedule off.
+static size_t l2_chunk_bytes() {
+	const char *e = getenv("DSP_DCT_L2_CHUNK_MB");             // read per execute: the tests switch it at run time
+	const double mb = e ? atof(e) : 40.0;
+	return mb > 0 ? (size_t)(mb * 1048576.0) : 0;
+}
+
+static bool run_one(dsp_dct_plan_s *P, size_t i, void *d_in, void *d_out, rt_stream st, long long c0, long long nc) {
+	PassPlan &pp = P->passes[i];
+	// with an 8-bit final store the T-typed intermediate lives in the plan's work buffer
+	void *mid = P->d_work ? P->d_work : d_out;
+	const bool first = i == 0, last = i + 1 == P->passes.size();
+	const char *in = (const char *)(first ? d_in : mid);
+	char *out = (char *)(last ? d_out : mid);
+	if (nc < pp.ch_cnt) {
+		// 8-bit sides (motion's pels) are addressed in bytes
+		const long long esi = (pp.row && pp.ra.in_u8) ? 1 : P->es, eso = (pp.row && pp.ra.out_u8) ? 1 : P->es;
+		in += c0 * pp.ch_is * esi;
+		out += c0 * pp.ch_os * eso;
+	}
+	DSP_TRACE("launch pass %zu in=%p out=%p chunk %lld+%lld of %lld", i, (const void *)in, (void *)out, c0, nc, pp.ch_cnt);
+#if DSP_GPU
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	const bool prof = P->profiling && P->ev.size() < 2 * 16384;  // bounded: unread timings stop accumulating
+	if (prof) {
+		cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0, st);
+	}
+#endif
+	if (!run_pass(P, pp, in, out, st, c0, nc)) return false;
+#if DSP_GPU
+	if (prof) {
+		cudaEventRecord(e1, st);
+		P->ev.push_back(e0); P->ev.push_back(e1);
+		P->ev_pass.push_back((int)i);
+		P->ev_frac.push_back((float)((double)nc / (double)pp.ch_cnt));
+	}
+#endif
+	return true;
+}
+
 static bool run_passes(dsp_dct_plan_s *P, void *d_in, void *d_out, rt_stream st) {
 	if (P->need_acc && !rt_zero(P->d_scalars, sizeof(double) * 4, st, g_err)) return false;
-	for (size_t i = 0; i < P->passes.size(); i++) {
-		PassPlan &pp = P->passes[i];
-		// with an 8-bit final store the T-typed intermediate lives in the plan's work buffer
-		void *mid = P->d_work ? P->d_work : d_out;
-		const void *in = i == 0 ? d_in : mid;
-		void *out = (i + 1 == P->passes.size()) ? d_out : mid;
-		DSP_TRACE("launch pass %zu in=%p out=%p", i, in, out);
-#if DSP_GPU
-		cudaEvent_t e0 = nullptr, e1 = nullptr;
-		if (P->profiling) {
-			cudaEventCreate(&e0); cudaEventCreate(&e1);
-			cudaEventRecord(e0, st);
+	const size_t np = P->passes.size();
+	const size_t budget = l2_chunk_bytes();
+	size_t i = 0;
+	while (i < np) {
+		// a run = consecutive passes that loop over the same outermost level (batch elements, frames): chunk by chunk,
+		// so that each chunk's intermediate is read back from L2 instead of HBM
+		size_t j = i + 1;
+		const PassPlan &p0 = P->passes[i];
+		// (spec's data-dependent range is resolved between its two passes from sums over the whole first pass)
+		const bool can = budget && p0.ch_slot >= 0 && p0.ch_cnt > 1 && P->fuse_kind != 1;
+		while (can && j < np && P->passes[j].ch_slot == p0.ch_slot && P->passes[j].ch_cnt == p0.ch_cnt) j++;
+		long long nc = p0.ch_cnt;
+		if (j - i >= 2) {
+			const double per = P->samples_per_launch / (double)p0.ch_cnt * (double)P->es;       // bytes per index of the level
+			long long fit = (long long)((double)budget / per);
+			if (fit >= 1 && fit < nc) {
+				// even chunks, each a whole number of "waves" is not needed: the kernels' grids are per chunk
+				const long long nchunks = (p0.ch_cnt + fit - 1) / fit;
+				nc = (p0.ch_cnt + nchunks - 1) / nchunks;
+			}
 		}
-#endif
-		const bool ok = run_pass(P, pp, in, out, st);
-		if (!ok) return false;
-#if DSP_GPU
-		if (P->profiling) {
-			cudaEventRecord(e1, st);
-			P->ev.push_back(e0); P->ev.push_back(e1);
-			P->ev_pass.push_back((int)i);
+		for (long long c0 = 0; c0 < p0.ch_cnt; c0 += nc) {
+			const long long n = c0 + nc <= p0.ch_cnt ? nc : p0.ch_cnt - c0;
+			for (size_t k = i; k < j; k++) {
+				if (!run_one(P, k, d_in, d_out, st, c0, n)) return false;
+				if (P->fuse_kind == 1 && k == 0) {
+					if (!launch_spec_resolve(P->prec, P->passes.back().sop, P->d_scalars, P->d_scalars + 4, st, g_err)) return false;
+					g_launches++;
+				}
+			}
 		}
-#endif
-		if (P->fuse_kind == 1 && i == 0) {
-			if (!launch_spec_resolve(P->prec, P->passes.back().sop, P->d_scalars, P->d_scalars + 4, st, g_err)) return false;
-			g_launches++;
-		}
+		i = j;
 	}
 	P->last_stream = st;
 	return true;
@@ -791,7 +876,7 @@ static bool ensure_kids(dsp_dct_plan_s *P) {
 		K->d_scalars = nullptr; K->d_signmap = nullptr; K->d_work = nullptr; K->d_split = nullptr;
 		K->split_bytes = 0; K->nscratch = 1; K->aux_ok = false;
 		K->kids.clear(); K->kid_b0.clear(); K->kids_failed = true;  // no recursion
-		K->ev.clear(); K->ev_pass.clear(); K->profiling = false;
+		K->ev.clear(); K->ev_pass.clear(); K->ev_frac.clear(); K->profiling = false;
 		K->c_nbatch = nb;
 		bool ok = build_plan(K, P->c_howmany, P->c_has_ie ? P->c_ie : nullptr, P->c_istride, P->c_idist,
 		                     P->c_has_oe ? P->c_oe : nullptr, P->c_ostride, P->c_odist, nb, P->c_ibdist, P->c_obdist);
@@ -923,6 +1008,11 @@ int dsp_dct_execute_dev(dsp_dct_plan p, void *d_in, void *d_out, void *stream) {
 void dsp_dct_execute(dsp_dct_plan p) {
 	g_err.clear();
 	if (!p) { g_err = "null plan"; return; }
+	if (!p->in || !p->out) {
+		g_err = "plan was created without buffers: use dsp_dct_execute_host / dsp_dct_execute_dev";
+		fprintf(stderr, "dsp_dct_execute: %s\n", g_err.c_str());
+		return;
+	}
 	bool ok;
 	if (rt_is_device_ptr(p->in)) ok = run_passes(p, p->in, p->out, 0) && rt_sync(0, g_err);
 	else ok = execute_host(p, p->in, p->out);
@@ -947,6 +1037,7 @@ void dsp_dct_free(void *p) { rt_host_free(p); }
 
 void dsp_dct_cleanup(void) {
 	std::lock_guard<std::mutex> lock(g_mu);
+	std::lock_guard<std::mutex> tab_lock(g_tab_mu);
 	for (auto &kv : g_tables) {
 		Tables *t = kv.second;
 		rt_free(t->tw); rt_free(t->om); rt_free(t->pos2); rt_free(t->pos3); rt_free(t->sig); rt_free(t->ctab);
@@ -983,18 +1074,23 @@ int dsp_dct_pass_stat_get(dsp_dct_plan p, int i, dsp_dct_pass_stat *out) {
 #if DSP_GPU
 	std::vector<cudaEvent_t> keep;
 	std::vector<int> keep_pass;
+	std::vector<float> keep_frac;
+	double execs = 0;                                           // a chunked pass is several launches per execute
 	for (size_t k = 0; k < p->ev_pass.size(); k++) {
 		cudaEvent_t e0 = p->ev[2 * k], e1 = p->ev[2 * k + 1];
-		if (p->ev_pass[k] != i) { keep.push_back(e0); keep.push_back(e1); keep_pass.push_back(p->ev_pass[k]); continue; }
+		if (p->ev_pass[k] != i) { keep.push_back(e0); keep.push_back(e1); keep_pass.push_back(p->ev_pass[k]); keep_frac.push_back(p->ev_frac[k]); continue; }
 		float ms = 0;
 		if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
 			out->ms_total += ms;
-			out->launches++;
+			execs += p->ev_frac[k];
+			out->kernel_launches++;
 		}
 		cudaEventDestroy(e0); cudaEventDestroy(e1);
 	}
+	out->launches = (int)(execs + 0.5);
 	p->ev.swap(keep);
 	p->ev_pass.swap(keep_pass);
+	p->ev_frac.swap(keep_frac);
 #endif
 	return 0;
 }
@@ -1015,6 +1111,11 @@ int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *co
 	g_err.clear();
 	if (!p) { g_err = "null plan"; return 1; }
 	PassPlan &l = p->passes.back();
+	if (l.seg_saved) {                                      // every call starts from the plan's own strides
+		for (int k = 0; k < 4; k++) l.ca.o.os[k] = l.seg_os[k];
+		l.ca.ax_os = l.seg_ax_os;
+		l.seg_saved = false;
+	}
 	if (nseg == 0) { l.seg_n = 0; l.ca.seg_rows = 0; return 0; }
 	if (!bases || nseg < 1 || nseg > 8 || seg_rows < 1) { g_err = "segments: 1..8 segments of >= 1 rows"; return 1; }
 	if (l.row || l.split || p->prec != 'f') { g_err = "segmented output needs a float plan whose last pass is a one-kernel strided-axis pass"; return 1; }
@@ -1025,15 +1126,18 @@ int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *co
 		g_err = "segmented output needs full, 16-byte aligned column tiles and no fused stage";
 		return 1;
 	}
+	for (int k = 0; k < 4; k++) l.seg_os[k] = c.o.os[k];
+	l.seg_ax_os = c.ax_os;
 	if (outer_stride) {
 		int live = 0, at = -1;
 		for (int k = 0; k < 4; k++) if (c.o.cnt[k] > 1) { live++; at = k; }
 		if (live > 1) { g_err = "outer stride override needs a single outer level"; return 1; }
-		if (at >= 0) c.o.os[at] = outer_stride;
+		if (at >= 0) { c.o.os[at] = outer_stride; l.seg_saved = true; }
 	}
 	if (row_stride) {
 		if (row_stride % 4) { g_err = "row stride override must keep 16-byte alignment"; return 1; }
 		c.ax_os = row_stride;
+		l.seg_saved = true;
 	}
 	c.seg_rows = seg_rows;
 	c.dseg = mk_fd((uint32_t)seg_rows);

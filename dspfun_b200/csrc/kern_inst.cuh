@@ -79,11 +79,12 @@ template <class TT, int ROW, int FAST, class L, class S>
 static bool launch_t(const KERN_ARGS &a, const FastDesc &f, const L &l, const S &s, int grid, int block, size_t smem,
                      rt_stream st, std::string &err) {
 #if DSP_GPU
-	static size_t attr_set = 0;
-	if (smem > 48 * 1024 && smem > attr_set) {
+	static unsigned long long attr_dev = 0;      // one bit per device: the attribute is per (function, device)
+	const int dev = rt_device() & 63;
+	if (smem > 48 * 1024 && !((attr_dev >> dev) & 1ull)) {
 		if (!rt_ok(cudaFuncSetAttribute(k_pass<TT, ROW, FAST, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute"))
 			return false;
-		attr_set = kMaxSmem;
+		attr_dev |= 1ull << dev;
 	}
 	k_pass<TT, ROW, FAST, L, S><<<grid, block, smem, st>>>(a, f, l, s);
 	return rt_ok(cudaGetLastError(), err, "pass kernel launch");

@@ -76,10 +76,11 @@ template <int LGM>
 static bool split_inv_fft_t(const SplitArgs &a, const FastDesc &fM, const FastDesc &fN, const OpMul<KERN_T> &lm, int grid, size_t smem,
                             rt_stream st, std::string &err) {
 #if DSP_GPU
-	static size_t attr_set = 0;
-	if (smem > 48 * 1024 && smem > attr_set) {
+	static unsigned long long attr_dev = 0;      // one bit per device: the attribute is per (function, device)
+	const int dev = rt_device() & 63;
+	if (smem > 48 * 1024 && !((attr_dev >> dev) & 1ull)) {
 		if (!rt_ok(cudaFuncSetAttribute(k_split_inv_fft<KERN_T, LGM, OpMul<KERN_T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
-		attr_set = kMaxSmem;
+		attr_dev |= 1ull << dev;
 	}
 	k_split_inv_fft<KERN_T, LGM, OpMul<KERN_T>><<<grid, kThreads, smem, st>>>(a, fM, fN, lm);
 	return rt_ok(cudaGetLastError(), err, "split inverse fft launch");
@@ -126,10 +127,11 @@ bool KS_NAME(launch_split_inv_outer_)(const SplitArgs &a, const FastDesc &fN, co
 template <int LGM, bool FWD, class L, class S>
 static bool split_fft_t(const SplitArgs &a, const FastDesc &fM, const L &l, const S &s, int grid, size_t smem, rt_stream st, std::string &err) {
 #if DSP_GPU
-	static size_t attr_set = 0;
-	if (smem > 48 * 1024 && smem > attr_set) {
+	static unsigned long long attr_dev = 0;      // one bit per device: the attribute is per (function, device)
+	const int dev = rt_device() & 63;
+	if (smem > 48 * 1024 && !((attr_dev >> dev) & 1ull)) {
 		if (!rt_ok(cudaFuncSetAttribute(k_split_fft<KERN_T, LGM, FWD, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem), err, "smem attribute")) return false;
-		attr_set = kMaxSmem;
+		attr_dev |= 1ull << dev;
 	}
 	k_split_fft<KERN_T, LGM, FWD, L, S><<<grid, kThreads, smem, st>>>(a, fM, l, s);
 	return rt_ok(cudaGetLastError(), err, "split fft launch");

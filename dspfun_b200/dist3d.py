@@ -61,6 +61,14 @@ class Dist3D:
                 self._setup_peer(device)
                 self.mode = "peer"
             except Exception as e:                      # no symmetric memory / layout not eligible: keep the NCCL path
+                # a partial setup must not survive: a plan that kept its output segments would store into the
+                # (now unused) peer buffers on the NCCL path
+                for p in (self.fwd2, self.invt):
+                    try:
+                        p.clear_output_segments()
+                    except Exception:
+                        pass
+                self.cols_buf = self.slab_buf = self.h_cols = self.h_slab = None
                 if exchange == "peer":
                     raise
                 self.peer_error = repr(e)

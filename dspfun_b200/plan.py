@@ -54,6 +54,11 @@ class Plan:
                                                           int(row_stride)))
         return self
 
+    def clear_output_segments(self):
+        """Back to the plan's own output addressing (nseg = 0 also restores overridden strides)."""
+        self._check(self.lib.dsp_dct_set_output_segments(self._h, 0, 0, None, 0, 0))
+        return self
+
     def fuse_spec(self, scaletype, signtype, rangetype, gain):
         sp = capi.SpecParams(int(scaletype), int(signtype), int(rangetype), float(gain))
         self._check(self.lib.dsp_dct_fuse_spec(self._h, ctypes.byref(sp)))
@@ -104,7 +109,8 @@ class Plan:
             self._check(self.lib.dsp_dct_pass_stat_get(self._h, i, ctypes.byref(st)))
             out.append(dict(kernel="row" if st.is_row else ("col-split" if st.split_panels else "col"), axis=st.axis, n=st.n, grid=st.grid, block=st.block,
                             smem_bytes=int(st.smem_bytes), launches=st.launches, ms_total=st.ms_total,
-                            samples=st.samples, split_panels=st.split_panels))
+                            samples=st.samples, split_panels=st.split_panels,
+                            kernel_launches=st.kernel_launches))
         return out
 
     def destroy(self):

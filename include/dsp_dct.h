@@ -102,6 +102,8 @@ typedef struct {
 	double samples;      /* scalar samples one launch reads and writes */
 	int split_panels;    /* > 0: the pass runs as two sub-kernels per column panel (this many panels per plane);
 	                        `launches` then counts passes, not sub-kernel launches */
+	int kernel_launches; /* timed launches behind `launches`: a pass of the chunked (L2-resident) schedule is one launch
+	                        per chunk of batch elements / frames, `launches` still counts whole passes */
 } dsp_dct_pass_stat;
 int dsp_dct_profile(dsp_dct_plan p, int enable);
 int dsp_dct_num_passes(dsp_dct_plan p);

@@ -68,6 +68,15 @@ def check_planar_3d_embed(lib, prec, dims, embed, kind, seed=2):
     return err
 
 
+def run_planar_3d_embed(lib, prec, dims, embed, kind, seed=2):
+    """The raw result of the same plan (for bit-for-bit comparisons between schedules)."""
+    buf = np.random.default_rng(seed).random(embed).astype(DT[prec])
+    p = Plan.planar_3d(prec, dims, embed, kind, lib=lib)
+    y = p.execute_host(buf.copy())
+    p.destroy()
+    return y
+
+
 def check_batched_images(lib, prec, nb, h, w, d, seed=3):
     rng = np.random.default_rng(seed)
     x = rng.random((nb, h, w, d)).astype(DT[prec])
