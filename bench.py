@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- DCT-II + DCT-III round-trip throughput (BASELINE.json metric) on N B200s of one node.
 
-A "step" is one forward (REDFT10 x REDFT10) plus one inverse (REDFT01 x REDFT01, fused 1/(4wh) store scale)
-2-D transform of every plane of the rank's batch, device resident, through the C ABI's dsp_dct_execute_dev.
-Default workload: 8192x8192 float32 single-channel planes (the size BASELINE.json's target is quoted on), `--planes`
-of them per GPU (weak scaling: per-GPU work is fixed).  Other workloads: --workload batch1024 (C4), spec512 (C1).
+A "step" is one forward (REDFT10) plus one inverse (REDFT01, fused 1/(4wh) store scale) transform of every plane of the
+rank's batch, device resident, through the C ABI's dsp_dct_execute_dev.
+
+The default invocation measures the three configurations BASELINE.json's north_star names and prints ONE JSON line:
+
+  headline  plane8192   C3  8192x8192 float32 single-channel planes, `--planes` per GPU (weak scaling, no collective)
+  records:  batch1024   C4  4096 RGB images of 1024x1024 float32 sharded over the ranks (strong scaling, no collective)
+            motion3d    C5  one 1920x1080x256 yuv420p 8-bit volume (Y + U + V), frame slabs over the ranks, 8-bit pels in
+                            -> 3-D DCT -> coefficient stages -> inverse -> 8-bit pels out; exchange around the temporal
+                            transform fused into the transform (peer stores over NVLink) or NCCL all-to-all
+
+`--workload X` runs one workload alone (profiling); `--impl reference` runs the CPU arm (oracle port: scipy pocketfft
+on all host threads; FFTW is not in the image).
 
   python bench.py --gpus 1 --steps 20 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-  python bench.py --impl reference ...   # CPU arm: the oracle port (scipy pocketfft, all host threads)
-
-Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
@@ -29,16 +35,22 @@ METRIC = "dct2+dct3 round-trip throughput"
 UNIT = "Gpixel/s"
 
 WORKLOADS = {
-    # name: (h, w, d, default planes per GPU, prec)
-    "plane8192": (8192, 8192, 1, 2, "f"),
-    "plane8192_f64": (8192, 8192, 1, 1, "d"),
-    "batch1024": (1024, 1024, 3, 64, "f"),
-    "spec512": (512, 512, 3, 64, "f"),
-    "plane4096x3": (4096, 4096, 3, 2, "f"),
+    # name: (h, w, d, planes per GPU (weak) or total (strong), prec, scaling)
+    "plane8192": (8192, 8192, 1, 2, "f", "weak"),
+    "plane8192_f64": (8192, 8192, 1, 1, "d", "weak"),
+    "batch1024": (1024, 1024, 3, 4096, "f", "strong"),       # BASELINE config 4: the 4096 images are sharded
+    "spec512": (512, 512, 3, 64, "f", "weak"),
+    "plane4096x3": (4096, 4096, 3, 2, "f", "weak"),
 }
-# motion -b 0x0x0 on the luma plane of BASELINE config 4 (1920x1080x256): ONE volume sharded by frame slabs over
-# the ranks (strong scaling), NCCL all-to-all transpose around the temporal transform
-MOTION3D = (256, 1080, 1920)
+# BASELINE config 5: yuv420p, 8-bit: (name, D, H, W)
+MOTION_PLANES = (("Y", 256, 1080, 1920), ("U", 256, 540, 960), ("V", 256, 540, 960))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def peaks():
@@ -156,226 +168,186 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
-def cpu_roundtrip(h, w, d, prec, reps, nplanes=1):
-    """The oracle port timed on the host cores: scipy pocketfft dctn type 2 then type 3 over (h, w) of an
-    interleaved [h][w][d] buffer, all threads.  Returns (Gpixel/s, cores, seconds per round trip)."""
+# ------------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_threads():
+    """pocketfft sizes its pool from OMP_NUM_THREADS at import; torchrun exports OMP_NUM_THREADS=1, which throttled
+    the reference arm 15x at N >= 2 in round 1.  Set it to the cores this process may use BEFORE scipy is imported."""
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return cores
+
+
+def cpu_roundtrip_2d(h, w, d, prec, nplanes, steps, warmup):
+    """The oracle port on the host cores: scipy pocketfft dctn type 2 then type 3 over (h, w) of an interleaved
+    [n][h][w][d] buffer, all threads.  Returns (Gpixel/s, cores, seconds per step)."""
+    cores = _cpu_threads()
     import numpy as np
     from oracle import dct as od
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(0)
-    x = rng.random((nplanes, h, w, d)).astype(np.float32 if prec == "f" else np.float64)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
+    x = np.random.default_rng(0).random((nplanes, h, w, d)).astype(np.float32 if prec == "f" else np.float64)
+
+    def one():
         y = od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores)
-        z = od.dctn_fast(y, [od.REDFT01] * 2, axes=(1, 2), workers=cores)
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
-    del z
-    return nplanes * h * w * d / best / 1e9, cores, best
-
-
-def run_motion3d(args):
-    """3-D DCT-II + DCT-III round trip of one 256x1080x1920 float volume, frame slabs over the ranks."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from dspfun_b200 import capi
-    from dspfun_b200.dist3d import Dist3D
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = capi.load()
-    D, H, W = MOTION3D
-    d3 = Dist3D(D, H, W, "f", exchange=os.environ.get("DSP_DIST_EXCHANGE", "auto"))
-    g = torch.Generator(device="cuda").manual_seed(3 + rank)
-    slab = torch.rand((D // world, H, W), device="cuda", dtype=torch.float32, generator=g)
-    ref = slab[0].clone()
-    scale = 1.0 / (8.0 * D * H * W)
-
-    def step(x):
-        c = d3.forward(x)
-        y = d3.inverse(c)
-        y.mul_(scale)            # keeps the round trip an identity across steps
-        return y
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    x = slab
-    for _ in range(args.warmup):
-        x = step(x)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = lib.dsp_dct_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        x = step(x)
-    e1.record()
-    if rank == 0:
-        sampler.sample_now()     # everything is enqueued, the GPU is still working: a sample under load, no stall
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = int(lib.dsp_dct_launch_count() - l0)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    err = (torch.linalg.norm((x[0] - ref).double()) / torch.linalg.norm(ref.double())).item()
-    samples = D * H * W
-    value = samples * args.steps / (ms * 1e-3) / 1e9
-    peak, peak_src = peaks()
-    # end to end: pinned host slab -> device -> forward + inverse -> host
-    hbuf = torch.empty(slab.shape, dtype=torch.float32).pin_memory()
-    hbuf.copy_(slab)
-    barrier()
+        return od.dctn_fast(y, [od.REDFT01] * 2, axes=(1, 2), workers=cores)
+    for _ in range(warmup):
+        one()
     t0 = time.perf_counter()
-    ks = 2
-    for _ in range(ks):
-        dev = hbuf.to("cuda", non_blocking=True)
-        out = step(dev)
-        hbuf.copy_(out, non_blocking=True)
-        torch.cuda.synchronize()
-    barrier()
-    dt = (time.perf_counter() - t0) / ks
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "motion3d", "shape": [D, H, W], "bytes_total": samples * 4,
-                       "l2_policy": "inputs larger than L2 (%.0f MB per GPU)" % (samples * 4 / world / 1e6),
-                       "parallelism": ("frame slabs; exchange around the temporal transform: " +
-                                       ("fused into the preceding pass (stores into peer-mapped buffers over NVLink)" if d3.mode == "peer"
-                                        else "pack + NCCL all-to-all")) if world > 1 else "single GPU, one rank-3 plan",
-                       "exchange": d3.mode if world > 1 else None},
-            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": (16.0 * samples / world * args.steps / (ms * 1e-3) / 1e9) / peak,
-                         "traffic": None, "peak_source": peak_src},
-            "cpu_baseline": None,
-            "e2e": {"value": samples / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": samples * 4 // world,
-                    "d2h_bytes_per_step": samples * 4 // world, "steps": ks, "ms_per_step": dt * 1e3},
-            "gpu_launches": launches, "clocks": clocks, "roundtrip_rel_l2": err,
-            "nvlink_bytes_per_gpu_per_step": d3.a2a_bytes // max(1, args.steps + args.warmup + ks),
-        }))
-    d3.destroy()
-    if world > 1:
-        dist.destroy_process_group()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return nplanes * h * w * d / dt / 1e9, cores, dt
+
+
+def cpu_roundtrip_3d(D, H, W, steps, warmup):
+    cores = _cpu_threads()
+    import numpy as np
+    from oracle import dct as od
+    x = np.random.default_rng(0).integers(0, 256, (D, H, W)).astype(np.float32)
+
+    def one():
+        y = od.dctn_fast(x, [od.REDFT10] * 3, workers=cores)
+        z = od.dctn_fast(y, [od.REDFT01] * 3, workers=cores)
+        return np.clip(np.rint(z * (1.0 / (8.0 * D * H * W))), 0, 255).astype(np.uint8)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return D * H * W / dt / 1e9, cores, dt
+
+
+def cpu_sample_planes(h, w, d):
+    """bounded CPU sample of a 2-D workload: about 2^24 samples per step"""
+    return 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
+
+
+def plane_config(name, planes, world):
+    h, w, d, default, prec, scaling = WORKLOADS[name]
+    es = 4 if prec == "f" else 8
+    per_gpu = planes if scaling == "weak" else planes // world
+    cfg = {"workload": name, "shape": [h, w, d], "planes_per_gpu": per_gpu,
+           "bytes_per_gpu": per_gpu * h * w * d * es,
+           "l2_policy": "inputs larger than L2 (%.0f MB per GPU per step)" % (per_gpu * h * w * d * es / 1e6),
+           "parallelism": "independent planes per GPU, no collective"}
+    if scaling == "strong":
+        cfg["images_total"] = planes
+    return cfg
 
 
 def run_reference(args):
-    if args.workload == "motion3d":
-        return run_reference_motion3d(args)
-    h, w, d, planes, prec = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    # bounded sample: one plane / a few images of the workload per step
-    nplanes = 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
-    import numpy as np
-    from oracle import dct as od
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(0)
-    x = rng.random((nplanes, h, w, d)).astype(np.float32 if prec == "f" else np.float64)
-    steps = min(args.steps, 5)
-    warm = min(args.warmup, 1)
-    for _ in range(warm):
-        od.dctn_fast(od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores), [od.REDFT01] * 2, axes=(1, 2), workers=cores)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        y = od.dctn_fast(x, [od.REDFT10] * 2, axes=(1, 2), workers=cores)
-        od.dctn_fast(y, [od.REDFT01] * 2, axes=(1, 2), workers=cores)
-    dt = (time.perf_counter() - t0) / steps
-    val = nplanes * h * w * d / dt / 1e9
-    sample = "%d x %dx%dx%d %s per step, forward+inverse, scipy pocketfft workers=%d" % (nplanes, h, w, d, "f32" if prec == "f" else "f64", cores)
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "shape": [h, w, d], "note": "FFTW is not in the image: oracle port (pocketfft stand-in, not FFTW) on the host cores"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
-
-
-def run_reference_motion3d(args):
+    """CPU arm: rank 0 only.  Each step is a bounded sample of the workload (stated in cpu_baseline.sample)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import numpy as np
-    from oracle import dct as od
-    D, H, W = MOTION3D
-    Ds = 32                                               # bounded sample: 1/8 of the frames
-    cores = os.cpu_count() or 1
-    x = np.random.default_rng(0).random((Ds, H, W)).astype(np.float32)
-    steps = min(args.steps, 3)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        y = od.dctn_fast(x, [od.REDFT10] * 3, workers=cores)
-        od.dctn_fast(y, [od.REDFT01] * 3, workers=cores)
-    dt = (time.perf_counter() - t0) / steps
-    val = Ds * H * W / dt / 1e9
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "motion3d", "shape": [D, H, W]},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%dx%dx%d of the volume per step, scipy pocketfft workers=%d (FFTW not in image)" % (Ds, H, W, cores)},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="plane8192", choices=sorted(WORKLOADS) + ["motion3d"])
-    ap.add_argument("--planes", type=int, default=0, help="planes/images per GPU (0 = workload default)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.workload == "motion3d":
-        return run_motion3d(args)
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from dspfun_b200 import REDFT01, REDFT10, Plan, capi
-
-    rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = capi.load()
+    name = "plane8192" if args.workload == "all" else args.workload
 
-    h, w, d, planes, prec = WORKLOADS[args.workload]
+    def rec2d(nm):
+        h, w, d, planes, prec, scaling = WORKLOADS[nm]
+        n = cpu_sample_planes(h, w, d)
+        v, cores, dt = cpu_roundtrip_2d(h, w, d, prec, n, args.steps, args.warmup)
+        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
+                "config": plane_config(nm, args.planes or planes, world),
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "each step = %d x %dx%dx%d of the workload, forward+inverse, scipy pocketfft workers=%d "
+                                           "(oracle port; FFTW is not in the image)" % (n, h, w, d, cores)},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    def rec3d():
+        Ds = 16
+        steps, warm = min(args.steps, 5), min(args.warmup, 1)
+        tot, tt = 0.0, 0.0
+        for _, D, H, W in MOTION_PLANES:
+            v, cores, dt = cpu_roundtrip_3d(Ds, H, W, steps, warm)
+            tot += Ds * H * W; tt += dt
+        v = tot / tt / 1e9
+        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": tt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": "motion3d", "planes": [list(p) for p in MOTION_PLANES]},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "each step = %d of the 256 frames of Y, U and V, 3-D forward+inverse+8-bit store, "
+                                           "scipy pocketfft workers=%d (oracle port; FFTW is not in the image)" % (Ds, cores)},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    out = rec3d() if name == "motion3d" else rec2d(name)
+    if args.workload == "all":
+        out["records"] = {"batch1024": rec2d("batch1024"), "motion3d": rec3d()}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from dspfun_b200 import capi
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.lib = capi.load()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, step, steps, warmup, sampler=None):
+        """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream,
+        max over ranks.  Returns (ms for the K steps, launches of our kernels inside the region)."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        if sampler is not None and self.rank == 0:
+            sampler.start()
+        l0 = self.lib.dsp_dct_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        if sampler is not None and self.rank == 0:
+            sampler.sample_now()     # everything is enqueued, the GPU is still working: a sample under load, no stall
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = int(self.lib.dsp_dct_launch_count() - l0)
+        return self.max_over_ranks(ms), launches
+
+
+def bench_planes(ctx, args, name, want_cpu):
+    """2-D round trip of a batch of planes / images (C3, C4 and the other --workload shapes)."""
+    import numpy as np
+    torch = ctx.torch
+    from dspfun_b200 import REDFT01, REDFT10, Plan, capi
+    lib, world, rank = ctx.lib, ctx.world, ctx.rank
+    h, w, d, planes, prec, scaling = WORKLOADS[name]
     if args.planes:
         planes = args.planes
+    total_planes = planes
+    if scaling == "strong":
+        lo, hi = rank * planes // world, (rank + 1) * planes // world
+        planes = hi - lo
     tdt = torch.float32 if prec == "f" else torch.float64
     es = 4 if prec == "f" else 8
     g = torch.Generator(device="cuda").manual_seed(1000 + rank)
-    x = torch.rand((planes, h, w, d), device="cuda", dtype=tdt, generator=g)
+    x = torch.empty((planes, h, w, d), device="cuda", dtype=tdt)
+    for i in range(0, planes, 256):                       # generated in slices: no second full-size temporary
+        x[i:i + 256].copy_(torch.rand((min(256, planes - i), h, w, d), device="cuda", dtype=tdt, generator=g))
     x0 = x[0].clone()
     fwd = Plan.interleaved_2d(prec, h, w, d, REDFT10, nbatch=planes)
     inv = Plan.interleaved_2d(prec, h, w, d, REDFT01, nbatch=planes).fuse_scale(1.0, 1.0 / (4.0 * h * w))
@@ -386,41 +358,40 @@ def main():
         fwd.execute_dev(ptr, ptr, stream)
         inv.execute_dev(ptr, ptr, stream)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    # per-pass device times (CUDA events around every launch).  Few launches per step: recorded over the timed region
+    # itself.  The chunked schedule of a large batch is thousands of launches per step: recorded over 3 extra steps
+    # before the timed region instead, so that the event traffic cannot perturb the headline.
+    for _ in range(max(1, args.warmup)):
         step()
-    barrier()
     fwd.profile(True); inv.profile(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = lib.dsp_dct_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    if rank == 0:
-        sampler.sample_now()     # everything is enqueued, the GPU is still working: a sample under load, no stall
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = int(lib.dsp_dct_launch_count() - l0)
+    step()
+    ctx.barrier()
+    probe = fwd.pass_stats() + inv.pass_stats()
+    in_region = sum(s["kernel_launches"] for s in probe) <= 64
+    if not in_region:
+        for _ in range(3):
+            step()
+        ctx.barrier()
+        fwd.profile(False); inv.profile(False)
+        stats = [("fwd", s) for s in fwd.pass_stats()] + [("inv", s) for s in inv.pass_stats()]
+    else:
+        fwd.profile(False); inv.profile(False)
+
+    sampler = ClockSampler(ctx.local)
+    if in_region:
+        # profiling is switched on after the warm-up steps inside ctx.timed would be cleaner, but the events of warm-up
+        # steps only add to the average: switch on here, warm-up included
+        fwd.profile(True); inv.profile(True)
+    ms, launches = ctx.timed(step, args.steps, args.warmup, sampler)
+    if in_region:
+        fwd.profile(False); inv.profile(False)
+        stats = [("fwd", s) for s in fwd.pass_stats()] + [("inv", s) for s in inv.pass_stats()]
     clocks = sampler.stop() if rank == 0 else None
-    fwd.profile(False); inv.profile(False)
-    stats = [("fwd", s) for s in fwd.pass_stats()] + [("inv", s) for s in inv.pass_stats()]
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     # round trip must be the identity (parity is the tests' job; this guards against a broken timed region)
     err = (torch.linalg.norm((x[0] - x0).double()) / torch.linalg.norm(x0.double())).item()
     samples_per_step = planes * h * w * d
-    value = world * samples_per_step * args.steps / (ms * 1e-3) / 1e9
+    job_samples = (world * samples_per_step) if scaling == "weak" else total_planes * h * w * d
+    value = job_samples * args.steps / (ms * 1e-3) / 1e9
     ms_per_step = ms / args.steps
 
     # roofline of the dominant kernel (largest share of the step)
@@ -430,21 +401,19 @@ def main():
         if s["launches"]:
             avg_ms = s["ms_total"] / s["launches"]
             kern.append({"plan": which, "kernel": s["kernel"], "axis": s["axis"], "n": s["n"], "grid": s["grid"],
-                         "smem_bytes": s["smem_bytes"], "avg_ms": avg_ms,
+                         "smem_bytes": s["smem_bytes"], "avg_ms": avg_ms, "launches_per_pass": s["kernel_launches"] / s["launches"],
                          "achieved_gbs": 2 * es * s["samples"] / (avg_ms * 1e-3) / 1e9})
     dom = max(kern, key=lambda k: k["avg_ms"]) if kern else None
     roofline = None
-    traffic = None
     if dom:
-        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if recorded
-        try:
+        traffic = None
+        try:     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if recorded
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]))
-            if traffic is not None and planes != WORKLOADS[args.workload][3]:
-                traffic = traffic * planes / WORKLOADS[args.workload][3]
+                traffic = json.load(f).get(name, {}).get("%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]))
+            if traffic is not None and planes != WORKLOADS[name][3]:
+                traffic = traffic * planes / WORKLOADS[name][3]
         except Exception:
             traffic = None
-    if dom:
         roofline = {"bound": "hbm", "kernel": "%s/%s(n=%d)" % (dom["plan"], dom["kernel"], dom["n"]),
                     "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["achieved_gbs"] / peak,
                     "traffic": traffic, "peak_source": peak_src,
@@ -454,53 +423,209 @@ def main():
     # end to end through the C ABI with pinned HOST buffers: H2D + passes + D2H for forward, then for inverse
     e2e = None
     if not args.no_e2e:
-        nbytes = samples_per_step * es
+        ep = min(planes, max(1, (3 << 30) // (h * w * d * es)))           # bounded: at most ~3 GiB of pinned host memory
+        if ep != planes:
+            fe = Plan.interleaved_2d(prec, h, w, d, REDFT10, nbatch=ep)
+            ie = Plan.interleaved_2d(prec, h, w, d, REDFT01, nbatch=ep).fuse_scale(1.0, 1.0 / (4.0 * h * w))
+        else:
+            fe, ie = fwd, inv
+        nsamp = ep * h * w * d
+        nbytes = nsamp * es
         hp = lib.dsp_dct_alloc(nbytes)
         if not hp:
             raise SystemExit("dsp_dct_alloc failed: " + capi.last_error(lib))
         ctype = ctypes.c_float if prec == "f" else ctypes.c_double
-        hbuf = np.ctypeslib.as_array((ctype * samples_per_step).from_address(hp))
-        hbuf[:] = np.random.default_rng(5 + rank).random(samples_per_step, dtype=np.float32 if prec == "f" else np.float64)
+        hbuf = np.ctypeslib.as_array((ctype * nsamp).from_address(hp))
+        hbuf[:] = np.random.default_rng(5 + rank).random(nsamp, dtype=np.float32 if prec == "f" else np.float64)
         ksteps = max(2, min(args.steps, 5))
-        fwd.execute_host(hbuf); inv.execute_host(hbuf)      # warm (allocates the plan's staging buffers)
-        barrier()
+        fe.execute_host(hbuf); ie.execute_host(hbuf)      # warm (allocates the plan's staging buffers)
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            fwd.execute_host(hbuf)
-            inv.execute_host(hbuf)
-        barrier()
-        dt = (time.perf_counter() - t0) / ksteps
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * samples_per_step / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
+            fe.execute_host(hbuf)
+            ie.execute_host(hbuf)
+        ctx.barrier()
+        dt = ctx.max_over_ranks((time.perf_counter() - t0) / ksteps)
+        e2e = {"value": world * nsamp / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
                "d2h_bytes_per_step": 2 * nbytes, "steps": ksteps, "ms_per_step": dt * 1e3,
-               "path": "dsp_dct_execute_host (pinned host buffers, forward then inverse)"}
+               "path": "dsp_dct_execute_host (pinned host buffers, forward then inverse)",
+               "sample": "%d of the rank's %d planes per step" % (ep, planes)}
         lib.dsp_dct_free(hp)
+        if fe is not fwd:
+            fe.destroy(); ie.destroy()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        nplanes = 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
-        v, cores, secs = cpu_roundtrip(h, w, d, prec, 3, nplanes)
+    if rank == 0 and world == 1 and want_cpu:
+        n = cpu_sample_planes(h, w, d)
+        v, cores, secs = cpu_roundtrip_2d(h, w, d, prec, n, 3, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d x %dx%dx%d round trip, best of 3 (%.0f ms), scipy pocketfft workers=%d (FFTW not in image)" % (nplanes, h, w, d, secs * 1e3, cores)}
+               "sample": "%d x %dx%dx%d round trip, mean of 3 (%.0f ms), scipy pocketfft workers=%d (oracle port; FFTW is not in the image)" % (n, h, w, d, secs * 1e3, cores)}
 
-    if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "shape": [h, w, d], "planes_per_gpu": planes,
-                       "bytes_per_gpu": samples_per_step * es, "l2_policy": "inputs larger than L2 (%.0f MB per GPU per pass)" % (samples_per_step * es / 1e6),
-                       "parallelism": "independent planes per GPU, no collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernels": kern, "roundtrip_rel_l2": err,
-        }
-        print(json.dumps(out))
     fwd.destroy(); inv.destroy()
-    if world > 1:
-        dist.destroy_process_group()
+    del x
+    torch.cuda.empty_cache()
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32" if prec == "f" else "f64", "data": "synthetic",
+        "config": plane_config(name, total_planes, world),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "kernels": kern, "kernel_times": "CUDA events over the timed region" if in_region else "CUDA events over 3 extra steps (chunked schedule: %d launches per step)" % sum(s["kernel_launches"] for s in probe),
+        "roundtrip_rel_l2": err,
+    }
+
+
+def bench_motion3d(ctx, args, want_cpu):
+    """C5: `motion -b 0x0x0` on a 1920x1080x256 yuv420p 8-bit volume: per plane (Y, U, V) 8-bit pels -> 3-D REDFT10 ->
+    coefficient stages (motion.c:644-751; no filter here, so the output must equal the input bit for bit) -> 3-D REDFT01
+    -> 8-bit pels.  One volume, frame slabs over the ranks (strong scaling)."""
+    torch = ctx.torch
+    from dspfun_b200.dist3d import Dist3D, motion_params
+    world, rank = ctx.world, ctx.rank
+    mode = os.environ.get("DSP_DIST_EXCHANGE", "auto")
+    planes = []
+    for nm, D, H, W in MOTION_PLANES:
+        d3 = Dist3D(D, H, W, "f", exchange=mode, motion=motion_params((D, H, W)))
+        g = torch.Generator(device="cuda").manual_seed(7 + rank)
+        pels = torch.randint(16, 236, (D // world, H, W), device="cuda", dtype=torch.uint8, generator=g)
+        planes.append(dict(name=nm, d3=d3, pels=pels, out=torch.empty_like(pels),
+                           work=torch.empty((D // world, H, W), device="cuda", dtype=torch.float32)))
+
+    def step():
+        for p in planes:
+            p["d3"].process(p["pels"], p["out"], p["work"])
+
+    sampler = ClockSampler(ctx.local)
+    ms, launches = ctx.timed(step, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if rank == 0 else None
+    exact = all(bool(torch.equal(p["out"], p["pels"])) for p in planes)
+    mism = sum(int((p["out"] != p["pels"]).sum().item()) for p in planes)
+    samples = sum(D * H * W for _, D, H, W in MOTION_PLANES)
+    value = samples * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    # algorithmic traffic of the round trip with 8-bit endpoints: forward 1 B in + 4 B out, inverse 4 B in + 1 B out
+    abytes = 10.0 * samples / world
+    ach = abytes * args.steps / (ms * 1e-3) / 1e9
+
+    # per-pass device times of the Y plane (untimed extra steps): which passes carry the exchange
+    passes = []
+    y = planes[0]["d3"]
+    names = ("fwd3", "inv3") if world == 1 else ("fwd2", "fwdt", "invt", "inv2")
+    for n in names:
+        getattr(y, n).profile(True)
+    for _ in range(3):
+        planes[0]["d3"].process(planes[0]["pels"], planes[0]["out"], planes[0]["work"])
+    ctx.barrier()
+    for n in names:
+        pl = getattr(y, n)
+        pl.profile(False)
+        for s in pl.pass_stats():
+            if s["launches"]:
+                remote = world > 1 and y.mode == "peer" and ((n == "fwd2" and not s["kernel"] == "row") or n == "invt")
+                passes.append({"plan": n, "kernel": s["kernel"], "axis": s["axis"], "n": s["n"],
+                               "avg_ms": s["ms_total"] / s["launches"], "stores_to_peers": bool(remote)})
+    comm_ms = sum(p["avg_ms"] for p in passes if p["stores_to_peers"])
+    tot_ms = sum(p["avg_ms"] for p in passes)
+
+    # end to end: pinned host 8-bit slabs -> device -> process -> host
+    e2e = None
+    if not args.no_e2e:
+        hin = [torch.empty(p["pels"].shape, dtype=torch.uint8).pin_memory() for p in planes]
+        hout = [torch.empty(p["pels"].shape, dtype=torch.uint8).pin_memory() for p in planes]
+        for hb, p in zip(hin, planes):
+            hb.copy_(p["pels"])
+        ks = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            for hb, ho, p in zip(hin, hout, planes):
+                p["pels"].copy_(hb, non_blocking=True)
+                p["d3"].process(p["pels"], p["out"], p["work"])
+                ho.copy_(p["out"], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ks):
+            e2e_step()
+        ctx.barrier()
+        dt = ctx.max_over_ranks((time.perf_counter() - t0) / ks)
+        nb = sum(int(p["pels"].numel()) for p in planes)
+        e2e = {"value": samples / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb, "steps": ks,
+               "ms_per_step": dt * 1e3, "path": "pinned 8-bit host slabs -> Dist3D.process (C ABI plans) -> pinned 8-bit host slabs"}
+
+    cpu = None
+    if rank == 0 and world == 1 and want_cpu:
+        Ds, tot, tt = 16, 0.0, 0.0
+        for _, D, H, W in MOTION_PLANES:
+            v, cores, dt = cpu_roundtrip_3d(Ds, H, W, 2, 1)
+            tot += Ds * H * W; tt += dt
+        cpu = {"value": tot / tt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the 256 frames of Y, U, V: 3-D forward+inverse+8-bit store, scipy pocketfft workers=%d (oracle port)" % (Ds, cores)}
+
+    modes = {p["name"]: (p["d3"].mode if world > 1 else None) for p in planes}
+    nvlink = sum(p["d3"].a2a_bytes for p in planes) // max(1, args.steps + args.warmup + 3 + (0 if args.no_e2e else 1 + max(2, min(args.steps, 5))))
+    rec = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "motion3d", "pixel_format": "yuv420p 8-bit", "planes": [list(p) for p in MOTION_PLANES],
+                   "endpoints": "8-bit pels in, 8-bit pels out (fused into the first / last pass)",
+                   "l2_policy": "inputs larger than L2 (%.0f MB of coefficients per GPU)" % (samples * 4 / world / 1e6),
+                   "parallelism": ("frame slabs; exchange around the temporal transform per plane: " + json.dumps(modes)) if world > 1
+                                  else "single GPU: one rank-3 plan pair per plane",
+                   "exchange": modes},
+        "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_sample": 10, "note": "forward 1 B in + 4 B out, inverse 4 B in + 1 B out"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "u8_roundtrip_exact": exact, "u8_mismatches": mism,
+        "passes_Y": passes, "comm_share_Y": (comm_ms / tot_ms) if tot_ms else None,
+        "nvlink_bytes_per_gpu_per_step": int(nvlink),
+    }
+    for p in planes:
+        p["d3"].destroy()
+    planes.clear()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS) + ["motion3d"])
+    ap.add_argument("--planes", type=int, default=0, help="planes/images per GPU (weak) or in total (strong); 0 = workload default")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    ctx = Ctx()
+    want_cpu = not args.no_cpu
+    if args.workload == "all":
+        out = bench_planes(ctx, args, "plane8192", want_cpu)
+        recs = {}
+        for nm in ("batch1024", "motion3d"):
+            try:
+                recs[nm] = bench_planes(ctx, args, nm, want_cpu) if nm != "motion3d" else bench_motion3d(ctx, args, want_cpu)
+            except Exception as e:                              # a failing sub-record must not take the headline with it
+                recs[nm] = {"error": repr(e)}
+                ctx.torch.cuda.synchronize()
+        out["records"] = recs
+        out["gpu_launches_total"] = out["gpu_launches"] + sum(r.get("gpu_launches", 0) for r in recs.values())
+    elif args.workload == "motion3d":
+        out = bench_motion3d(ctx, args, want_cpu)
+    else:
+        out = bench_planes(ctx, args, args.workload, want_cpu)
+    if ctx.rank == 0:
+        print(json.dumps(out))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def _clean_stdout():

@@ -29,6 +29,7 @@ SYMBOLS = [
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
     "dsp_block_store_u8",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
+    "dsp_dct_fuse_pel_load", "dsp_dct_fuse_motion_coeff", "dsp_dct_fuse_pel_store", "dsp_dct_is_emulation",
 ]
 
 
@@ -141,6 +142,14 @@ def bind(path):
     lib.dsp_dct_num_passes.argtypes = [vp]
     lib.dsp_dct_pass_stat_get.restype = ci
     lib.dsp_dct_pass_stat_get.argtypes = [vp, ci, ctypes.POINTER(PassStat)]
+    lib.dsp_dct_fuse_pel_load.restype = ci
+    lib.dsp_dct_fuse_pel_load.argtypes = [vp, ci]
+    lib.dsp_dct_fuse_motion_coeff.restype = ci
+    lib.dsp_dct_fuse_motion_coeff.argtypes = [vp, ctypes.POINTER(MotionParams), vp, ci, ctypes.c_longlong]
+    lib.dsp_dct_fuse_pel_store.restype = ci
+    lib.dsp_dct_fuse_pel_store.argtypes = [vp, ctypes.POINTER(MotionParams)]
+    lib.dsp_dct_is_emulation.restype = ci
+    lib.dsp_dct_is_emulation.argtypes = []
     return lib
 
 
@@ -155,7 +164,11 @@ def load():
             raise DspDctError(
                 "dspfun_b200/libdspdct.so is missing: build it with `make -C dspfun_b200/csrc` "
                 "(or python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
-        _LIB = bind(LIB_PATH)
+        lib = bind(LIB_PATH)
+        if lib.dsp_dct_is_emulation():
+            raise DspDctError("%s is the host emulation of the kernels (a test harness): the product loader only takes "
+                              "the CUDA build.  There is no CPU path." % LIB_PATH)
+        _LIB = lib
     return _LIB
 
 

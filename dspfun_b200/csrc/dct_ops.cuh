@@ -118,7 +118,11 @@ struct OpAny {
 			return (idx >= lo && idx < hi) ? v : (T)0;                                               // scan.c:429-432
 		}
 		case OP_MOTION_COEFF: {
-			const int z = c.i0, y = c.i1, x = c.i2;
+			int z = c.i0, y = c.i1, x = c.i2;
+			if (w > 0) {                                  // temporal pass of a slab-sharded volume: [D][slice of flattened h*w]
+				const int hw = lo + c.ch;
+				z = c.i2; y = hw / w; x = hw - y * w;
+			}
 			if (z >= a3[0] || y >= a3[1] || x >= a3[2]) return (T)0;                                 // outside the active box: motion.c:617
 			const I nf = (2 * SQRT2) / ((x ? 1.0 : SQRT2) * (y ? 1.0 : SQRT2) * (z ? 1.0 : SQRT2));
 			T f = (T)((I)v * nf);                                                                    // :644-647

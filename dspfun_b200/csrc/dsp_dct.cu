@@ -1050,6 +1050,8 @@ const char *dsp_dct_last_error(void) { return g_err.c_str(); }
 
 unsigned long long dsp_dct_launch_count(void) { return g_launches.load(); }
 
+int dsp_dct_is_emulation(void) { return DSP_GPU ? 0 : 1; }
+
 int dsp_dct_profile(dsp_dct_plan p, int enable) {
 	if (!p) return 1;
 	p->profiling = enable != 0;
@@ -1328,6 +1330,96 @@ int dsp_scan_sum(dsp_scan s, void *sum) {
 
 void dsp_scan_destroy(dsp_scan s) { scan_free(s); }
 
+// ------------------------------------------------------------------------------------------------ motion stages
+// The three fused stages of motion's block body as plan-level calls, so that the slab-sharded volume (dist3d) can put
+// them on its own plans: pel load on the first forward pass, coefficient stages on the first inverse pass, pel store
+// on the last inverse pass.
+int dsp_dct_fuse_pel_load(dsp_dct_plan p, int float_pixels) {
+	g_err.clear();
+	if (!p) { g_err = "null plan"; return 1; }
+	PassPlan &f0 = p->passes.front();
+	if (!f0.row) { g_err = "pel load needs a plan whose first pass runs along the contiguous axis"; return 1; }
+	if (float_pixels) {
+		if (p->prec != 'f') { g_err = "float pels need the float build (COEFF_PRECISION=F)"; return 1; }
+		f0.lop.kind = OP_SCALE; f0.lop.p[0] = 255.0;                                        // motion.c:622
+	} else f0.ra.in_u8 = 1;                                                                  // motion.c:624
+	return 0;
+}
+
+static void motion_constants(const dsp_motion_params *mp, double &scalefactor, double &norm) {
+	const double sw = mp->scaled[2], sh = mp->scaled[1], sd = mp->scaled[0];
+	const double bw = mp->block[2], bh = mp->block[1], bd = mp->block[0];
+	scalefactor = (sw * sh * sd) / (bw * bh * bd);                                           // motion.c:566
+	norm = 1.0 / sqrt(sw * sh * sd * 8.0);                                                   // motion.c:567
+}
+
+int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsigned long long *d_counter, int flat_w,
+                              long long flat_base) {
+	g_err.clear();
+	if (!p || !mp) { g_err = "null plan or params"; return 1; }
+	if (p->fuse_kind && p->fuse_kind != 4) { g_err = "plan already carries a fused stage"; return 1; }
+	double scalefactor, norm;
+	motion_constants(mp, scalefactor, norm);
+	const double sw = mp->scaled[2], sh = mp->scaled[1], sd = mp->scaled[0];
+	OpAny op;
+	memset(&op, 0, sizeof(op));
+	op.kind = OP_MOTION_COEFF;
+	for (int i = 0; i < 3; i++) {
+		const int active = mp->block[i] < mp->scaled[i] ? mp->block[i] : mp->scaled[i];      // motion.c:494-496
+		if (mp->bp_begin[i] < 0 || mp->bp_end[i] > active || mp->bp_begin[i] > mp->bp_end[i]) { g_err = "band-pass box outside the active box"; return 1; }
+		op.a3[i] = active; op.b3[i] = mp->bp_begin[i]; op.e3[i] = mp->bp_end[i];
+	}
+	op.m[0] = mp->damp; op.m[1] = mp->boost;
+	op.m[2] = mp->threshold_min * 255.0 / norm / norm; op.m[3] = mp->threshold_max * 255.0 / norm / norm;   // motion.c:571-572
+	if (p->prec == 'f') { op.m[2] = (double)(float)op.m[2]; op.m[3] = (double)(float)op.m[3]; }
+	op.m[4] = mp->quant * 8.0 * sqrt(sw * sh * sd);                                          // motion.c:570
+	if (p->prec == 'f') op.m[4] = (double)(float)op.m[4];
+	op.m[5] = 127.5 / (norm * norm * scalefactor);                                           // motion.c:736
+	op.flag = mp->preserve_dc;
+	op.aux = d_counter;
+	// flat_w > 0: the plan is the temporal pass of a slab-sharded volume over a [D][hw-slice] array -- the axis index is
+	// z and (y, x) come from the flattened column index: hw = flat_base + column, y = hw / flat_w, x = hw % flat_w
+	op.w = flat_w; op.lo = (int)flat_base;
+	if (flat_w > 0 && (p->rank != 1 || p->passes.size() != 1 || p->passes[0].row)) {
+		g_err = "flat coefficient coordinates need the rank-1 strided-axis plan of a [D][h*w slice] array";
+		return 1;
+	}
+	if (p->kind[0] == DSP_DCT_REDFT10) {
+		// on a forward plan the stages ride in the last pass's store (same pointwise map, applied one step earlier)
+		PassPlan &l = p->passes.back();
+		l.sop = op; l.fused = true;
+	} else {
+		PassPlan &i0 = p->passes.front();
+		i0.lop = op; i0.fused = true;
+	}
+	p->fuse_kind = 4;
+	return 0;
+}
+
+int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp) {
+	g_err.clear();
+	if (!p || !mp) { g_err = "null plan or params"; return 1; }
+	if (p->fuse_kind && p->fuse_kind != 4) { g_err = "plan already carries a fused stage"; return 1; }
+	PassPlan &il = p->passes.back();
+	if (!il.row) { g_err = "pel store needs a plan whose last pass runs along the contiguous axis"; return 1; }
+	if (mp->float_pixels && p->prec != 'f') { g_err = "float pels need the float build (COEFF_PRECISION=F)"; return 1; }
+	double scalefactor, norm;
+	motion_constants(mp, scalefactor, norm);
+	OpAny op;
+	memset(&op, 0, sizeof(op));
+	op.kind = OP_MOTION_STORE;
+	op.m[6] = scalefactor * norm * norm;                                                     // motion.c:757,767
+	op.flag2 = mp->float_pixels;
+	il.sop = op; il.fused = true;
+	if (!mp->float_pixels) {
+		il.ra.out_u8 = 1;
+		// the passes before the 8-bit store keep their T-typed intermediate in a work buffer of the output's extent
+		if (p->passes.size() > 1 && !p->d_work && !rt_malloc(&p->d_work, p->out_span * (size_t)p->es, g_err)) return 1;
+	}
+	p->fuse_kind = 4;
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ motion session
 struct dsp_motion_s {
 	char prec;
@@ -1377,41 +1469,9 @@ dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp) {
 		m->inv = m->fwd ? dsp_dct_plan_many(prec, 3, mp->scaled, 1, nullptr, m->minbuf, 1, 0, nullptr, m->minbuf, 1, 0, k01, 0) : nullptr;
 		ok = m->fwd && m->inv;
 	}
-	if (ok) {
-		const double sw = mp->scaled[2], sh = mp->scaled[1], sd = mp->scaled[0];
-		const double bw = mp->block[2], bh = mp->block[1], bd = mp->block[0];
-		const double scalefactor = (sw * sh * sd) / (bw * bh * bd);                        // motion.c:566
-		const double norm = 1.0 / sqrt(sw * sh * sd * 8.0);                                 // motion.c:567
-		// forward: first pass (row pass over w) reads the pels
-		PassPlan &f0 = m->fwd->passes.front();
-		if (!mp->float_pixels) f0.ra.in_u8 = 1;
-		else { f0.lop.kind = OP_SCALE; f0.lop.p[0] = 255.0; }                               // motion.c:622
-		// inverse: first pass carries every coefficient-space stage, last pass the pel store
-		PassPlan &i0 = m->inv->passes.front(), &il = m->inv->passes.back();
-		OpAny op;
-		memset(&op, 0, sizeof(op));
-		op.kind = OP_MOTION_COEFF;
-		for (int i = 0; i < 3; i++) { op.a3[i] = active[i]; op.b3[i] = mp->bp_begin[i]; op.e3[i] = mp->bp_end[i]; }
-		op.m[0] = mp->damp; op.m[1] = mp->boost;
-		op.m[2] = mp->threshold_min * 255.0 / norm / norm; op.m[3] = mp->threshold_max * 255.0 / norm / norm;   // motion.c:571-572
-		if (prec == 'f') { op.m[2] = (double)(float)op.m[2]; op.m[3] = (double)(float)op.m[3]; }
-		op.m[4] = mp->quant * 8.0 * sqrt(sw * sh * sd);                                     // motion.c:570
-		if (prec == 'f') op.m[4] = (double)(float)op.m[4];
-		op.m[5] = 127.5 / (norm * norm * scalefactor);                                      // motion.c:736
-		op.flag = mp->preserve_dc;
-		op.aux = m->d_counter;
-		i0.lop = op; i0.fused = true;
-		memset(&op, 0, sizeof(op));
-		op.kind = OP_MOTION_STORE;
-		op.m[6] = scalefactor * norm * norm;                                                // motion.c:757,767
-		op.flag2 = mp->float_pixels;
-		il.sop = op; il.fused = true;
-		if (!mp->float_pixels) {
-			il.ra.out_u8 = 1;
-			ok = rt_malloc(&m->inv->d_work, m->coeff_bytes, g_err);
-		}
-		m->inv->fuse_kind = 4;
-	}
+	if (ok)
+		ok = dsp_dct_fuse_pel_load(m->fwd, mp->float_pixels) == 0 &&
+		     dsp_dct_fuse_motion_coeff(m->inv, mp, m->d_counter, 0, 0) == 0 && dsp_dct_fuse_pel_store(m->inv, mp) == 0;
 	if (!ok) { motion_free(m); return nullptr; }
 	return m;
 }

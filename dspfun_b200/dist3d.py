@@ -31,8 +31,24 @@ def _ptr(t):
     return t.data_ptr()
 
 
+def motion_params(dims, damp=1.0, boost=1.0, bandpass=None, threshold=(0.0, 0.0), quant=0.0, preserve_dc=0,
+                  float_pixels=False):
+    """dsp_motion_params of a full-volume block (`motion -b 0x0x0`: block == scaled == the plane volume)."""
+    mp = capi.MotionParams()
+    bp = bandpass if bandpass is not None else ((0, 0, 0), tuple(dims))
+    for i in range(3):
+        mp.block[i] = mp.scaled[i] = int(dims[i])
+        mp.bp_begin[i], mp.bp_end[i] = int(bp[0][i]), int(bp[1][i])
+    mp.float_pixels = int(bool(float_pixels))
+    mp.damp, mp.boost = float(damp), float(boost)
+    mp.threshold_min, mp.threshold_max = float(threshold[0]), float(threshold[1])
+    mp.quant = float(quant)
+    mp.preserve_dc = int(preserve_dc)
+    return mp
+
+
 class Dist3D:
-    def __init__(self, D, H, W, prec="f", group=None, lib=None, exchange="auto", device=None):
+    def __init__(self, D, H, W, prec="f", group=None, lib=None, exchange="auto", device=None, motion=None):
         self.D, self.H, self.W = int(D), int(H), int(W)
         self.prec = prec
         self.tdt = torch.float32 if prec == "f" else torch.float64
@@ -54,6 +70,17 @@ class Dist3D:
             # time axis of a [D][Pl] array: stride Pl, Pl adjacent columns
             self.fwdt = Plan(prec, [D], [capi.REDFT10], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
             self.invt = Plan(prec, [D], [capi.REDFT01], self.Pl, None, self.Pl, 1, None, self.Pl, 1, **kw)
+        # motion's pel endpoints and coefficient stages (motion.c:618-624, 617-751, 757-776) fused into the plans either
+        # side of the exchange: 8-bit pels in, 8-bit pels out, see process()
+        self.motion = motion
+        if motion is not None:
+            if G == 1:
+                self.fwd3.fuse_pel_load(bool(motion.float_pixels))
+                self.inv3.fuse_motion_coeff(motion).fuse_pel_store(motion)
+            else:
+                self.fwd2.fuse_pel_load(bool(motion.float_pixels))
+                self.fwdt.fuse_motion_coeff(motion, None, W, self.rank * self.Pl)    # coefficient stages: temporal pass's store
+                self.inv2.fuse_pel_store(motion)
         self.a2a_bytes = 0
         self.mode = "nccl"
         if G > 1 and exchange in ("auto", "peer"):
@@ -116,6 +143,27 @@ class Dist3D:
         return torch.cuda.current_stream().cuda_stream if t.is_cuda else None
 
     # -- transforms ------------------------------------------------------------------------------------------------
+    def process(self, pels, out=None, work=None):
+        """motion -b 0x0x0 on this rank's frames (needs motion=...): pels [D/G][H][W] uint8 (float32 with float pels)
+        -> forward 3-D DCT -> coefficient stages -> inverse -> pels of the same type.  `work`: float [D/G][H][W] scratch."""
+        assert self.motion is not None
+        t = torch
+        pel_dt = t.float32 if self.motion.float_pixels else t.uint8
+        assert pels.dtype == pel_dt and pels.is_contiguous() and tuple(pels.shape) == (self.Dl, self.H, self.W)
+        if out is None:
+            out = t.empty_like(pels)
+        if work is None:
+            work = t.empty((self.Dl, self.H, self.W), dtype=self.tdt, device=pels.device)
+        st = self._stream(pels)
+        if self.G == 1:
+            self.fwd3.execute_dev(_ptr(pels), _ptr(work), st)
+            self.inv3.execute_dev(_ptr(work), _ptr(out), st)
+            return out
+        coeffs = self._forward_from(pels, work, st)
+        slab = self._inverse_to_slab(coeffs, st)
+        self.inv2.execute_dev(_ptr(slab), _ptr(out), st)
+        return out
+
     def forward(self, slab):
         """slab: [D/G][H][W] local frames (modified in place as scratch).  Returns the coefficients this rank owns:
         G == 1: [D][H][W];  G > 1: [D][HW/G] -- all temporal frequencies of its slice of flattened (h, w)."""
@@ -124,17 +172,21 @@ class Dist3D:
         if self.G == 1:
             self.fwd3.execute_dev(_ptr(slab), _ptr(slab), st)
             return slab
+        return self._forward_from(slab, slab, st)
+
+    def _forward_from(self, src, slab, st):
+        """frames `src` (same tensor as `slab`, or 8-bit pels with a fused pel load) -> coefficients [D][HW/G]"""
         G, Dl, Pl = self.G, self.Dl, self.Pl
         if self.mode == "peer":
             # (the returned array is the plan-owned symmetric buffer: valid until the next forward())
             self.h_cols.barrier(channel=0)                      # every peer is done with its previous cols
-            self.fwd2.execute_dev(_ptr(slab), _ptr(slab), st)   # last pass stores into the peers' cols
+            self.fwd2.execute_dev(_ptr(src), _ptr(slab), st)    # last pass stores into the peers' cols
             self.h_cols.barrier(channel=0)                      # all runs have landed
             cols = self.cols_buf.view(self.D, Pl)
             self.fwdt.execute_dev(_ptr(cols), _ptr(cols), st)
             self.a2a_bytes += slab.numel() * slab.element_size() * (G - 1) // G
             return cols
-        self.fwd2.execute_dev(_ptr(slab), _ptr(slab), st)
+        self.fwd2.execute_dev(_ptr(src), _ptr(slab), st)
         send = slab.view(Dl, G, Pl).permute(1, 0, 2).contiguous()          # [G][Dl][Pl]
         recv = torch.empty_like(send)
         self._all_to_all(recv, send)
@@ -149,22 +201,25 @@ class Dist3D:
         if self.G == 1:
             self.inv3.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
             return coeffs
+        slab = self._inverse_to_slab(coeffs, st)
+        self.inv2.execute_dev(_ptr(slab), _ptr(slab), st)
+        return slab
+
+    def _inverse_to_slab(self, coeffs, st):
+        """temporal inverse + exchange: coefficients [D][HW/G] -> this rank's frames [D/G][H][W], spatial axes still
+        in the frequency domain"""
         G, Dl, Pl = self.G, self.Dl, self.Pl
         if self.mode == "peer":
             self.h_slab.barrier(channel=1)
             self.invt.execute_dev(_ptr(coeffs), _ptr(coeffs), st)   # stores frames into the owning ranks' slabs
             self.h_slab.barrier(channel=1)
-            slab = self.slab_buf.view(Dl, self.H, self.W)
-            self.inv2.execute_dev(_ptr(slab), _ptr(slab), st)
             self.a2a_bytes += coeffs.numel() * coeffs.element_size() * (G - 1) // G
-            return slab
+            return self.slab_buf.view(Dl, self.H, self.W)
         self.invt.execute_dev(_ptr(coeffs), _ptr(coeffs), st)
         send = coeffs.view(G, Dl, Pl)                                       # chunk g = frames of rank g
         recv = torch.empty_like(send)
         self._all_to_all(recv, send.contiguous())
-        slab = recv.permute(1, 0, 2).contiguous().view(Dl, self.H, self.W)
-        self.inv2.execute_dev(_ptr(slab), _ptr(slab), st)
-        return slab
+        return recv.permute(1, 0, 2).contiguous().view(Dl, self.H, self.W)
 
     def destroy(self):
         for n in ("fwd3", "inv3", "fwd2", "inv2", "fwdt", "invt"):

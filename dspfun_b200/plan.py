@@ -59,6 +59,20 @@ class Plan:
         self._check(self.lib.dsp_dct_set_output_segments(self._h, 0, 0, None, 0, 0))
         return self
 
+    # motion's stages on a caller-owned plan (include/dsp_dct.h; motion/motion.c:618-624, 617-751, 757-776)
+    def fuse_pel_load(self, float_pixels=False):
+        self._check(self.lib.dsp_dct_fuse_pel_load(self._h, int(bool(float_pixels))))
+        return self
+
+    def fuse_motion_coeff(self, mp, d_counter=None, flat_w=0, flat_base=0):
+        self._mp = mp
+        self._check(self.lib.dsp_dct_fuse_motion_coeff(self._h, ctypes.byref(mp), d_counter, int(flat_w), int(flat_base)))
+        return self
+
+    def fuse_pel_store(self, mp):
+        self._check(self.lib.dsp_dct_fuse_pel_store(self._h, ctypes.byref(mp)))
+        return self
+
     def fuse_spec(self, scaletype, signtype, rangetype, gain):
         sp = capi.SpecParams(int(scaletype), int(signtype), int(rangetype), float(gain))
         self._check(self.lib.dsp_dct_fuse_spec(self._h, ctypes.byref(sp)))

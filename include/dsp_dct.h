@@ -89,6 +89,10 @@ const char *dsp_dct_last_error(void);
 /* Number of this library's kernels launched so far by this process (bench.py's gpu_launches). */
 unsigned long long dsp_dct_launch_count(void);
 
+/* 0 for the product (CUDA) build.  1 for the sequential host emulation of the same kernel sources that the CPU test
+ * suite compiles (tests/emu); the package's loader refuses such a library. */
+int dsp_dct_is_emulation(void);
+
 /* Per-pass device timing (CUDA events on the launching stream around every pass of every execute while enabled).
  * dsp_dct_pass_stat blocks until the recorded executes finished, returns the statistics accumulated since the
  * last call for pass `i` and resets them.  Returns non-zero when `i` is out of range. */
@@ -190,6 +194,21 @@ typedef struct {
 } dsp_motion_params;
 typedef struct dsp_motion_s *dsp_motion;
 dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp);
+
+/* The same three stages on caller-owned plans (what dsp_motion_create does to its own): the slab-sharded full-volume
+ * transform (motion -b 0x0x0 over several GPUs) puts them on the plans either side of its exchange.
+ *   dsp_dct_fuse_pel_load   first pass (along the contiguous axis) reads 8-bit pels, or float pels * 255 (motion.c:618-624)
+ *   dsp_dct_fuse_motion_coeff  first pass of an inverse plan applies motion.c:617,644-751 as it loads (on a forward
+ *                           plan the same map rides in the last pass's store instead).  flat_w > 0: the
+ *                           plan is the temporal pass over a [D][slice of flattened h*w] array; the axis index is z and
+ *                           (y, x) = divmod(flat_base + column, flat_w).  d_counter (device, may be NULL) counts the
+ *                           non-zero coefficients after --quant.
+ *   dsp_dct_fuse_pel_store  last pass (along the contiguous axis) scales, clamps, rounds and stores 8-bit pels, or
+ *                           float pels / 255 (motion.c:757-776); an 8-bit store gives the plan a work buffer. */
+int dsp_dct_fuse_pel_load(dsp_dct_plan p, int float_pixels);
+int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsigned long long *d_counter, int flat_w,
+                              long long flat_base);
+int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp);
 /* host staging buffers (pels_out may equal pels_in); *coeffs_coded += non-zero coefficients after --quant */
 int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned long long *coeffs_coded);
 /* device-resident: same layout, device pointers, enqueued on `stream` */

@@ -116,3 +116,70 @@ def test_scan_shard_ranges_cover():
         for world in (1, 2, 3, 8):
             r = [shard_range(n, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _pel_diff_ok(got, want, pel):
+    """8-bit pels: identical except where the reference's own unrounded value sits on a rounding tie"""
+    diff = got.astype(np.int64) != want.astype(np.int64)
+    if diff.any():
+        assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
+        frac = np.abs(pel.astype(np.float64))
+        assert (np.abs(frac - np.floor(frac) - 0.5)[diff] < 2e-3).all()
+    return float(diff.mean())
+
+
+def _motion_worker(rank, world, port, dims, filt, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dspfun_b200.dist3d import Dist3D, motion_params
+        from tests.emu import emu
+        D, H, W = dims
+        vol = np.random.default_rng(21).integers(16, 236, dims).astype(np.uint8)
+        kw = dict(filt)
+        kw["preserve_dc"] = {None: 0, "dc": 1, "grey": 2}[kw.get("preserve_dc")]
+        d3 = Dist3D(D, H, W, prec="f", lib=emu.load(), motion=motion_params(dims, **kw))
+        Dl = D // world
+        out = d3.process(torch.from_numpy(vol[rank * Dl:(rank + 1) * Dl].copy()))
+        d3.destroy()
+        q.put((rank, out.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("filt", [dict(), dict(damp=0.0, bandpass=((0, 0, 0), (4, 6, 8))),
+                                  dict(boost=1.5, bandpass=((1, 2, 2), (6, 10, 12)), preserve_dc="dc"), dict(quant=0.02)])
+def test_motion_volume_u8_world2(filt):
+    """motion -b 0x0x0 over two ranks: 8-bit pels in, fused pel load / coefficient stages (flat coordinates on the
+    temporal pass) / pel store, 8-bit pels out == the restated reference block loop on the whole volume"""
+    from oracle import pipelines as op
+    dims = (8, 12, 16)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_motion_worker, args=(r, 2, port, dims, filt, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.concatenate([r[1] for r in res])
+    vol = np.random.default_rng(21).integers(16, 236, dims).astype(np.uint8)
+    want, _, pel = op.motion_block(vol, dims, **filt)
+    _pel_diff_ok(got, want, pel)
+    if not filt:
+        assert np.array_equal(got, vol)          # no filter: the round trip reproduces the 8-bit source
+
+
+def test_motion_volume_single_rank_matches_session():
+    from dspfun_b200.dist3d import Dist3D, motion_params
+    from oracle import pipelines as op
+    from tests.emu import emu
+    dims = (4, 10, 12)
+    vol = np.random.default_rng(22).integers(16, 236, dims).astype(np.uint8)
+    d3 = Dist3D(*dims, prec="f", lib=emu.load(), motion=motion_params(dims, damp=0.25, bandpass=((0, 1, 1), (4, 8, 9))))
+    out = d3.process(torch.from_numpy(vol.copy())).numpy()
+    d3.destroy()
+    want, _, pel = op.motion_block(vol, dims, damp=0.25, bandpass=((0, 1, 1), (4, 8, 9)))
+    _pel_diff_ok(out, want, pel)
