@@ -699,7 +699,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 // the next chunk's input have to sit in it together.  DSP_DCT_L2_CHUNK_MB tunes it, 0 turns the schedule off.
 static size_t l2_chunk_bytes() {
 	const char *e = getenv("DSP_DCT_L2_CHUNK_MB");             // read per execute: the tests switch it at run time
-	const double mb = e ? atof(e) : 40.0;
+	const double mb = e ? atof(e) : 0.0;               // measured (profiles/r02_chunk_sweep.md): serial chunks lose to one launch per pass
 	return mb > 0 ? (size_t)(mb * 1048576.0) : 0;
 }
 
