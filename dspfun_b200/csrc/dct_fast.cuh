@@ -17,7 +17,17 @@
 
 namespace dsp {
 
-struct FastDesc {
+template <class T> DSP_DEV void tw_powers(const C2<T> *tw, int idx, C2<T> *w);
+
+// Twiddle sources of the radix-16 passes.  The default reads the global tables through L1; the ring row kernel
+// (dct_ring.cuh) overrides them with tables it keeps in shared memory.
+template <class D> struct TwGlobal {
+	template <class T> DSP_DEVM void tw_mid(int i, int twsh, C2<T> *w) const { tw_powers<T>((const C2<T> *)static_cast<const D *>(this)->tw, i << twsh, w); }
+	template <class T> DSP_DEVM void tw_outer(int i, C2<T> *w) const { tw_powers<T>((const C2<T> *)static_cast<const D *>(this)->tw, i, w); }
+	template <class T> DSP_DEVM C2<T> om_at(int i) const { return ldg_c2((const C2<T> *)static_cast<const D *>(this)->om + i); }
+};
+
+struct FastDesc : TwGlobal<FastDesc> {
 	int n, M;                    // length, n/16
 	int r0;                      // contiguous radix (first DIT pass / last DIF pass); 1 = none
 	int nmid;                    // radix-16 middle passes between the contiguous and the outer pass
@@ -41,7 +51,7 @@ struct FastDesc {
 // The same description with the length fixed at compile time (float padding): every smem offset, loop bound and
 // division of the passes folds to an immediate.  Kernels are instantiated for the common lengths; the runtime
 // FastDesc serves the rest.
-template <int LG> struct FastFixed {
+template <int LG> struct FastFixedBase {
 	const void *tw, *om;
 	const uint16_t *sig;
 	enum { kFixed = 1, kN = 1 << LG };
@@ -55,10 +65,12 @@ template <int LG> struct FastFixed {
 	DSP_HDM constexpr int R0() const { return 1 << kL0; }
 	DSP_HDM constexpr int NMID() const { return kK; }
 	static constexpr int kNpad0 = (1 << LG) - 1 + (((1 << LG) - 1) >> 4) + (((1 << LG) - 1) >> 8) + (((1 << LG) - 1) >> 12) + 1;
-	DSP_HDM constexpr int NPAD() const { return kNpad0 + ((17 - kNpad0 % 16) % 16); }   // == 1 (mod 16), as the planner pads
+	static constexpr int kNPAD = kNpad0 + ((17 - kNpad0 % 16) % 16);                    // == 1 (mod 16), as the planner pads
+	DSP_HDM constexpr int NPAD() const { return kNPAD; }
 	DSP_HDM constexpr int PO(int q, int j) const { return padc(j * ((1 << kL0) << (4 * q))); }
 	DSP_DEVM uint32_t divHalf(uint32_t u) const { return u / (uint32_t)((1 << (LG - 4)) / 2 + 1); }
 };
+template <int LG> struct FastFixed : FastFixedBase<LG>, TwGlobal<FastFixed<LG>> {};
 
 // ------------------------------------------------------------------------------------------------ radix 32
 template <class T> struct Dft<T, 32> {
@@ -145,13 +157,12 @@ DSP_DEV void mid_pass(C2<T> *s, int nseq, const F &f, int q, int tid, int nthr) 
 	const int lnb = ilog2(f.N()) - 4;                           // log2 (butterflies per sequence)
 	const int total = nseq << lnb;
 	const int twsh = ilog2(f.N()) - lsh - 4;                    // log2 (n / L)
-	const C2<T> *tw = (const C2<T> *)f.tw;
 	for (int g = tid; g < total; g += nthr) {
 		const int seq = g >> lnb, b = g & ((1 << lnb) - 1);
 		const int blk = b >> lsh, i = b & ((1 << lsh) - 1);
 		C2<T> *p = s + seq * f.NPAD() + Pad<T>::of((blk << (lsh + 4)) + i);
 		C2<T> v[16], w[16];
-		if (i != 0) tw_powers<T>(tw, i << twsh, w);
+		if (i != 0) f.template tw_mid<T>(i, twsh, w);
 #pragma unroll
 		for (int j = 0; j < 16; j++) v[j] = p[f.PO(q, j)];
 		if (DIT && i != 0) {
@@ -199,6 +210,7 @@ template <class T, class F> struct SmemBf {
 		DSP_DEVM void put(int j, C2<T> v) const { p[f->PO(f->NMID(), j)] = v; }
 	};
 	DSP_DEVM Row row(int i) const { return Row{base + Pad<T>::of(i), f}; }
+	DSP_DEVM Row rowb(int i) const { return row(i); }       // second butterfly of a pair (register-staged storage tells them apart)
 };
 // GlobBf: row (j M + i) of a [16 M][...] global scratch, one complex (= one column pair) per row
 template <class T> struct GlobBf {
@@ -211,6 +223,7 @@ template <class T> struct GlobBf {
 		DSP_DEVM void put(int j, C2<T> v) const { p[j * js] = v; }
 	};
 	DSP_DEVM Row row(int i) const { return Row{base + (long long)i * rs, (long long)M * rs}; }
+	DSP_DEVM Row rowb(int i) const { return row(i); }
 };
 
 // ------------------------------------------------------------------------------------------------ DCT-II outer pass
@@ -225,7 +238,6 @@ DSP_DEV void dct2_pair(C2<T> w, int k, int n, C2<T> z, C2<T> y, bool self, Sink 
 template <class T, class Bf, class Sink, class F>
 DSP_DEV void dct2_outer_unit(const Bf &bf, const F &f, int i, Sink &sink) {
 	const int n = f.N(), M = f.Mq();
-	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
 		const typename Bf::Row p = bf.row(0);
@@ -238,7 +250,7 @@ DSP_DEV void dct2_outer_unit(const Bf &bf, const F &f, int i, Sink &sink) {
 		dct2_pair<T>(OmConst<T>::e(8), 8 * M, n, a[8], a[8], true, sink);
 		return;
 	}
-	tw_powers<T>(tw, i, w);
+	f.template tw_outer<T>(i, w);
 	if (2 * i == M) {
 		const typename Bf::Row p = bf.row(i);
 #pragma unroll
@@ -250,7 +262,7 @@ DSP_DEV void dct2_outer_unit(const Bf &bf, const F &f, int i, Sink &sink) {
 		for (int m = 0; m < 8; m++) dct2_pair<T>(OmConst<T>::h(m), i + M * m, n, a[m], a[15 - m], false, sink);
 		return;
 	}
-	const C2<T> wi = ldg_c2(om + i);
+	const C2<T> wi = f.template om_at<T>(i);
 	C2<T> b[16];
 	{
 		const typename Bf::Row p = bf.row(i);
@@ -258,7 +270,7 @@ DSP_DEV void dct2_outer_unit(const Bf &bf, const F &f, int i, Sink &sink) {
 		for (int j = 0; j < 16; j++) a[j] = p.get(j);
 	}
 	{
-		const typename Bf::Row p = bf.row(M - i);
+		const typename Bf::Row p = bf.rowb(M - i);
 #pragma unroll
 		for (int j = 0; j < 16; j++) b[j] = p.get(j);
 	}
@@ -286,7 +298,6 @@ DSP_DEV void dct3_pair(C2<T> w, C2<T> xk, C2<T> xn, C2<T> &wk, C2<T> &wn) {
 template <class T, class Bf, class Source, class F>
 DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
 	const int M = f.Mq();
-	const C2<T> *tw = (const C2<T> *)f.tw, *om = (const C2<T> *)f.om;
 	C2<T> a[16], w[16];
 	if (i == 0) {
 		// k = M j; partner of j is 16-j; j = 0 and j = 8 are their own partners
@@ -310,7 +321,7 @@ DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
 #pragma unroll
 		for (int j = 0; j < 8; j++) dct3_pair<T>(OmConst<T>::h(j), x[j], x[15 - j], a[j], a[15 - j]);
 		Dft<T, 16>::run(a);
-		tw_powers<T>(tw, i, w);
+		f.template tw_outer<T>(i, w);
 #pragma unroll
 		for (int j = 1; j < 16; j++) a[j] = cmul(a[j], w[j]);
 		const typename Bf::Row p = bf.row(i);
@@ -318,7 +329,7 @@ DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
 		for (int j = 0; j < 16; j++) p.put(j, a[j]);
 		return;
 	}
-	const C2<T> wi = ldg_c2(om + i);
+	const C2<T> wi = f.template om_at<T>(i);
 	C2<T> b[16];
 	{
 		C2<T> xa[16], xb[16];
@@ -334,7 +345,7 @@ DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
 	}
 	Dft<T, 16>::run(a);
 	Dft<T, 16>::run(b);
-	tw_powers<T>(tw, i, w);
+	f.template tw_outer<T>(i, w);
 #pragma unroll
 	for (int j = 1; j < 16; j++) { a[j] = cmul(a[j], w[j]); b[j] = cmul_conj(b[j], w[j]); }
 	{
@@ -343,7 +354,7 @@ DSP_DEV void dct3_outer_unit(const Bf &bf, const F &f, int i, Source &src) {
 		for (int j = 0; j < 16; j++) p.put(j, a[j]);
 	}
 	{
-		const typename Bf::Row p = bf.row(M - i);
+		const typename Bf::Row p = bf.rowb(M - i);
 #pragma unroll
 		for (int j = 0; j < 16; j++) p.put(j, b[j]);
 	}

@@ -7,6 +7,7 @@
 #include "../../include/dsp_dct.h"
 #include "dsp_kernels.h"
 #include "dct_split.cuh"
+#include "dct_ring.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -579,7 +580,18 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		const bool spec = pp.fast && f32 && !pp.fused && (a.d == 1 || a.d == 3) && a.simple && a.vec_in && a.vec_out &&
 		                  nn >= 256 && nn <= 8192 && (a.lines_per_cta % 2) == 0 && (a.nlines % 2) == 0 &&
 		                  !getenv("DSP_DCT_NO_FIXED") && !getenv("DSP_DCT_NO_PLANAR");
-		if (spec && a.d == 1) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
+		// planar lines, n = 256 .. 8192: the persistent TMA-fed ring kernel (dct_ring.cuh); DSP_DCT_NO_RING=1 keeps the
+		// one-shot kernel (A/B measurements)
+		static const bool no_ring = getenv("DSP_DCT_NO_RING") != nullptr;
+		if (spec && a.d == 1 && !no_ring && ring_supports(nn) && ((a.ls_in | a.ls_out) % 4) == 0) {
+			RingArgs r;
+			r.in = (const float *)in; r.out = (float *)out;
+			r.ls_in = a.ls_in; r.ls_out = a.ls_out; r.nlines = a.nlines;
+			r.lscale = (float)(pp.lop.kind == OP_SCALE ? pp.lop.p[0] : 1.0); r.sscale = (float)(pp.sop.kind == OP_SCALE ? pp.sop.p[0] : 1.0);
+			r.tw = pp.ff.tw; r.om = pp.ff.om; r.sig = pp.ff.sig;
+			DSP_TRACE("row pass: ring kernel n=%d lines=%d", nn, a.nlines);
+			ok = launch_row_ring_f32(r, nn, a.kind == DSP_KIND_REDFT10, st, g_err);
+		} else if (spec && a.d == 1) ok = launch_row_fast_f32p(a, pp.ff, false, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 		else if (spec) ok = launch_row_fast_f32i3(a, pp.ff, false, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 		else if (pp.fast && f32) ok = launch_row_fast_f32(a, pp.ff, pp.fused, pp.lop, pp.sop, grid, pp.block, pp.smem, st, g_err);
 #if DSP_FAST_F64

@@ -29,6 +29,10 @@ DSP_DECL_LAUNCH(launch_col_fast_f32, ColArgs)
 DSP_DECL_LAUNCH(launch_col_fast_f64, ColArgs)
 #undef DSP_DECL_LAUNCH
 
+struct RingArgs;
+bool ring_supports(int n);
+bool launch_row_ring_f32(const RingArgs &a, int n, bool fwd, rt_stream st, std::string &err);   // dct_ring.cuh
+
 bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int row_bytes, rt_stream st, std::string &err);
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
 bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,

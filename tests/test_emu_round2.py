@@ -80,3 +80,46 @@ def test_fused_spec_ranges_on_the_wide_path(lib, prec, shape, rng_):
     assert np.all(np.isfinite(s1))
     assert od.rel_l2(s1, s0) < cases.OK[prec] * 4, od.rel_l2(s1, s0)
     assert np.allclose(dc1, dc0, rtol=1e-5 if prec == "f" else 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- ring row kernel
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(2, 256), (70, 256), (6, 512), (36, 512), (4, 1024), (22, 1024), (10, 2048), (6, 4096), (2, 8192), (10, 8192)])
+def test_ring_row_kernel_planar(lib, kind, shape):
+    """dct_ring.cuh: planar power-of-two lines through the persistent bulk-copy-fed kernel (emulated: memcpy + the same
+    index arithmetic); line counts that fill whole buffers, leave a ragged last buffer, and spread over several CTAs"""
+    h, w = shape
+    cases.check_interleaved_2d(lib, "f", h, w, 1, kind)
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_ring_row_kernel_strided_lines_and_scale(lib, kind):
+    """lines at a stride larger than n (embedded boxes: one bulk copy per line) and the fused load / store scale"""
+    n, lines, dist = 1024, 12, 1024 + 64
+    rng = np.random.default_rng(31)
+    buf = rng.random(lines * dist).astype(np.float32)
+    ref = buf.astype(np.float64).copy()
+    ok = cases.ORK[kind]
+    for b in range(lines):
+        ref[b * dist:b * dist + n] = od.dctn_fast(buf[b * dist:b * dist + n].astype(np.float64) * 0.5, [ok]) * 3.0
+    p = Plan("f", [n], [kind], lines, None, 1, dist, None, 1, dist, lib=lib).fuse_scale(0.5, 3.0)
+    y = p.execute_host(buf.copy())
+    p.destroy()
+    sel = np.zeros(lines * dist, bool)
+    for b in range(lines):
+        sel[b * dist:b * dist + n] = True
+    assert od.rel_l2(y[sel], ref[sel]) < 1e-5
+    assert np.array_equal(y[~sel], buf[~sel])
+
+
+def test_ring_row_kernel_matches_one_shot_kernel(lib):
+    """same lines through the ring kernel and the one-shot row kernel (DSP_DCT_NO_RING is read once per process, so the
+    comparison goes through a shape the ring kernel does not take: an odd line count)"""
+    rng = np.random.default_rng(32)
+    x = rng.random((5, 2048)).astype(np.float32)
+    p = Plan("f", [2048], [REDFT10], 4, None, 1, 2048, None, 1, 2048, lib=lib)       # even: ring
+    q = Plan("f", [2048], [REDFT10], 5, None, 1, 2048, None, 1, 2048, lib=lib)       # odd: one-shot kernel
+    a = p.execute_host(x[:4].copy().reshape(-1)).reshape(4, 2048)
+    b = q.execute_host(x.copy().reshape(-1)).reshape(5, 2048)
+    p.destroy(); q.destroy()
+    assert od.rel_l2(a, b[:4]) < 2e-7

@@ -1,0 +1,121 @@
+"""GPU suite (-m gpu), round-2 additions: the persistent bulk-copy-fed row kernel (dct_ring.cuh), the chunked
+(L2-resident) schedule, and the fused stages on the wide (column-pass) path -- same cases as tests/test_emu_round2.py,
+through the product library's C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from dspfun_b200 import REDFT01, REDFT10, Plan, capi
+from dspfun_b200 import spec as gspec
+from oracle import dct as od
+from oracle import pipelines as pl
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load()
+
+
+@pytest.fixture
+def chunk_env():
+    old = os.environ.get("DSP_DCT_L2_CHUNK_MB")
+
+    def set_mb(v):
+        os.environ["DSP_DCT_L2_CHUNK_MB"] = str(v)
+    yield set_mb
+    if old is None:
+        os.environ.pop("DSP_DCT_L2_CHUNK_MB", None)
+    else:
+        os.environ["DSP_DCT_L2_CHUNK_MB"] = old
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(2, 256), (70, 256), (6, 512), (36, 512), (4, 1024), (22, 1024), (10, 2048), (6, 4096),
+                                   (2, 8192), (10, 8192), (3000, 256), (2048, 1024), (1000, 4096), (700, 8192)])
+def test_ring_row_kernel_planar(lib, kind, shape):
+    """whole buffers, ragged last buffers, fewer iterations than SMs, many iterations per CTA (ring wrap-around, both
+    mbarrier phases)"""
+    h, w = shape
+    cases.check_interleaved_2d(lib, "f", h, w, 1, kind)
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+def test_ring_row_kernel_strided_lines_and_scale(lib, kind):
+    n, lines, dist = 1024, 1200, 1024 + 64
+    rng = np.random.default_rng(31)
+    buf = rng.random(lines * dist).astype(np.float32)
+    ref = buf.astype(np.float64).copy()
+    ok = cases.ORK[kind]
+    for b in range(lines):
+        ref[b * dist:b * dist + n] = od.dctn_fast(buf[b * dist:b * dist + n].astype(np.float64) * 0.5, [ok]) * 3.0
+    p = Plan("f", [n], [kind], lines, None, 1, dist, None, 1, dist, lib=lib).fuse_scale(0.5, 3.0)
+    y = p.execute_host(buf.copy())
+    p.destroy()
+    sel = np.zeros(lines * dist, bool)
+    for b in range(lines):
+        sel[b * dist:b * dist + n] = True
+    assert od.rel_l2(y[sel], ref[sel]) < 1e-5
+    assert np.array_equal(y[~sel], buf[~sel])
+
+
+def test_ring_row_kernel_repeatable(lib):
+    """the ring hands buffers between two thread groups: the same input twice must give the same bits"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((4096, 8192), device="cuda", dtype=torch.float32, generator=g)
+    p = Plan("f", [8192], [REDFT10], 4096, None, 1, 8192, None, 1, 8192, lib=lib)
+    a, b = x.clone(), x.clone()
+    p.execute_dev(a.data_ptr(), a.data_ptr(), None)
+    p.execute_dev(b.data_ptr(), b.data_ptr(), None)
+    torch.cuda.synchronize()
+    p.destroy()
+    assert torch.equal(a, b)
+    ref = od.dctn_fast(x[1234].cpu().numpy().astype(np.float64), [od.REDFT10])
+    assert od.rel_l2(a[1234].cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+@pytest.mark.parametrize("mb", [0, 1, 4])
+def test_chunked_batches_match_oracle(lib, chunk_env, prec, mb):
+    chunk_env(mb)
+    cases.check_batched_images(lib, prec, 7, 128, 256, 3)
+    cases.check_batched_images(lib, prec, 16, 256, 256, 1)
+
+
+def test_chunked_frames_of_a_rank3_plan(lib, chunk_env):
+    dims, embed = (12, 64, 96), (12, 80, 112)
+    for kind in (REDFT10, REDFT01):
+        chunk_env(0)
+        a = cases.run_planar_3d_embed(lib, "f", dims, embed, kind)
+        chunk_env(0.1)
+        b = cases.run_planar_3d_embed(lib, "f", dims, embed, kind)
+        assert np.array_equal(a, b)
+        cases.check_planar_3d_embed(lib, "f", dims, embed, kind)
+
+
+def test_chunked_motion_keeps_fused_coordinates(lib, chunk_env):
+    chunk_env(0.002)
+    cases.check_motion(lib, (8, 16, 16), boost=1.5, bandpass=((1, 2, 2), (6, 12, 12)), preserve_dc="dc")
+    cases.check_motion(lib, (8, 16, 16), scaled=(4, 8, 12))
+
+
+@pytest.mark.parametrize("prec,shape", [("d", (2, 8192, 3)), ("f", (3, 8192, 4))])
+def test_fused_scan_on_the_wide_path(lib, prec, shape):
+    cases.check_scan(lib, prec, *shape, order="horizontal", step=shape[0] * shape[1] // 3 + 1)
+
+
+@pytest.mark.parametrize("prec,shape", [("d", (2, 8192, 3)), ("f", (2, 16384, 2))])
+@pytest.mark.parametrize("rng_", ["dc", "dcs"])
+def test_fused_spec_ranges_on_the_wide_path(lib, prec, shape, rng_):
+    rs = np.random.default_rng(11)
+    px = (rs.integers(0, 256, shape) / 255.0).astype(cases.DT[prec])
+    params = ("log", "shift", "reference", rng_)
+    s1, dc1 = gspec.spec(px, None, lib=lib, scale="log", sign="shift", range_=rng_, gain="reference")
+    s0, dc0 = pl.spec_forward(px, params=params, custom_gain=1.0, intermediate=cases.INTERMEDIATE[prec])
+    assert np.all(np.isfinite(s1))
+    assert od.rel_l2(s1, s0) < cases.OK[prec] * 4, od.rel_l2(s1, s0)
+    assert np.allclose(dc1, dc0, rtol=1e-5 if prec == "f" else 1e-12)
