@@ -283,6 +283,7 @@ template <int LG> struct RingSmem {
 	static constexpr int kBufElems = RingGeom<LG>::NSEQ * F::kNPAD;
 	static constexpr size_t kTablesBytes = ((size_t)F::kTableElems * sizeof(C2<float>) + 127) / 128 * 128;
 	static constexpr size_t kBufBytes = ((size_t)kBufElems * sizeof(C2<float>) + 127) / 128 * 128;
+	static constexpr int kBufStride = (int)(kBufBytes / sizeof(C2<float>));     // buffers start 128-byte aligned (bulk copies need 16)
 	static constexpr size_t kTotal = kTablesBytes + kRingBufs * kBufBytes + 64;
 };
 
@@ -345,13 +346,13 @@ DSP_DEV void ring_cta(const RingArgs &a, unsigned char *smem, int cta, int ncta,
 	if (tid == 0) {
 		for (int it = 0; it < kRingBufs && it < iters; it++) {
 			const long long l0 = ring_line0<LG>(cta, ncta, it);
-			ring_issue<LG>(a, (float *)(bufs + (size_t)it * S::kBufElems), l0, ring_pairs<LG>(a, l0), full + it);
+			ring_issue<LG>(a, (float *)(bufs + (size_t)it * S::kBufStride), l0, ring_pairs<LG>(a, l0), full + it);
 		}
 	}
 	const int group = tid / kRingGroup, gt = tid - group * kRingGroup;
 	for (int it = group; it < iters; it += kRingGroups) {
 		const int b = it % kRingBufs;
-		C2<float> *buf = bufs + (size_t)b * S::kBufElems;
+		C2<float> *buf = bufs + (size_t)b * S::kBufStride;
 		const long long l0 = ring_line0<LG>(cta, ncta, it);
 		const int np = ring_pairs<LG>(a, l0);
 		mbar_wait(full + b, (uint32_t)((it / kRingBufs) & 1));
