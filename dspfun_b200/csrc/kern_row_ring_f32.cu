@@ -18,7 +18,7 @@ static bool ring_launch_t(const RingArgs &a, int sms, rt_stream st, std::string 
 		if (!rt_ok(cudaFuncSetAttribute(k_row_ring<LG, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err, "smem attribute")) return false;
 		attr_dev |= 1ull << dev;
 	}
-	k_row_ring<LG, FWD><<<grid, kRingGroups * kRingGroup, smem, st>>>(a);
+	k_row_ring<LG, FWD><<<grid, kRingGroups * kRingGroupThreads, smem, st>>>(a);
 	return rt_ok(cudaGetLastError(), err, "ring row kernel launch");
 #else
 	(void)st; (void)err;
