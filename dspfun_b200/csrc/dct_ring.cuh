@@ -24,10 +24,7 @@
 // table in the emulation.
 #pragma once
 #include "dct_fast.cuh"
-#if !DSP_GPU
-#include <string.h>
-#include <vector>
-#endif
+#include "dct_tma.cuh"
 
 namespace dsp {
 
@@ -42,39 +39,7 @@ static const int kRingGroups = 2;
 static const int kRingBufs = 3;
 static const int kRingPoints = 8192;     // complex points per buffer
 
-// ------------------------------------------------------------------------------------------------ PTX wrappers
 #if DSP_GPU
-DSP_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-DSP_DEV void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-DSP_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-DSP_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-DSP_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
-	uint32_t ok;
-	do {      // try_wait suspends the thread in hardware for a bounded time; no labels, so the block may be duplicated freely
-		asm volatile(
-		    "{\n"
-		    ".reg .pred p;\n"
-		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-		    "selp.u32 %0, 1, 0, p;\n"
-		    "}\n"
-		    : "=r"(ok)
-		    : "r"(smem_u32(bar)), "r"(parity)
-		    : "memory");
-	} while (!ok);
-}
-// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned); completes on `bar`
-DSP_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
-// orders this thread's (and, after a barrier, its group's) generic-proxy accesses to shared memory before later
-// async-proxy (bulk copy) writes to the same locations
-DSP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DSP_DEV void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kRingGroupThreads) : "memory"); }
 #define RING_SYNC(g) group_sync(g)
 #else

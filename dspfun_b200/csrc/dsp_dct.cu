@@ -8,6 +8,7 @@
 #include "dsp_kernels.h"
 #include "dct_split.cuh"
 #include "dct_ring.cuh"
+#include "dct_colring.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -259,6 +260,9 @@ struct PassPlan {
 	// chunk, so the intermediate of a chunk is still in L2 when the next pass reads it
 	int ch_slot;                             // coordinate slot of that level (-1: the pass has no outer level)
 	long long ch_cnt, ch_is, ch_os, ch_inner;// its count and strides (elements), product of the levels below it
+	// ring sub-pass kernels (dct_colring.cuh): tensor maps per (input, output, scratch) pointer triple
+	struct RingMaps { const void *in; void *out, *scratch; ColRingArgs args; };
+	std::vector<RingMaps> ring_maps;
 	bool seg_saved;                          // strides below hold the plan's own values while an override is active
 	long long seg_os[4], seg_ax_os;
 };
@@ -655,7 +659,29 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					ok = launch_l2_prefetch((const char *)sa.in + (size_t)nc0 * P->es, sa.ax_is * P->es, c.f.n, ncols * P->es, st, g_err);
 				}
 				const bool dit_inv = !fwd && !pp.sp_force_inv;
-				if (ok && dit_inv) {
+				static const bool no_cring = getenv("DSP_DCT_NO_COLRING") != nullptr;
+				if (ok && fwd && f32 && !pp.fused && !no_cring && colring_supports(c.f.n) && (c.ncols % 32) == 0 && (sa.pcols % 32) == 0 &&
+				    (pp.sp_P % 32) == 0 && (c.ax_is % 4) == 0 && (c.ax_os % 4) == 0) {
+					// persistent TMA-fed sub-passes; the tensor maps depend on the pointers only and are cached in the plan
+					PassPlan::RingMaps *rm = nullptr;
+					for (auto &e : pp.ring_maps) if (e.in == sa.in && e.out == sa.out && e.scratch == sa.scratch) rm = &e;
+					if (!rm) {
+						PassPlan::RingMaps e;
+						memset(&e.args, 0, sizeof(e.args));
+						e.in = sa.in; e.out = sa.out; e.scratch = sa.scratch;
+						ok = colring_encode(e.args, c.f.n, (const float *)sa.in, c.ax_is, (float *)sa.out, c.ax_os, c.ncols, (float *)sa.scratch, pp.sp_P, g_err);
+						e.args.twM = pp.ffM.tw; e.args.sigM = pp.ffM.sig;
+						e.args.twN = pp.ff.tw; e.args.omN = pp.ff.om; e.args.sigN = pp.ff.sig;
+						if (ok) { if (pp.ring_maps.size() >= 64) pp.ring_maps.clear(); pp.ring_maps.push_back(e); rm = &pp.ring_maps.back(); }
+					}
+					DSP_TRACE("split pass: ring sub-pass kernels n=%d panel cols %d+%d", c.f.n, sa.pcol0, sa.pcols);
+					if (ok) {
+						ColRingArgs ra = rm->args;
+						ra.col0 = sa.pcol0; ra.ntiles = sa.pcols / 32;
+						ra.lscale = (float)(pp.lop.kind == OP_SCALE ? pp.lop.p[0] : 1.0); ra.sscale = (float)(pp.sop.kind == OP_SCALE ? pp.sop.p[0] : 1.0);
+						ok = launch_col_ring_f32(ra, c.f.n, true, st, g_err) && launch_col_ring_f32(ra, c.f.n, false, st, g_err);
+					}
+				} else if (ok && dit_inv) {
 					sa.tci = 16; sa.ntilesi = (sa.pcols + 15) / 16;
 					ok = launch_split_inv_fft_f32(sa, pp.ffM, pp.ff, pp.lop, sa.ntilesi * 9, pp.sp_smem_inv, st, g_err) &&
 					     launch_split_inv_outer_f32(sa, pp.ff, pp.sop, sa.ngroups * M, st, g_err);

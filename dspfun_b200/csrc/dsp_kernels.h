@@ -33,6 +33,12 @@ struct RingArgs;
 bool ring_supports(int n);
 bool launch_row_ring_f32(const RingArgs &a, int n, bool fwd, rt_stream st, std::string &err);   // dct_ring.cuh
 
+struct ColRingArgs;
+bool colring_supports(int n);
+bool colring_encode(ColRingArgs &a, int n, const float *in, long long ax_is, float *out, long long ax_os, int ncols, float *scratch, int P,
+                    std::string &err);
+bool launch_col_ring_f32(const ColRingArgs &a, int n, bool sub_a, rt_stream st, std::string &err);   // dct_colring.cuh
+
 bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int row_bytes, rt_stream st, std::string &err);
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
 bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,

@@ -123,3 +123,34 @@ def test_ring_row_kernel_matches_one_shot_kernel(lib):
     b = q.execute_host(x.copy().reshape(-1)).reshape(5, 2048)
     p.destroy(); q.destroy()
     assert od.rel_l2(a, b[:4]) < 2e-7
+
+
+# ---------------------------------------------------------------------------------------------- ring column sub-passes
+@pytest.fixture
+def small_panels():
+    old = os.environ.get("DSP_DCT_SPLIT_PANEL_MB")
+    os.environ["DSP_DCT_SPLIT_PANEL_MB"] = "1"          # 64-column panels at n = 4096 / 8192: several panels per plane
+    yield
+    if old is None:
+        os.environ.pop("DSP_DCT_SPLIT_PANEL_MB", None)
+    else:
+        os.environ["DSP_DCT_SPLIT_PANEL_MB"] = old
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(4096, 64, 1), (4096, 160, 1), (8192, 96, 1), (8192, 32, 3), (4096, 32, 2)])
+def test_ring_column_subpasses(lib, small_panels, kind, shape):
+    """dct_colring.cuh: long power-of-two columns through the tensor-copy-fed sub-pass kernels (emulated boxes):
+    several tiles per panel, several panels, interleaved channels as plain columns, a last panel narrower than the rest"""
+    cases.check_interleaved_2d(lib, "f", *shape, kind)
+
+
+def test_ring_column_subpasses_batched_and_scaled(lib, small_panels):
+    """outer (batch) offsets enter through the tensor maps' base pointers; fused store scale"""
+    rng = np.random.default_rng(41)
+    x = rng.random((2, 4096, 64)).astype(np.float32)
+    p = Plan("f", [4096, 64], [REDFT10, REDFT10], 1, None, 1, 0, None, 1, 0, 2, 4096 * 64, 4096 * 64, lib=lib).fuse_scale(1.0, 0.25)
+    y = p.execute_host(x.copy())
+    p.destroy()
+    ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 2, axes=(1, 2)) * 0.25
+    assert od.rel_l2(y, ref) < 1e-5

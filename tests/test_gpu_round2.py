@@ -119,3 +119,38 @@ def test_fused_spec_ranges_on_the_wide_path(lib, prec, shape, rng_):
     assert np.all(np.isfinite(s1))
     assert od.rel_l2(s1, s0) < cases.OK[prec] * 4, od.rel_l2(s1, s0)
     assert np.allclose(dc1, dc0, rtol=1e-5 if prec == "f" else 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- ring column sub-passes
+@pytest.fixture
+def small_panels():
+    old = os.environ.get("DSP_DCT_SPLIT_PANEL_MB")
+    os.environ["DSP_DCT_SPLIT_PANEL_MB"] = "1"
+    yield
+    if old is None:
+        os.environ.pop("DSP_DCT_SPLIT_PANEL_MB", None)
+    else:
+        os.environ["DSP_DCT_SPLIT_PANEL_MB"] = old
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(4096, 64, 1), (4096, 160, 1), (8192, 96, 1), (8192, 32, 3), (4096, 32, 2)])
+def test_ring_column_subpasses_small_panels(lib, small_panels, kind, shape):
+    cases.check_interleaved_2d(lib, "f", *shape, kind)
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape", [(4096, 2048, 1), (8192, 1024, 1), (8192, 512, 3), (4096, 4096, 1)])
+def test_ring_column_subpasses(lib, kind, shape):
+    """default 32 MB panels: hundreds of iterations per CTA (ring wrap-around, deferred refills after tensor stores)"""
+    cases.check_interleaved_2d(lib, "f", *shape, kind)
+
+
+def test_ring_column_subpasses_batched_and_scaled(lib, small_panels):
+    rng = np.random.default_rng(41)
+    x = rng.random((2, 4096, 64)).astype(np.float32)
+    p = Plan("f", [4096, 64], [REDFT10, REDFT10], 1, None, 1, 0, None, 1, 0, 2, 4096 * 64, 4096 * 64, lib=lib).fuse_scale(1.0, 0.25)
+    y = p.execute_host(x.copy())
+    p.destroy()
+    ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 2, axes=(1, 2)) * 0.25
+    assert od.rel_l2(y, ref) < 1e-5
