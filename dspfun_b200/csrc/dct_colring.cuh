@@ -6,6 +6,11 @@
 // and shared memory moves by tensor copy (cp.async.bulk.tensor, UTMALDG / UTMASTG), through the same ring as the row
 // kernel (dct_ring.cuh): one CTA per SM, two thread groups, three 68 KB buffers, loads two iterations ahead.
 //
+// One launch walks all panels of the pass: A(0), A(1), B(0), A(2), B(1), ... -- B of a panel follows A of the next, so
+// that by the time an item of B(q) is loaded every CTA has long finished A(q).  That order is a dependency, not a
+// hope: every finished item bumps its panel's counter in global memory, and a load of B(q) (or of A(q + 3), which
+// reuses B(q)'s scratch panel) is issued only once the counter is full.
+//
 // DCT-II, per column panel (scratch = [16][M][P] floats, stays in L2):
 //   A  iteration = (sub-FFT j, 32-column tile).  Load: the image viewed as [n/32][32][cols]; sub-sequence j of the
 //      Makhoul-permuted column is the rows of phase 2j (ascending) followed by the rows of phase 31 - 2j (descending):
@@ -22,15 +27,20 @@
 
 namespace dsp {
 
+static const int kColRingScratch = 3;      // scratch panels in rotation: A(q+1) fills one while B(q) reads another
+static const int kColRingMaxPanels = 96;   // panels (outer index x column panel) one launch walks
+
 struct ColRingArgs {
-	TmaDesc in_map;       // A load : image   [n/32][32][cols]   box {32, 1, M/2}
-	TmaDesc sc_st_map;    // A store: scratch [16][M][P]         box {32, min(M, 256), 1}
-	TmaDesc sc_ld_map;    // B load : scratch [16][M][P]         box {32, 16, 16}
-	TmaDesc sc_ld1_map;   // B load : scratch, butterfly M/2     box {32, 1, 16}
-	TmaDesc out_map;      // B store: image   [16][M][cols]      box {32, 16, 16}
-	TmaDesc out1_map;     // B store: image, butterfly M/2       box {32, 1, 16}
-	int col0;             // first column of the panel (image maps; the scratch maps start at 0)
-	int ntiles;           // 32-column tiles in the panel
+	TmaDesc in_map;       // A load : image   [planes][n/32][32][cols]   box {32, 1, M/2, 1}
+	TmaDesc sc_st_map;    // A store: scratch [3][16][M][P]              box {32, min(M, 256), 1, 1}
+	TmaDesc sc_ld_map;    // B load : scratch                            box {32, 16, 16, 1}
+	TmaDesc sc_ld1_map;   // B load : scratch, butterfly M/2             box {32, 1, 16, 1}
+	TmaDesc out_map;      // B store: image   [planes][16][M][cols]      box {32, 16, 16, 1}
+	TmaDesc out1_map;     // B store: image, butterfly M/2               box {32, 1, 16, 1}
+	int nplanes, ppp;     // outer indices (planes / batch elements) and column panels per plane
+	int P, ncols;         // panel width (the last panel of a plane may be narrower); columns per plane
+	int reverse;          // walk the panels of a plane from the last to the first (inverse plans)
+	int *done;            // [2][nplanes * ppp] items finished per panel: sub-pass A | sub-pass B.  Zero before the launch.
 	float lscale, sscale;
 	const void *twM;      // C2<float>[M]      sub-FFT twiddles
 	const uint16_t *sigM; // [M]               sub-FFT slot table
@@ -163,20 +173,60 @@ DSP_DEV void colB_iter(const ColRingArgs &a, const RingFixed<LGM + 4> &fN, C2<fl
 	RING_SYNC(group);
 }
 
+// ------------------------------------------------------------------------------------------------ work list
+// Panel q = plane * ppp + column panel.  Segments in launch order: A(0); then A(q), B(q-1) for q = 1..Q-1; then B(Q-1).
+struct ColItem {
+	int sub_b;            // 0: sub-pass A, 1: sub-pass B
+	int q;                // panel
+	int local;            // item within the segment
+	int plane, col0, ntiles;
+};
+template <int LGM> struct ColWork {
+	typedef ColGeom<LGM> G;
+	DSP_DEVM static int panels(const ColRingArgs &a) { return a.nplanes * a.ppp; }
+	DSP_DEVM static int ntiles(const ColRingArgs &a, int q) {
+		int p = q % a.ppp;
+		if (a.reverse) p = a.ppp - 1 - p;
+		const int left = a.ncols - p * a.P;
+		return (left < a.P ? left : a.P) / 32;
+	}
+	DSP_DEVM static int seg_panel(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? Q - 1 : ((s & 1) ? (s + 1) / 2 : s / 2 - 1)); }
+	DSP_DEVM static int seg_is_b(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? 1 : ((s & 1) ? 0 : 1)); }
+	DSP_DEVM static int seg_items(const ColRingArgs &a, int s, int Q) { return ntiles(a, seg_panel(s, Q)) * (seg_is_b(s, Q) ? (int)G::NBLK : 16); }
+	// seg_start[s] = first global item of segment s (2Q + 1 entries, filled once per CTA)
+	DSP_DEVM static void decode(const ColRingArgs &a, const int *seg_start, int gi, int &cursor, ColItem &w) {
+		const int Q = panels(a);
+		while (gi >= seg_start[cursor + 1]) cursor++;
+		w.sub_b = seg_is_b(cursor, Q);
+		w.q = seg_panel(cursor, Q);
+		w.local = gi - seg_start[cursor];
+		w.plane = w.q / a.ppp;
+		int p = w.q % a.ppp;
+		if (a.reverse) p = a.ppp - 1 - p;
+		w.col0 = p * a.P;
+		w.ntiles = ntiles(a, w.q);
+	}
+};
+
 // ------------------------------------------------------------------------------------------------ CTA bodies
 template <int LGM> struct ColRingSmem {
 	typedef RingSmem<LGM + 4> S;                                        // same buffers as the row ring at n = 16 M
-	static constexpr size_t kTablesBytes = S::kTablesBytes, kBufBytes = S::kBufBytes, kTotal = S::kTotal;
+	typedef RingFixed<LGM> FM;
+	static constexpr size_t kBufBytes = S::kBufBytes;
 	static constexpr int kBufStride = S::kBufStride;
+	static constexpr size_t kTabNBytes = S::kTablesBytes;                                                // tables of the n-point outer pass
+	static constexpr size_t kTabMBytes = ((size_t)(4 * (1 << FM::kL0) + 8) * sizeof(C2<float>) + 127) / 128 * 128;   // sub-FFT: s_mid, s_sig
+	static constexpr size_t kSegBytes = ((size_t)(2 * kColRingMaxPanels + 2) * sizeof(int) + 127) / 128 * 128;
+	static constexpr size_t kTablesBytes = kTabNBytes + kTabMBytes + kSegBytes;
+	static constexpr size_t kTotal = kTablesBytes + kRingBufs * kBufBytes + 64;
 	static_assert((size_t)ColGeom<LGM>::NSEQ * ColGeom<LGM>::NPAD * sizeof(C2<float>) <= kBufBytes, "tile does not fit the ring buffer");
 	static_assert((size_t)(8192 + 16 * 16) * sizeof(C2<float>) <= kBufBytes, "outer-pass boxes do not fit the ring buffer");
+	static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 // tables of the M-point sub-FFT in shared memory (only the radix-16 pass's twiddles and the slot table are used)
 template <int LGM>
 DSP_DEV void colA_fill_tables(const ColRingArgs &a, C2<float> *tab, RingFixed<LGM> &f, int t0, int t1, int nthr) {
-	RingArgs ra;
-	ra.tw = a.twM; ra.om = nullptr; ra.sig = a.sigM;
 	typedef RingFixed<LGM> F;
 	const int R0 = 1 << F::kL0, M = 1 << LGM;
 	C2<float> *s_mid = tab;
@@ -193,140 +243,192 @@ DSP_DEV void colA_fill_tables(const ColRingArgs &a, C2<float> *tab, RingFixed<LG
 	f.s_out = nullptr; f.s_om = nullptr; f.s_mid = s_mid; f.s_sig = s_sig;
 }
 
-// iteration gi of sub-pass A: sub-FFT j = gi / ntiles, tile = gi % ntiles
+template <int LGM>
+DSP_DEV void col_fill_segments(const ColRingArgs &a, int *seg_start) {
+	const int Q = ColWork<LGM>::panels(a);
+	int acc = 0;
+	for (int s = 0; s < 2 * Q; s++) { seg_start[s] = acc; acc += ColWork<LGM>::seg_items(a, s, Q); }
+	seg_start[2 * Q] = acc;
+}
+
+// ---- loads / stores of an item
 template <int LGM, class Bar>
-DSP_DEV void colA_load(const ColRingArgs &a, C2<float> *buf, int gi, Bar *bar) {
+DSP_DEV void col_load(const ColRingArgs &a, const ColItem &w, C2<float> *buf, Bar *bar) {
 	typedef ColGeom<LGM> G;
-	const int j = gi / a.ntiles, tile = gi - j * a.ntiles;
-	const int c = a.col0 + 32 * tile;
-	tma_load3(buf, &a.in_map, c, 2 * j, 0, bar);
-	tma_load3(buf + (G::M / 2) * 16, &a.in_map, c, 31 - 2 * j, 0, bar);
+	const int sc = w.q % kColRingScratch;
+	if (!w.sub_b) {                          // sub-FFT j of a tile: rows of phase 2j ascending, rows of phase 31 - 2j descending
+		const int j = w.local / w.ntiles, tile = w.local - j * w.ntiles;
+		const int c = w.col0 + 32 * tile;
+		tma_load4(buf, &a.in_map, c, 2 * j, 0, w.plane, bar);
+		tma_load4(buf + (G::M / 2) * 16, &a.in_map, c, 31 - 2 * j, 0, w.plane, bar);
+	} else {                                 // block of 16 butterflies i and the mirror block M - i (+ butterfly M/2 with block 0)
+		const int blk = w.local / w.ntiles, tile = w.local - blk * w.ntiles;
+		tma_load4(buf, &a.sc_ld_map, 32 * tile, 16 * blk, 0, sc, bar);
+		tma_load4(buf + 4096, &a.sc_ld_map, 32 * tile, G::M - 16 * blk - 15, 0, sc, bar);
+		if (blk == 0) tma_load4(buf + 8192, &a.sc_ld1_map, 32 * tile, G::M / 2, 0, sc, bar);
+	}
+}
+template <int LGM> DSP_DEV uint32_t col_load_bytes(const ColItem &w) {
+	if (!w.sub_b) return (uint32_t)(ColGeom<LGM>::M * 16 * sizeof(C2<float>));
+	return 2u * 32768u + ((w.local / w.ntiles) == 0 ? 2048u : 0u);
 }
 template <int LGM>
-DSP_DEV void colA_store(const ColRingArgs &a, const C2<float> *buf, int gi) {
+DSP_DEV void col_store(const ColRingArgs &a, const ColItem &w, const C2<float> *buf) {
 	typedef ColGeom<LGM> G;
-	const int j = gi / a.ntiles, tile = gi - j * a.ntiles;
-	for (int h = 0; h < G::M / G::SROWS; h++) tma_store3(&a.sc_st_map, buf + h * G::SROWS * 16, 32 * tile, h * G::SROWS, j);
+	const int sc = w.q % kColRingScratch;
+	if (!w.sub_b) {
+		const int j = w.local / w.ntiles, tile = w.local - j * w.ntiles;
+		for (int h = 0; h < G::M / G::SROWS; h++) tma_store4(&a.sc_st_map, buf + h * G::SROWS * 16, 32 * tile, h * G::SROWS, j, sc);
+	} else {
+		const int blk = w.local / w.ntiles, tile = w.local - blk * w.ntiles;
+		const int c = w.col0 + 32 * tile;
+		tma_store4(&a.out_map, buf, c, 16 * blk, 0, w.plane);
+		tma_store4(&a.out_map, buf + 4096, c, G::M - 16 * blk - 15, 0, w.plane);
+		if (blk == 0) tma_store4(&a.out1_map, buf + 8192, c, G::M / 2, 0, w.plane);
+	}
 }
-// iteration gi of sub-pass B: block = gi / ntiles, tile = gi % ntiles
-template <int LGM, class Bar>
-DSP_DEV void colB_load(const ColRingArgs &a, C2<float> *buf, int gi, Bar *bar) {
-	typedef ColGeom<LGM> G;
-	const int blk = gi / a.ntiles, tile = gi - blk * a.ntiles;
-	tma_load3(buf, &a.sc_ld_map, 32 * tile, 16 * blk, 0, bar);
-	tma_load3(buf + 4096, &a.sc_ld_map, 32 * tile, G::M - 16 * blk - 15, 0, bar);
-	if (blk == 0) tma_load3(buf + 8192, &a.sc_ld1_map, 32 * tile, G::M / 2, 0, bar);
+// what has to be finished before the item's boxes may be loaded: (counter index, count), or index -1
+template <int LGM> DSP_DEV void col_dependency(const ColRingArgs &a, const ColItem &w, int &idx, int &need) {
+	const int Q = ColWork<LGM>::panels(a);
+	if (w.sub_b) { idx = w.q; need = 16 * w.ntiles; }                                      // all sub-FFTs of the panel are in the scratch
+	else if (w.q >= kColRingScratch) { idx = Q + w.q - kColRingScratch; need = (int)ColGeom<LGM>::NBLK * ColWork<LGM>::ntiles(a, w.q - kColRingScratch); }   // the scratch panel's previous user is done with it
+	else { idx = -1; need = 0; }
 }
-template <int LGM>
-DSP_DEV void colB_store(const ColRingArgs &a, const C2<float> *buf, int gi) {
-	typedef ColGeom<LGM> G;
-	const int blk = gi / a.ntiles, tile = gi - blk * a.ntiles;
-	const int c = a.col0 + 32 * tile;
-	tma_store3(&a.out_map, buf, c, 16 * blk, 0);
-	tma_store3(&a.out_map, buf + 4096, c, G::M - 16 * blk - 15, 0);
-	if (blk == 0) tma_store3(&a.out1_map, buf + 8192, c, G::M / 2, 0);
-}
-template <int LGM> DSP_DEV uint32_t colB_bytes(const ColRingArgs &a, int gi) { return 2u * 32768u + ((gi / a.ntiles) == 0 ? 2048u : 0u); }
 
 #if DSP_GPU
-// The ring with tensor-copy stores: an iteration ends by handing its buffer to the copy engine; the refill of that
-// buffer (iteration it + 3) waits until the engine has read it, which the issuing thread checks one barrier into its
-// next iteration -- by then the store is long under way, and the load still lands before the other group needs it.
-template <int LGM, bool SUBA>
+DSP_DEV int ld_acquire(const int *p) {
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+DSP_DEV void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int LGM>
+DSP_DEV void col_issue(const ColRingArgs &a, const int *seg_start, int gi, int &cursor, C2<float> *buf, uint64_t *bar) {
+	ColItem w;
+	ColWork<LGM>::decode(a, seg_start, gi, cursor, w);
+	int idx, need;
+	col_dependency<LGM>(a, w, idx, need);
+	if (idx >= 0) {
+		while (ld_acquire(a.done + idx) < need) __nanosleep(64);
+		fence_proxy_async_all();                                 // the boxes are read by the async proxy: order it after the acquire
+	}
+	mbar_expect_tx(bar, col_load_bytes<LGM>(w));
+	col_load<LGM>(a, w, buf, bar);
+}
+
+// The ring with tensor-copy stores.  An item ends by handing its buffer to the copy engine.  At the top of the
+// group's next item the issuing thread (1) waits for that store, publishes the item in its panel's counter, and only
+// then (2) refills the buffer with the item three ahead -- which may have to wait for a counter -- and (3) waits for
+// its own data.  Publishing before waiting is what keeps the counters free of cycles: reaching the top of an item
+// never depends on a load, and a load only depends on items that precede it by a whole segment (>= one item per CTA).
+template <int LGM>
 DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int ncta, int tid) {
 	typedef ColRingSmem<LGM> S;
-	typedef ColGeom<LGM> G;
-	C2<float> *tab = (C2<float> *)smem;
+	C2<float> *tabN = (C2<float> *)smem;
+	C2<float> *tabM = (C2<float> *)(smem + S::kTabNBytes);
+	int *seg_start = (int *)(smem + S::kTabNBytes + S::kTabMBytes);
 	C2<float> *bufs = (C2<float> *)(smem + S::kTablesBytes);
 	uint64_t *full = (uint64_t *)(smem + S::kTablesBytes + kRingBufs * S::kBufBytes);
 	RingFixed<LGM> fM;
 	RingFixed<LGM + 4> fN;
-	if (SUBA) colA_fill_tables<LGM>(a, tab, fM, tid, tid + 1, kRingGroups * kRingGroupThreads);
-	else {
+	const int nthr = kRingGroups * kRingGroupThreads;
+	colA_fill_tables<LGM>(a, tabM, fM, tid, tid + 1, nthr);
+	{
 		RingArgs ra;
 		ra.tw = a.twN; ra.om = a.omN; ra.sig = a.sigN;
-		ring_fill_tables<LGM + 4>(ra, tab, fN, tid, tid + 1, kRingGroups * kRingGroupThreads);
+		ring_fill_tables<LGM + 4>(ra, tabN, fN, tid, tid + 1, nthr);
 	}
-	const int total = a.ntiles * (SUBA ? 16 : G::NBLK);
-	const int iters = (total - cta + ncta - 1) / ncta;
 	if (tid == 0) {
+		col_fill_segments<LGM>(a, seg_start);
 		for (int b = 0; b < kRingBufs; b++) mbar_init(full + b, 1);
 		mbar_fence_init();
 	}
 	__syncthreads();
+	const int total = seg_start[2 * ColWork<LGM>::panels(a)];
+	const int iters = (total - cta + ncta - 1) / ncta;
 	if (tid == 0) {
-		for (int it = 0; it < kRingBufs && it < iters; it++) {
-			const int gi = cta + it * ncta;
-			C2<float> *buf = bufs + (size_t)it * S::kBufStride;
-			if (SUBA) { mbar_expect_tx(full + it, (uint32_t)(G::M * 16 * sizeof(C2<float>))); colA_load<LGM>(a, buf, gi, full + it); }
-			else { mbar_expect_tx(full + it, colB_bytes<LGM>(a, gi)); colB_load<LGM>(a, buf, gi, full + it); }
-		}
+		int cur = 0;
+		for (int it = 0; it < kRingBufs && it < iters; it++) col_issue<LGM>(a, seg_start, cta + it * ncta, cur, bufs + (size_t)it * S::kBufStride, full + it);
 	}
 	const int group = tid / kRingGroupThreads, gt = tid - group * kRingGroupThreads;
-	int refill_it = -1;                                          // iteration whose buffer waits for its store before the refill
+	int cursor = 0, issue_cursor = 0;
+	int refill_it = -1;                                          // item whose buffer waits for its store before the refill
+	int publish = -1;                                            // counter of the item whose store is in flight
 	for (int it = group; it < iters; it += kRingGroups) {
 		const int b = it % kRingBufs, gi = cta + it * ncta;
 		C2<float> *buf = bufs + (size_t)b * S::kBufStride;
-		mbar_wait(full + b, (uint32_t)((it / kRingBufs) & 1));
-		if (refill_it >= 0) {
-			// (the first barrier of the iteration sits inside *_iter; issuing here, before it, costs the thread only the
-			// wait for a store that was handed over a whole mbarrier wait ago)
-			if (gt == 0) {
-				tma_wait_read0();
-				const int nb = refill_it % kRingBufs, ngi = cta + (refill_it + kRingBufs) * ncta;
-				C2<float> *nbuf = bufs + (size_t)nb * S::kBufStride;
-				if (SUBA) { mbar_expect_tx(full + nb, (uint32_t)(G::M * 16 * sizeof(C2<float>))); colA_load<LGM>(a, nbuf, ngi, full + nb); }
-				else { mbar_expect_tx(full + nb, colB_bytes<LGM>(a, ngi)); colB_load<LGM>(a, nbuf, ngi, full + nb); }
+		if (gt == 0) {
+			if (publish >= 0) {
+				tma_wait_all0();                                     // the item's boxes are in global memory
+				__threadfence();
+				atomicAdd(a.done + publish, 1);
 			}
-			refill_it = -1;
+			if (refill_it >= 0) {
+				const int nb = refill_it % kRingBufs;
+				col_issue<LGM>(a, seg_start, cta + (refill_it + kRingBufs) * ncta, issue_cursor, bufs + (size_t)nb * S::kBufStride, full + nb);
+			}
 		}
-		if (SUBA) colA_iter<LGM>(a, fM, buf, group, gt, gt + 1);
-		else colB_iter<LGM>(a, fN, buf, gi / a.ntiles, group, gt, gt + 1);
-		// the iteration ended on a group barrier: every result is in the buffer
+		refill_it = -1; publish = -1;
+		mbar_wait(full + b, (uint32_t)((it / kRingBufs) & 1));
+		ColItem w;
+		ColWork<LGM>::decode(a, seg_start, gi, cursor, w);
+		if (!w.sub_b) colA_iter<LGM>(a, fM, buf, group, gt, gt + 1);
+		else colB_iter<LGM>(a, fN, buf, w.local / w.ntiles, group, gt, gt + 1);
+		// the item ended on a group barrier: every result is in the buffer
 		if (gt == 0) {
 			fence_proxy_async();
-			if (SUBA) colA_store<LGM>(a, buf, gi); else colB_store<LGM>(a, buf, gi);
+			col_store<LGM>(a, w, buf);
 			tma_commit();
 		}
+		publish = (w.sub_b ? ColWork<LGM>::panels(a) : 0) + w.q;
 		if (it + kRingBufs < iters) refill_it = it;
 	}
-	if (gt == 0) tma_wait_all0();                               // shared memory must outlive the engine's reads
+	if (gt == 0 && publish >= 0) {                              // shared memory must outlive the engine's reads; the last item counts too
+		tma_wait_all0();
+		__threadfence();
+		atomicAdd(a.done + publish, 1);
+	}
 }
 
-template <int LGM, bool SUBA>
+template <int LGM>
 __global__ void __launch_bounds__(kRingGroups *kRingGroupThreads, 1) k_col_ring(const __grid_constant__ ColRingArgs a) {
 	extern __shared__ __align__(128) unsigned char ring_smem[];
-	colring_cta<LGM, SUBA>(a, ring_smem, (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x);
+	colring_cta<LGM>(a, ring_smem, (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x);
 }
 #else
-template <int LGM, bool SUBA>
+template <int LGM>
 static void colring_emulate(const ColRingArgs &a, int ncta) {
 	typedef ColRingSmem<LGM> S;
-	typedef ColGeom<LGM> G;
 	std::vector<unsigned char> smem(S::kTotal + 128);
-	C2<float> *tab = (C2<float> *)smem.data();
+	C2<float> *tabN = (C2<float> *)smem.data();
+	C2<float> *tabM = (C2<float> *)(smem.data() + S::kTabNBytes);
+	int *seg_start = (int *)(smem.data() + S::kTabNBytes + S::kTabMBytes);
 	C2<float> *buf = (C2<float> *)(smem.data() + S::kTablesBytes);
 	RingFixed<LGM> fM;
 	RingFixed<LGM + 4> fN;
-	if (SUBA) colA_fill_tables<LGM>(a, tab, fM, 0, kRingGroupThreads, kRingGroupThreads);
-	else {
-		RingArgs ra;
-		ra.tw = a.twN; ra.om = a.omN; ra.sig = a.sigN;
-		ring_fill_tables<LGM + 4>(ra, tab, fN, 0, kRingGroupThreads, kRingGroupThreads);
+	colA_fill_tables<LGM>(a, tabM, fM, 0, kRingGroupThreads, kRingGroupThreads);
+	RingArgs ra;
+	ra.tw = a.twN; ra.om = a.omN; ra.sig = a.sigN;
+	ring_fill_tables<LGM + 4>(ra, tabN, fN, 0, kRingGroupThreads, kRingGroupThreads);
+	col_fill_segments<LGM>(a, seg_start);
+	const int Q = ColWork<LGM>::panels(a), total = seg_start[2 * Q];
+	// the emulation runs the items in launch order (which satisfies every dependency) and checks the counters it would
+	// have waited for
+	int cursor = 0;
+	for (int gi = 0; gi < total; gi++) {
+		(void)ncta;
+		ColItem w;
+		ColWork<LGM>::decode(a, seg_start, gi, cursor, w);
+		int idx, need;
+		col_dependency<LGM>(a, w, idx, need);
+		if (idx >= 0 && a.done[idx] < need) abort();           // launch order must satisfy the dependencies
+		col_load<LGM>(a, w, buf, (void *)nullptr);
+		if (!w.sub_b) colA_iter<LGM>(a, fM, buf, 0, 0, kRingGroupThreads);
+		else colB_iter<LGM>(a, fN, buf, w.local / w.ntiles, 0, 0, kRingGroupThreads);
+		col_store<LGM>(a, w, buf);
+		a.done[(w.sub_b ? Q : 0) + w.q] += 1;
 	}
-	const int total = a.ntiles * (SUBA ? 16 : G::NBLK);
-	for (int cta = 0; cta < ncta; cta++)
-		for (int gi = cta; gi < total; gi += ncta) {
-			if (SUBA) {
-				colA_load<LGM>(a, buf, gi, (void *)nullptr);
-				colA_iter<LGM>(a, fM, buf, 0, 0, kRingGroupThreads);
-				colA_store<LGM>(a, buf, gi);
-			} else {
-				colB_load<LGM>(a, buf, gi, (void *)nullptr);
-				colB_iter<LGM>(a, fN, buf, gi / a.ntiles, 0, 0, kRingGroupThreads);
-				colB_store<LGM>(a, buf, gi);
-			}
-		}
 }
 #endif
 

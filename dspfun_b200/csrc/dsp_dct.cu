@@ -261,8 +261,9 @@ struct PassPlan {
 	int ch_slot;                             // coordinate slot of that level (-1: the pass has no outer level)
 	long long ch_cnt, ch_is, ch_os, ch_inner;// its count and strides (elements), product of the levels below it
 	// ring sub-pass kernels (dct_colring.cuh): tensor maps per (input, output, scratch) pointer triple
-	struct RingMaps { const void *in; void *out, *scratch; ColRingArgs args; };
+	struct RingMaps { const void *in; void *out, *scratch; int nplanes; ColRingArgs args; };
 	std::vector<RingMaps> ring_maps;
+	int rg_P;                                // ring sub-pass kernels: panel width (0 = not eligible)
 	bool seg_saved;                          // strides below hold the plan's own values while an override is active
 	long long seg_os[4], seg_ax_os;
 };
@@ -289,6 +290,7 @@ struct dsp_dct_plan_s {
 	double *d_scalars;                       // acc[4] | scale_z[4] | dc_out[4]
 	unsigned char *d_signmap;
 	void *d_work;                            // T scratch the passes run in when the final store is 8-bit
+	int *d_ring_done;                        // completion counters of the ring sub-pass kernels (2 x max panels)
 	void *d_split;                           // panel scratch of the split column passes (nscratch parts: panels rotate)
 	size_t split_bytes;
 	int nscratch;
@@ -405,6 +407,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 		const bool wide = d > 4 || (d > 1 && (size_t)t->npad * 2 * (size_t)P->es * (size_t)d > kMaxSmem);
 		pp.row = ax == r - 1 && !wide;
 		pp.fast = t->sig != nullptr;
+		pp.rg_P = 0;
 		pp.split = false; pp.sp_P = 0; pp.sp_tc = 0; pp.sp_smem = 0; pp.sp_smem_inv = 0; pp.sp_force_inv = false;
 		pp.seg_n = 0; pp.seg_saved = false;
 		memset(&pp.ffM, 0, sizeof(pp.ffM));
@@ -522,7 +525,19 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 					pp.sp_smem = (size_t)(stc / 2) * seqM;
 					pp.sp_force_inv = split_inv;
 					pp.sp_smem_inv = 2 * (size_t)(16 / 2) * seqM;               // DIT-style inverse: sub-sequence pair of a 16-column tile
-					const size_t need = (size_t)nn * (size_t)pw * (size_t)P->es;
+					size_t need = (size_t)nn * (size_t)pw * (size_t)P->es;
+					// ring sub-pass kernels (dct_colring.cuh): one launch walks all panels; three scratch panels in rotation
+					pp.rg_P = 0;
+					if (P->prec == 'f' && colring_supports(nn) && (A.ncols % 32) == 0 && (A.ax_is % 4) == 0 && (A.ax_os % 4) == 0 && !getenv("DSP_DCT_NO_COLRING")) {
+						const double mb = getenv("DSP_DCT_RING_PANEL_MB") ? atof(getenv("DSP_DCT_RING_PANEL_MB")) : 16.0;
+						long long rp = (long long)(mb * 1048576.0) / ((long long)nn * 4);
+						rp = (rp / 32) * 32;
+						if (rp < 32) rp = 32;
+						if (rp >= A.ncols) rp = ((A.ncols / 2) / 32) * 32;                  // at least two panels per plane (the kernel's dependency order)
+						pp.rg_P = (int)rp;
+						const size_t ring_need = ((size_t)colring_scratch_panels() * (size_t)nn * (size_t)(rp > 0 ? rp : 0) * 4 + 1) / 2;   // (the plan allocates nscratch >= 2 parts)
+						if (ring_need > need) need = ring_need;
+					}
 					if (need > P->split_bytes) P->split_bytes = need;
 				}
 			}
@@ -548,6 +563,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 	if (getenv("DSP_DCT_NAUX")) { naux = atoi(getenv("DSP_DCT_NAUX")); if (naux < 1) naux = 1; if (naux > 4) naux = 4; }
 	P->nscratch = naux;
 	if (P->split_bytes && !rt_malloc(&P->d_split, (size_t)naux * P->split_bytes, g_err)) return false;
+	if (P->split_bytes && !rt_malloc((void **)&P->d_ring_done, sizeof(int) * 2 * (size_t)colring_max_panels(), g_err)) return false;
 #if DSP_GPU
 	P->naux = naux;
 	if (P->split_bytes && !getenv("DSP_DCT_NO_AUX")) {
@@ -611,6 +627,44 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		long long no = 1;
 		for (int k = 0; k < 4; k++) no *= c.o.cnt[k];
 		if (part) no = nc * pp.ch_inner;
+		int live = 0, at = 0;
+		for (int k = 0; k < 4; k++) if (c.o.cnt[k] > 1) { live++; at = k; }
+		if (fwd && f32 && !pp.fused && pp.rg_P > 0 && live <= 1 && P->d_ring_done) {
+			// ring sub-pass kernels: ONE persistent launch walks every panel of every plane (dct_colring.cuh); the tensor maps
+			// depend on the pointers only and are cached in the plan
+			const int ppp = (c.ncols + pp.rg_P - 1) / pp.rg_P;
+			int per = colring_max_panels() / ppp;
+			if (per < 1) per = 1;
+			ok = ppp <= colring_max_panels();
+			if (!ok) g_err = "ring column pass: too many panels per plane";
+			for (long long p0 = 0; p0 < no && ok; p0 += per) {
+				const int np = (int)(no - p0 < per ? no - p0 : per);
+				const char *bin = (const char *)in + p0 * c.o.is[at] * P->es;
+				char *bout = (char *)out + p0 * c.o.os[at] * P->es;
+				PassPlan::RingMaps *rm = nullptr;
+				for (auto &e : pp.ring_maps) if (e.in == bin && e.out == bout && e.scratch == P->d_split && e.nplanes == np) rm = &e;
+				if (!rm) {
+					PassPlan::RingMaps e;
+					memset(&e.args, 0, sizeof(e.args));
+					e.in = bin; e.out = bout; e.scratch = P->d_split; e.nplanes = np;
+					ok = colring_encode(e.args, c.f.n, (const float *)bin, c.ax_is, c.o.is[at], (float *)bout, c.ax_os, c.o.os[at], np, c.ncols,
+					                    (float *)P->d_split, pp.rg_P, g_err);
+					e.args.twM = pp.ffM.tw; e.args.sigM = pp.ffM.sig;
+					e.args.twN = pp.ff.tw; e.args.omN = pp.ff.om; e.args.sigN = pp.ff.sig;
+					e.args.nplanes = np; e.args.ppp = ppp; e.args.P = pp.rg_P; e.args.ncols = c.ncols; e.args.reverse = 0;
+					e.args.done = P->d_ring_done;
+					if (ok) { if (pp.ring_maps.size() >= 64) pp.ring_maps.clear(); pp.ring_maps.push_back(e); rm = &pp.ring_maps.back(); }
+				}
+				if (ok) {
+					ColRingArgs ra = rm->args;
+					ra.lscale = (float)(pp.lop.kind == OP_SCALE ? pp.lop.p[0] : 1.0); ra.sscale = (float)(pp.sop.kind == OP_SCALE ? pp.sop.p[0] : 1.0);
+					DSP_TRACE("split pass: ring sub-pass kernel n=%d planes %d panels/plane %d width %d", c.f.n, np, ppp, pp.rg_P);
+					ok = rt_zero(P->d_ring_done, sizeof(int) * 2 * (size_t)colring_max_panels(), st, g_err) && launch_col_ring_f32(ra, c.f.n, st, g_err);
+					if (ok) g_launches++;
+				}
+			}
+			if (ok) g_launches--;                  // the caller adds one
+		} else {
 		const int M = c.f.n / 16;
 		ok = true;
 		rt_stream pst[4] = {st, st, st, st};
@@ -659,29 +713,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					ok = launch_l2_prefetch((const char *)sa.in + (size_t)nc0 * P->es, sa.ax_is * P->es, c.f.n, ncols * P->es, st, g_err);
 				}
 				const bool dit_inv = !fwd && !pp.sp_force_inv;
-				static const bool no_cring = getenv("DSP_DCT_NO_COLRING") != nullptr;
-				if (ok && fwd && f32 && !pp.fused && !no_cring && colring_supports(c.f.n) && (c.ncols % 32) == 0 && (sa.pcols % 32) == 0 &&
-				    (pp.sp_P % 32) == 0 && (c.ax_is % 4) == 0 && (c.ax_os % 4) == 0) {
-					// persistent TMA-fed sub-passes; the tensor maps depend on the pointers only and are cached in the plan
-					PassPlan::RingMaps *rm = nullptr;
-					for (auto &e : pp.ring_maps) if (e.in == sa.in && e.out == sa.out && e.scratch == sa.scratch) rm = &e;
-					if (!rm) {
-						PassPlan::RingMaps e;
-						memset(&e.args, 0, sizeof(e.args));
-						e.in = sa.in; e.out = sa.out; e.scratch = sa.scratch;
-						ok = colring_encode(e.args, c.f.n, (const float *)sa.in, c.ax_is, (float *)sa.out, c.ax_os, c.ncols, (float *)sa.scratch, pp.sp_P, g_err);
-						e.args.twM = pp.ffM.tw; e.args.sigM = pp.ffM.sig;
-						e.args.twN = pp.ff.tw; e.args.omN = pp.ff.om; e.args.sigN = pp.ff.sig;
-						if (ok) { if (pp.ring_maps.size() >= 64) pp.ring_maps.clear(); pp.ring_maps.push_back(e); rm = &pp.ring_maps.back(); }
-					}
-					DSP_TRACE("split pass: ring sub-pass kernels n=%d panel cols %d+%d", c.f.n, sa.pcol0, sa.pcols);
-					if (ok) {
-						ColRingArgs ra = rm->args;
-						ra.col0 = sa.pcol0; ra.ntiles = sa.pcols / 32;
-						ra.lscale = (float)(pp.lop.kind == OP_SCALE ? pp.lop.p[0] : 1.0); ra.sscale = (float)(pp.sop.kind == OP_SCALE ? pp.sop.p[0] : 1.0);
-						ok = launch_col_ring_f32(ra, c.f.n, true, st, g_err) && launch_col_ring_f32(ra, c.f.n, false, st, g_err);
-					}
-				} else if (ok && dit_inv) {
+				if (ok && dit_inv) {
 					sa.tci = 16; sa.ntilesi = (sa.pcols + 15) / 16;
 					ok = launch_split_inv_fft_f32(sa, pp.ffM, pp.ff, pp.lop, sa.ntilesi * 9, pp.sp_smem_inv, st, g_err) &&
 					     launch_split_inv_outer_f32(sa, pp.ff, pp.sop, sa.ngroups * M, st, g_err);
@@ -703,6 +735,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		if (P->aux_ok)
 			for (int k = 0; k < P->naux; k++) { cudaEventRecord(P->ev_join[k], P->aux[k]); cudaStreamWaitEvent(st, P->ev_join[k], 0); }
 #endif
+		}
 	} else {
 		ColArgs a = pp.ca;
 		a.in = in; a.out = out;
@@ -847,6 +880,7 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->d_signmap = nullptr;
 	P->d_work = nullptr;
 	P->d_split = nullptr;
+	P->d_ring_done = nullptr;
 	P->split_bytes = 0;
 	P->nscratch = 1;
 #if DSP_GPU
@@ -911,7 +945,7 @@ static bool ensure_kids(dsp_dct_plan_s *P) {
 		dsp_dct_plan_s *K = new dsp_dct_plan_s(*P);             // same geometry; owned resources reset below
 		K->passes.clear();
 		K->d_in = K->d_out = nullptr; K->d_in_bytes = K->d_out_bytes = 0;
-		K->d_scalars = nullptr; K->d_signmap = nullptr; K->d_work = nullptr; K->d_split = nullptr;
+		K->d_scalars = nullptr; K->d_signmap = nullptr; K->d_work = nullptr; K->d_split = nullptr; K->d_ring_done = nullptr;
 		K->split_bytes = 0; K->nscratch = 1; K->aux_ok = false;
 		K->kids.clear(); K->kid_b0.clear(); K->kids_failed = true;  // no recursion
 		K->ev.clear(); K->ev_pass.clear(); K->ev_frac.clear(); K->profiling = false;
@@ -995,6 +1029,7 @@ static void destroy_plan(dsp_dct_plan_s *p) {
 	rt_free(p->d_signmap);
 	rt_free(p->d_work);
 	rt_free(p->d_split);
+	rt_free(p->d_ring_done);
 #if DSP_GPU
 	if (p->aux_ok) {
 		cudaEventDestroy(p->ev_fork);

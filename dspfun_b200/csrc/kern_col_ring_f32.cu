@@ -20,66 +20,79 @@ static int ring_sm_count() {
 #endif
 }
 
-template <int LGM, bool SUBA>
+template <int LGM>
 static bool colring_launch_t(const ColRingArgs &a, rt_stream st, std::string &err) {
-	typedef ColGeom<LGM> G;
-	const int total = a.ntiles * (SUBA ? 16 : G::NBLK), sms = ring_sm_count();
-	const int grid = total < sms ? total : sms;
+	const int Q = a.nplanes * a.ppp;
+	int minseg = 1 << 30;
+	for (int s = 0; s < 2 * Q; s++) { const int n = ColWork<LGM>::seg_items(a, s, Q); if (n < minseg) minseg = n; }
+	// The counters are free of cycles when a CTA never holds an item of A(q) right before one of B(q) and its first three
+	// items (loaded before anything is computed) carry no dependency: every segment needs >= 1.5 items per CTA, and B(q)
+	// must not follow A(q) directly (>= 2 panels).  See colring_cta.
+	if (Q < 2 || minseg < 3) { err = "ring column pass needs at least two panels"; return false; }
+	const int sms = ring_sm_count();
+	int grid = (2 * minseg) / 3;
+	if (grid > sms) grid = sms;
 #if DSP_GPU
 	const size_t smem = ColRingSmem<LGM>::kTotal;
 	static unsigned long long attr_dev = 0;      // one bit per device: the attribute is per (function, device)
 	const int dev = rt_device() & 63;
 	if (!((attr_dev >> dev) & 1ull)) {
-		if (!rt_ok(cudaFuncSetAttribute(k_col_ring<LGM, SUBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err, "smem attribute")) return false;
+		if (!rt_ok(cudaFuncSetAttribute(k_col_ring<LGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err, "smem attribute")) return false;
 		attr_dev |= 1ull << dev;
 	}
-	k_col_ring<LGM, SUBA><<<grid, kRingGroups * kRingGroupThreads, smem, st>>>(a);
-	return rt_ok(cudaGetLastError(), err, "ring column kernel launch");
+	// every CTA must be resident (items wait on counters other CTAs bump): a cooperative launch makes the driver check it
+	void *params[] = {(void *)&a};
+	return rt_ok(cudaLaunchCooperativeKernel((const void *)k_col_ring<LGM>, dim3(grid), dim3(kRingGroups * kRingGroupThreads), params, smem, st), err,
+	             "ring column kernel launch");
 #else
 	(void)st; (void)err;
-	colring_emulate<LGM, SUBA>(a, grid);
+	colring_emulate<LGM>(a, grid);
 	return true;
 #endif
 }
 
 bool colring_supports(int n) { return n == 4096 || n == 8192; }
+int colring_max_panels() { return kColRingMaxPanels; }
+int colring_scratch_panels() { return kColRingScratch; }
 
-// tensor maps of one (input image, output image, scratch) triple; the panel enters through coordinates
-bool colring_encode(ColRingArgs &a, int n, const float *in, long long ax_is, float *out, long long ax_os, int ncols, float *scratch,
-                    int P, std::string &err) {
+// tensor maps of one (input image, output image, scratch) triple; planes and panels enter through coordinates
+bool colring_encode(ColRingArgs &a, int n, const float *in, long long ax_is, long long plane_is, float *out, long long ax_os,
+                    long long plane_os, int nplanes, int ncols, float *scratch, int P, std::string &err) {
 	const int M = n / 16;
 	TmaView v;
-	v.rank = 3;
-	v.dims[3] = 1; v.strides[3] = 0; v.box[3] = 1; v.strides[0] = 4;
-	// image as [n/32][32][cols] (sub-pass A load)
+	v.rank = 4;
+	v.strides[0] = 4;
+	// image as [planes][n/32][32][cols] (sub-pass A load)
 	v.base = (void *)in;
-	v.dims[0] = (unsigned long long)ncols; v.dims[1] = 32; v.dims[2] = (unsigned long long)(n / 32);
+	v.dims[0] = (unsigned long long)ncols; v.dims[1] = 32; v.dims[2] = (unsigned long long)(n / 32); v.dims[3] = (unsigned long long)nplanes;
 	v.strides[1] = (unsigned long long)ax_is * 4; v.strides[2] = 32ull * (unsigned long long)ax_is * 4;
-	v.box[0] = 32; v.box[1] = 1; v.box[2] = (unsigned)(M / 2);
+	v.strides[3] = nplanes > 1 ? (unsigned long long)plane_is * 4 : v.strides[2] * v.dims[2];
+	v.box[0] = 32; v.box[1] = 1; v.box[2] = (unsigned)(M / 2); v.box[3] = 1;
 	if (!tma_encode(&a.in_map, v, err)) return false;
-	// scratch as [16][M][P]
+	// scratch as [3][16][M][P]
 	v.base = scratch;
-	v.dims[0] = (unsigned long long)P; v.dims[1] = (unsigned long long)M; v.dims[2] = 16;
-	v.strides[1] = (unsigned long long)P * 4; v.strides[2] = (unsigned long long)M * (unsigned long long)P * 4;
+	v.dims[0] = (unsigned long long)P; v.dims[1] = (unsigned long long)M; v.dims[2] = 16; v.dims[3] = kColRingScratch;
+	v.strides[1] = (unsigned long long)P * 4; v.strides[2] = (unsigned long long)M * (unsigned long long)P * 4; v.strides[3] = 16 * v.strides[2];
 	v.box[0] = 32; v.box[1] = (unsigned)(M < 256 ? M : 256); v.box[2] = 1;
 	if (!tma_encode(&a.sc_st_map, v, err)) return false;
 	v.box[1] = 16; v.box[2] = 16;
 	if (!tma_encode(&a.sc_ld_map, v, err)) return false;
 	v.box[1] = 1;
 	if (!tma_encode(&a.sc_ld1_map, v, err)) return false;
-	// image as [16][M][cols] (sub-pass B store)
+	// image as [planes][16][M][cols] (sub-pass B store)
 	v.base = out;
-	v.dims[0] = (unsigned long long)ncols; v.dims[1] = (unsigned long long)M; v.dims[2] = 16;
+	v.dims[0] = (unsigned long long)ncols; v.dims[1] = (unsigned long long)M; v.dims[2] = 16; v.dims[3] = (unsigned long long)nplanes;
 	v.strides[1] = (unsigned long long)ax_os * 4; v.strides[2] = (unsigned long long)M * (unsigned long long)ax_os * 4;
+	v.strides[3] = nplanes > 1 ? (unsigned long long)plane_os * 4 : v.strides[2] * v.dims[2];
 	v.box[1] = 16; v.box[2] = 16;
 	if (!tma_encode(&a.out_map, v, err)) return false;
 	v.box[1] = 1;
 	return tma_encode(&a.out1_map, v, err);
 }
 
-bool launch_col_ring_f32(const ColRingArgs &a, int n, bool sub_a, rt_stream st, std::string &err) {
-	if (n == 8192) return sub_a ? colring_launch_t<9, true>(a, st, err) : colring_launch_t<9, false>(a, st, err);
-	if (n == 4096) return sub_a ? colring_launch_t<8, true>(a, st, err) : colring_launch_t<8, false>(a, st, err);
+bool launch_col_ring_f32(const ColRingArgs &a, int n, rt_stream st, std::string &err) {
+	if (n == 8192) return colring_launch_t<9>(a, st, err);
+	if (n == 4096) return colring_launch_t<8>(a, st, err);
 	err = "no ring column kernel for this length";
 	return false;
 }
