@@ -183,18 +183,18 @@ struct ColItem {
 };
 template <int LGM> struct ColWork {
 	typedef ColGeom<LGM> G;
-	DSP_DEVM static int panels(const ColRingArgs &a) { return a.nplanes * a.ppp; }
-	DSP_DEVM static int ntiles(const ColRingArgs &a, int q) {
+	DSP_HDM static int panels(const ColRingArgs &a) { return a.nplanes * a.ppp; }
+	DSP_HDM static int ntiles(const ColRingArgs &a, int q) {
 		int p = q % a.ppp;
 		if (a.reverse) p = a.ppp - 1 - p;
 		const int left = a.ncols - p * a.P;
 		return (left < a.P ? left : a.P) / 32;
 	}
-	DSP_DEVM static int seg_panel(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? Q - 1 : ((s & 1) ? (s + 1) / 2 : s / 2 - 1)); }
-	DSP_DEVM static int seg_is_b(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? 1 : ((s & 1) ? 0 : 1)); }
-	DSP_DEVM static int seg_items(const ColRingArgs &a, int s, int Q) { return ntiles(a, seg_panel(s, Q)) * (seg_is_b(s, Q) ? (int)G::NBLK : 16); }
+	DSP_HDM static int seg_panel(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? Q - 1 : ((s & 1) ? (s + 1) / 2 : s / 2 - 1)); }
+	DSP_HDM static int seg_is_b(int s, int Q) { return s == 0 ? 0 : (s == 2 * Q - 1 ? 1 : ((s & 1) ? 0 : 1)); }
+	DSP_HDM static int seg_items(const ColRingArgs &a, int s, int Q) { return ntiles(a, seg_panel(s, Q)) * (seg_is_b(s, Q) ? (int)G::NBLK : 16); }
 	// seg_start[s] = first global item of segment s (2Q + 1 entries, filled once per CTA)
-	DSP_DEVM static void decode(const ColRingArgs &a, const int *seg_start, int gi, int &cursor, ColItem &w) {
+	DSP_HDM static void decode(const ColRingArgs &a, const int *seg_start, int gi, int &cursor, ColItem &w) {
 		const int Q = panels(a);
 		while (gi >= seg_start[cursor + 1]) cursor++;
 		w.sub_b = seg_is_b(cursor, Q);
@@ -318,10 +318,15 @@ DSP_DEV void col_issue(const ColRingArgs &a, const int *seg_start, int gi, int &
 }
 
 // The ring with tensor-copy stores.  An item ends by handing its buffer to the copy engine.  At the top of the
-// group's next item the issuing thread (1) waits for that store, publishes the item in its panel's counter, and only
-// then (2) refills the buffer with the item three ahead -- which may have to wait for a counter -- and (3) waits for
-// its own data.  Publishing before waiting is what keeps the counters free of cycles: reaching the top of an item
-// never depends on a load, and a load only depends on items that precede it by a whole segment (>= one item per CTA).
+// group's next item the issuing thread waits until the engine has READ that buffer (short) and refills it with the item
+// three ahead -- which may have to wait for a counter.  The item is PUBLISHED in its panel's counter only when its
+// boxes are in global memory, which the thread checks at the end of its next item (by then they long are: the single
+// spare buffer of the ring must never sit through a store's full round trip -- measured: that halves the throughput).
+// Why the counters cannot deadlock: item x is published at the end of item x + 2 of the same CTA; the load of item y is
+// issued at the top of item y - 1 and waits for items of an earlier segment.  The launcher sizes the grid so that
+// every segment holds more than 3 items per CTA, hence those items are x <= y - 4, and their publication (end of item
+// <= y - 2, run by the other thread group or earlier in program order) never waits for the load of y.  The first
+// three items of a CTA, loaded before anything is computed, belong to the first two segments, which have no dependency.
 template <int LGM>
 DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int ncta, int tid) {
 	typedef ColRingSmem<LGM> S;
@@ -358,18 +363,12 @@ DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int
 	for (int it = group; it < iters; it += kRingGroups) {
 		const int b = it % kRingBufs, gi = cta + it * ncta;
 		C2<float> *buf = bufs + (size_t)b * S::kBufStride;
-		if (gt == 0) {
-			if (publish >= 0) {
-				tma_wait_all0();                                     // the item's boxes are in global memory
-				__threadfence();
-				atomicAdd(a.done + publish, 1);
-			}
-			if (refill_it >= 0) {
-				const int nb = refill_it % kRingBufs;
-				col_issue<LGM>(a, seg_start, cta + (refill_it + kRingBufs) * ncta, issue_cursor, bufs + (size_t)nb * S::kBufStride, full + nb);
-			}
+		if (gt == 0 && refill_it >= 0) {
+			tma_wait_read0();                                        // the engine has read the stored buffer: it may be overwritten
+			const int nb = refill_it % kRingBufs;
+			col_issue<LGM>(a, seg_start, cta + (refill_it + kRingBufs) * ncta, issue_cursor, bufs + (size_t)nb * S::kBufStride, full + nb);
 		}
-		refill_it = -1; publish = -1;
+		refill_it = -1;
 		mbar_wait(full + b, (uint32_t)((it / kRingBufs) & 1));
 		ColItem w;
 		ColWork<LGM>::decode(a, seg_start, gi, cursor, w);
@@ -377,6 +376,11 @@ DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int
 		else colB_iter<LGM>(a, fN, buf, w.local / w.ntiles, group, gt, gt + 1);
 		// the item ended on a group barrier: every result is in the buffer
 		if (gt == 0) {
+			if (publish >= 0) {                                      // the group's previous item: its store was handed over a whole
+				tma_wait_all0();                                     // item ago, so this does not wait; its boxes are in global memory
+				__threadfence();
+				atomicAdd(a.done + publish, 1);
+			}
 			fence_proxy_async();
 			col_store<LGM>(a, w, buf);
 			tma_commit();

@@ -529,7 +529,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 					// ring sub-pass kernels (dct_colring.cuh): one launch walks all panels; three scratch panels in rotation
 					pp.rg_P = 0;
 					if (P->prec == 'f' && colring_supports(nn) && (A.ncols % 32) == 0 && (A.ax_is % 4) == 0 && (A.ax_os % 4) == 0 && !getenv("DSP_DCT_NO_COLRING")) {
-						const double mb = getenv("DSP_DCT_RING_PANEL_MB") ? atof(getenv("DSP_DCT_RING_PANEL_MB")) : 16.0;
+						const double mb = getenv("DSP_DCT_RING_PANEL_MB") ? atof(getenv("DSP_DCT_RING_PANEL_MB")) : 32.0;   // 512 items per segment at n = 8192: > 3 per CTA on 148 SMs
 						long long rp = (long long)(mb * 1048576.0) / ((long long)nn * 4);
 						rp = (rp / 32) * 32;
 						if (rp < 32) rp = 32;

@@ -25,12 +25,11 @@ static bool colring_launch_t(const ColRingArgs &a, rt_stream st, std::string &er
 	const int Q = a.nplanes * a.ppp;
 	int minseg = 1 << 30;
 	for (int s = 0; s < 2 * Q; s++) { const int n = ColWork<LGM>::seg_items(a, s, Q); if (n < minseg) minseg = n; }
-	// The counters are free of cycles when a CTA never holds an item of A(q) right before one of B(q) and its first three
-	// items (loaded before anything is computed) carry no dependency: every segment needs >= 1.5 items per CTA, and B(q)
-	// must not follow A(q) directly (>= 2 panels).  See colring_cta.
-	if (Q < 2 || minseg < 3) { err = "ring column pass needs at least two panels"; return false; }
+	// The counters are free of cycles when every segment holds more than 3 items per CTA and B(q) does not follow A(q)
+	// directly (>= 2 panels): see colring_cta.
+	if (Q < 2 || minseg < 4) { err = "ring column pass needs at least two panels"; return false; }
 	const int sms = ring_sm_count();
-	int grid = (2 * minseg) / 3;
+	int grid = (minseg - 1) / 3;
 	if (grid > sms) grid = sms;
 #if DSP_GPU
 	const size_t smem = ColRingSmem<LGM>::kTotal;

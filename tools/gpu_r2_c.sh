@@ -7,7 +7,7 @@ if ! grep -q "cring pytest rc=0" gpurun_out/pytest_cring.log; then
   timeout 120 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_round2.py -x -q -k "ring_column_subpasses_small_panels and shape0" 2>&1 | tail -30
   exit 0
 fi
-for env in "DSP_DCT_RING_PANEL_MB=8" "DSP_DCT_RING_PANEL_MB=16" "DSP_DCT_RING_PANEL_MB=24" "DSP_DCT_RING_PANEL_MB=32" "DSP_DCT_NO_COLRING=1"; do
+for env in "DSP_DCT_RING_PANEL_MB=16" "DSP_DCT_RING_PANEL_MB=32" "DSP_DCT_RING_PANEL_MB=64" "DSP_DCT_NO_COLRING=1"; do
   echo "== plane8192 $env"
   env $env timeout 300 python bench.py --workload plane8192 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
 import json,sys
