@@ -24,6 +24,7 @@
 // DCT-III mirrors it (pre-twiddle + sub-FFTs into the scratch, then the outer DIT butterflies): see the inverse section.
 #pragma once
 #include "dct_ring.cuh"
+#include "dct_split.cuh"
 
 namespace dsp {
 
@@ -41,6 +42,11 @@ struct ColRingArgs {
 	int P, ncols;         // panel width (the last panel of a plane may be narrower); columns per plane
 	int reverse;          // walk the panels of a plane from the last to the first (inverse plans)
 	int *done;            // [2][nplanes * ppp] items finished per panel: sub-pass A | sub-pass B.  Zero before the launch.
+	int flags;            // bit 0: do not discard dead scratch lines (DSP_DCT_RING_NODISCARD, A/B measurements)
+	long long *trace;     // debug (DSP_DCT_RING_TRACE): per item of CTA 0, 4 globaltimer stamps; nullptr = off
+	float *scratch;       // [3][16][M][P]: sub-pass B discards the rows it has read (no write-back of dead scratch lines to HBM)
+	float *out;           // sub-pass B stores its results from registers (STG.64, 128 B per half warp): image base,
+	long long ax_os, plane_os;   // row and plane strides (elements)
 	float lscale, sscale;
 	const void *twM;      // C2<float>[M]      sub-FFT twiddles
 	const uint16_t *sigM; // [M]               sub-FFT slot table
@@ -126,6 +132,7 @@ DSP_DEV void colA_iter(const ColRingArgs &a, const RingFixed<LGM> &fM, C2<float>
 			for (int m = 0; m < 16; m++) buf[(i + R0 * m) * 16 + cp] = vv[m];
 		}
 	}
+	RING_PROXY_FENCE();                                          // the buffer goes to the copy engine (tensor store) next
 	RING_SYNC(group);
 }
 
@@ -153,24 +160,60 @@ template <int LGM> struct BoxSink {
 	}
 };
 
-template <int LGM>
-DSP_DEV void colB_iter(const ColRingArgs &a, const RingFixed<LGM + 4> &fN, C2<float> *buf, int blk, int group, int t0, int t1) {
+// The butterflies' inputs go to registers first and the buffer is handed back at once (`released`, called by every
+// thread after the barrier): the outer pass works in registers and stores its results to the image directly, so a
+// sub-pass B item keeps its buffer only for the flight of its load -- all three buffers of the ring can be in flight.
+template <int LGM, class Released>
+DSP_DEV void colB_iter(const ColRingArgs &a, const RingFixed<LGM + 4> &fN, C2<float> *buf, int blk, int col, int pcol0, int sc, int plane,
+                       int group, int t0, int t1, const Released &released) {
 	typedef ColGeom<LGM> G;
 	const int M = G::M;
+#if DSP_GPU
+	C2<float> va[16], vb[16];
+#else
+	static thread_local C2<float> va_all[kRingGroupThreads][16], vb_all[kRingGroupThreads][16];
+#endif
+#if DSP_GPU
+	// The scratch rows of this item are dead: written once (sub-pass A), read once (the boxes have landed), rewritten
+	// three panels later.  Without the discard the L2 writes most of them back to HBM (ncu r02: 986 MB of DRAM writes per
+	// pass against 537 MB of results).  One 128-byte line per (j, i) row of the boxes; issued and fenced BEFORE the group
+	// barrier, i.e. before the item is published: a late discard must not meet the panel's next contents.
+	if (t0 < 32 && !(a.flags & 1)) {                            // one warp: 16 or 17 lines per lane, one fence per lane
+		const int tile_col = col - pcol0;
+		const float *sbase = a.scratch + (size_t)sc * 16 * M * a.P;
+		for (int l = t0; l < 512; l += 32) {
+			const int j = (l >> 4) & 15, ii = l & 15;
+			const int row = l < 256 ? 16 * blk + ii : M - 16 * blk - 15 + ii;
+			if (row < M) discard_l2(sbase + ((size_t)j * M + row) * a.P + tile_col);
+		}
+		if (blk == 0 && t0 < 16) discard_l2(sbase + ((size_t)t0 * M + M / 2) * a.P + tile_col);
+		__threadfence();
+	}
+#endif
 	for (int tid = t0; tid < t1 && tid < kRingGroup; tid++) {
 		const int cp = tid & 15, ii = tid >> 4, i = 16 * blk + ii;
-		C2<float> *b1 = buf + ii * 16 + cp, *b2 = buf + 4096 + (15 - ii) * 16 + cp, *b3 = buf + 8192 + cp;
-		if (i != 0) {
-			const BoxSink<LGM> sink{b1, b2, 256, i, a.sscale};
-			dct2_outer_unit<float>(BoxBf{b1, b2, 256}, fN, i, sink);
-		} else {
-			const BoxSink<LGM> s0{b1, b1, 256, 0, a.sscale};
-			dct2_outer_unit<float>(BoxBf{b1, b1, 256}, fN, 0, s0);
-			const BoxSink<LGM> sh{b3, b3, 16, M / 2, a.sscale};
-			dct2_outer_unit<float>(BoxBf{b3, b3, 16}, fN, M / 2, sh);
+		const C2<float> *b1 = buf + ii * 16 + cp, *b2 = i != 0 ? buf + 4096 + (15 - ii) * 16 + cp : buf + 8192 + cp;
+		const int js2 = i != 0 ? 256 : 16;                           // (butterfly 0 travels with butterfly M/2, from the third box)
+		C2<float> *xa = RING_REGS(va, tid), *xb = RING_REGS(vb, tid);
+#pragma unroll
+		for (int j = 0; j < 16; j++) { xa[j] = b1[j * 256]; xb[j] = b2[j * js2]; }
+	}
+	RING_PROXY_FENCE();                                          // the buffer goes back to the copy engine (refill) next
+	RING_SYNC(group);
+	released();
+	const OpMul<float> sop = {a.sscale};
+	for (int tid = t0; tid < t1 && tid < kRingGroup; tid++) {
+		const int cp = tid & 15, ii = tid >> 4, i = 16 * blk + ii;
+		GlobalCols<float, OpMul<float>, true> sink;
+		sink.p = a.out + (long long)plane * a.plane_os + col + 2 * cp; sink.rs = a.ax_os; sink.hasb = true; sink.vec = true;
+		sink.ax_slot = 0; sink.ca = Coord{0, 0, 0, 0, 0}; sink.cb = sink.ca; sink.op = &sop;
+		C2<float> *xa = RING_REGS(va, tid), *xb = RING_REGS(vb, tid);
+		if (i != 0) dct2_outer_unit<float>(RegBf{xa, xb}, fN, i, sink);
+		else {
+			dct2_outer_unit<float>(RegBf{xa, xa}, fN, 0, sink);
+			dct2_outer_unit<float>(RegBf{xb, xb}, fN, M / 2, sink);
 		}
 	}
-	RING_SYNC(group);
 }
 
 // ------------------------------------------------------------------------------------------------ work list
@@ -196,6 +239,7 @@ template <int LGM> struct ColWork {
 	// seg_start[s] = first global item of segment s (2Q + 1 entries, filled once per CTA)
 	DSP_HDM static void decode(const ColRingArgs &a, const int *seg_start, int gi, int &cursor, ColItem &w) {
 		const int Q = panels(a);
+		while (gi < seg_start[cursor]) cursor--;                  // (a deferred first load is issued after later ones)
 		while (gi >= seg_start[cursor + 1]) cursor++;
 		w.sub_b = seg_is_b(cursor, Q);
 		w.q = seg_panel(cursor, Q);
@@ -259,13 +303,15 @@ DSP_DEV void col_load(const ColRingArgs &a, const ColItem &w, C2<float> *buf, Ba
 	if (!w.sub_b) {                          // sub-FFT j of a tile: rows of phase 2j ascending, rows of phase 31 - 2j descending
 		const int j = w.local / w.ntiles, tile = w.local - j * w.ntiles;
 		const int c = w.col0 + 32 * tile;
-		tma_load4(buf, &a.in_map, c, 2 * j, 0, w.plane, bar);
-		tma_load4(buf + (G::M / 2) * 16, &a.in_map, c, 31 - 2 * j, 0, w.plane, bar);
+		const auto stream = l2_policy_evict_first();                 // image data passes through once: leave L2 to the scratch
+		tma_load4_hint(buf, &a.in_map, c, 2 * j, 0, w.plane, bar, stream);
+		tma_load4_hint(buf + (G::M / 2) * 16, &a.in_map, c, 31 - 2 * j, 0, w.plane, bar, stream);
 	} else {                                 // block of 16 butterflies i and the mirror block M - i (+ butterfly M/2 with block 0)
 		const int blk = w.local / w.ntiles, tile = w.local - blk * w.ntiles;
-		tma_load4(buf, &a.sc_ld_map, 32 * tile, 16 * blk, 0, sc, bar);
-		tma_load4(buf + 4096, &a.sc_ld_map, 32 * tile, G::M - 16 * blk - 15, 0, sc, bar);
-		if (blk == 0) tma_load4(buf + 8192, &a.sc_ld1_map, 32 * tile, G::M / 2, 0, sc, bar);
+		const auto last_use = l2_policy_evict_first();               // the scratch rows are dead once read
+		tma_load4_hint(buf, &a.sc_ld_map, 32 * tile, 16 * blk, 0, sc, bar, last_use);
+		tma_load4_hint(buf + 4096, &a.sc_ld_map, 32 * tile, G::M - 16 * blk - 15, 0, sc, bar, last_use);
+		if (blk == 0) tma_load4_hint(buf + 8192, &a.sc_ld1_map, 32 * tile, G::M / 2, 0, sc, bar, last_use);
 	}
 }
 template <int LGM> DSP_DEV uint32_t col_load_bytes(const ColItem &w) {
@@ -278,13 +324,8 @@ DSP_DEV void col_store(const ColRingArgs &a, const ColItem &w, const C2<float> *
 	const int sc = w.q % kColRingScratch;
 	if (!w.sub_b) {
 		const int j = w.local / w.ntiles, tile = w.local - j * w.ntiles;
-		for (int h = 0; h < G::M / G::SROWS; h++) tma_store4(&a.sc_st_map, buf + h * G::SROWS * 16, 32 * tile, h * G::SROWS, j, sc);
-	} else {
-		const int blk = w.local / w.ntiles, tile = w.local - blk * w.ntiles;
-		const int c = w.col0 + 32 * tile;
-		tma_store4(&a.out_map, buf, c, 16 * blk, 0, w.plane);
-		tma_store4(&a.out_map, buf + 4096, c, G::M - 16 * blk - 15, 0, w.plane);
-		if (blk == 0) tma_store4(&a.out1_map, buf + 8192, c, G::M / 2, 0, w.plane);
+		const auto keep = l2_policy_evict_last();                    // the scratch is read back a segment later: keep it in L2
+		for (int h = 0; h < G::M / G::SROWS; h++) tma_store4_hint(&a.sc_st_map, buf + h * G::SROWS * 16, 32 * tile, h * G::SROWS, j, sc, keep);
 	}
 }
 // what has to be finished before the item's boxes may be loaded: (counter index, count), or index -1
@@ -301,6 +342,7 @@ DSP_DEV int ld_acquire(const int *p) {
 	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
+DSP_DEV long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 DSP_DEV void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int LGM>
@@ -317,16 +359,14 @@ DSP_DEV void col_issue(const ColRingArgs &a, const int *seg_start, int gi, int &
 	col_load<LGM>(a, w, buf, bar);
 }
 
-// The ring with tensor-copy stores.  An item ends by handing its buffer to the copy engine.  At the top of the
-// group's next item the issuing thread waits until the engine has READ that buffer (short) and refills it with the item
-// three ahead -- which may have to wait for a counter.  The item is PUBLISHED in its panel's counter only when its
-// boxes are in global memory, which the thread checks at the end of its next item (by then they long are: the single
-// spare buffer of the ring must never sit through a store's full round trip -- measured: that halves the throughput).
-// Why the counters cannot deadlock: item x is published at the end of item x + 2 of the same CTA; the load of item y is
-// issued at the top of item y - 1 and waits for items of an earlier segment.  The launcher sizes the grid so that
-// every segment holds more than 3 items per CTA, hence those items are x <= y - 4, and their publication (end of item
-// <= y - 2, run by the other thread group or earlier in program order) never waits for the load of y.  The first
-// three items of a CTA, loaded before anything is computed, belong to the first two segments, which have no dependency.
+// The ring.  A sub-pass A item ends by handing its buffer to the copy engine (tensor store to the scratch), waits for
+// the store, publishes the item in its panel's counter and refills the buffer with the item three ahead.  A sub-pass B
+// item gives its buffer back as soon as its boxes are in registers (and publishes that the scratch rows are read).
+// Why the counters cannot deadlock: an item is published by the thread that ran it, right at its end, whatever else
+// happens; a load of item y is issued by the thread group of items y - 3 / y - 1 and waits for items of an EARLIER
+// SEGMENT.  The launcher sizes the grid so that every segment holds at least one item of every CTA, so those items
+// are y - 2 or older in this CTA: either already done by this thread, or being run by the other thread group, which
+// never waits for this one.  Items 0 and 1 of a CTA belong to the first two segments, which have no dependency.
 template <int LGM>
 DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int ncta, int tid) {
 	typedef ColRingSmem<LGM> S;
@@ -352,46 +392,63 @@ DSP_DEV void colring_cta(const ColRingArgs &a, unsigned char *smem, int cta, int
 	__syncthreads();
 	const int total = seg_start[2 * ColWork<LGM>::panels(a)];
 	const int iters = (total - cta + ncta - 1) / ncta;
+	// The first items are loaded before anything is computed: only those without a dependency (with >= one item per CTA
+	// in every segment that is items 0 and 1 at least); a third one that has to wait is issued at the top of its own turn.
+	int deferred = -1;
 	if (tid == 0) {
 		int cur = 0;
-		for (int it = 0; it < kRingBufs && it < iters; it++) col_issue<LGM>(a, seg_start, cta + it * ncta, cur, bufs + (size_t)it * S::kBufStride, full + it);
+		for (int it = 0; it < kRingBufs && it < iters; it++) {
+			ColItem w;
+			int c2 = cur, idx, need;
+			ColWork<LGM>::decode(a, seg_start, cta + it * ncta, c2, w);
+			col_dependency<LGM>(a, w, idx, need);
+			if (idx >= 0 && it == kRingBufs - 1) { deferred = it; break; }
+			col_issue<LGM>(a, seg_start, cta + it * ncta, cur, bufs + (size_t)it * S::kBufStride, full + it);
+		}
 	}
 	const int group = tid / kRingGroupThreads, gt = tid - group * kRingGroupThreads;
 	int cursor = 0, issue_cursor = 0;
-	int refill_it = -1;                                          // item whose buffer waits for its store before the refill
-	int publish = -1;                                            // counter of the item whose store is in flight
 	for (int it = group; it < iters; it += kRingGroups) {
 		const int b = it % kRingBufs, gi = cta + it * ncta;
 		C2<float> *buf = bufs + (size_t)b * S::kBufStride;
-		if (gt == 0 && refill_it >= 0) {
-			tma_wait_read0();                                        // the engine has read the stored buffer: it may be overwritten
-			const int nb = refill_it % kRingBufs;
-			col_issue<LGM>(a, seg_start, cta + (refill_it + kRingBufs) * ncta, issue_cursor, bufs + (size_t)nb * S::kBufStride, full + nb);
-		}
-		refill_it = -1;
+		if (tid == 0 && it == deferred) col_issue<LGM>(a, seg_start, gi, issue_cursor, buf, full + b);       // (tid 0 is thread 0 of group 0: item 2 is its own)
+		const bool tr = a.trace && cta == 0 && gt == 0 && it < 4096;
+		if (tr) a.trace[4 * it + 0] = gtimer();
 		mbar_wait(full + b, (uint32_t)((it / kRingBufs) & 1));
+		if (tr) a.trace[4 * it + 1] = gtimer();
 		ColItem w;
 		ColWork<LGM>::decode(a, seg_start, gi, cursor, w);
-		if (!w.sub_b) colA_iter<LGM>(a, fM, buf, group, gt, gt + 1);
-		else colB_iter<LGM>(a, fN, buf, w.local / w.ntiles, group, gt, gt + 1);
-		// the item ended on a group barrier: every result is in the buffer
-		if (gt == 0) {
-			if (publish >= 0) {                                      // the group's previous item: its store was handed over a whole
-				tma_wait_all0();                                     // item ago, so this does not wait; its boxes are in global memory
-				__threadfence();
-				atomicAdd(a.done + publish, 1);
+		const bool more = it + kRingBufs < iters;
+		if (!w.sub_b) {
+			colA_iter<LGM>(a, fM, buf, group, gt, gt + 1);
+			// the item ended on a group barrier: every result is in the buffer.  Store it, and PUBLISH it as soon as its boxes
+			// are in global memory: the thread waits for the store here (the rest of the group is already at the next item;
+			// the pass waits on memory, not on this thread).  Publishing at once is what lets the panels be small enough for
+			// their scratch to stay in L2: a load then only ever waits for items at least two places back in its own CTA.
+			if (gt == 0) {
+				if (tr) a.trace[4 * it + 2] = gtimer();
+				fence_proxy_async();
+				col_store<LGM>(a, w, buf);
+				tma_commit();
+				tma_wait_all0();
+				if (tr) a.trace[4 * it + 3] = gtimer();
+				fence_proxy_async_all();                             // the boxes were written by the async proxy: order them before
+				__threadfence();                                     // the (generic-proxy) release of the counter
+				atomicAdd(a.done + w.q, 1);
+				if (more) col_issue<LGM>(a, seg_start, cta + (it + kRingBufs) * ncta, issue_cursor, buf, full + b);
 			}
-			fence_proxy_async();
-			col_store<LGM>(a, w, buf);
-			tma_commit();
+		} else {
+			const int blk = w.local / w.ntiles, tile = w.local - blk * w.ntiles;
+			colB_iter<LGM>(a, fN, buf, blk, w.col0 + 32 * tile, w.col0, w.q % kColRingScratch, w.plane, group, gt, gt + 1, [&]() {
+				if (gt != 0) return;
+				if (tr) a.trace[4 * it + 2] = -gtimer();                 // (negative: a sub-pass B item, stamp = buffer released)
+				atomicAdd(a.done + ColWork<LGM>::panels(a) + w.q, 1);     // the scratch rows of this item have been read
+				if (more) {
+					fence_proxy_async();
+					col_issue<LGM>(a, seg_start, cta + (it + kRingBufs) * ncta, issue_cursor, buf, full + b);
+				}
+			});
 		}
-		publish = (w.sub_b ? ColWork<LGM>::panels(a) : 0) + w.q;
-		if (it + kRingBufs < iters) refill_it = it;
-	}
-	if (gt == 0 && publish >= 0) {                              // shared memory must outlive the engine's reads; the last item counts too
-		tma_wait_all0();
-		__threadfence();
-		atomicAdd(a.done + publish, 1);
 	}
 }
 
@@ -429,7 +486,7 @@ static void colring_emulate(const ColRingArgs &a, int ncta) {
 		if (idx >= 0 && a.done[idx] < need) abort();           // launch order must satisfy the dependencies
 		col_load<LGM>(a, w, buf, (void *)nullptr);
 		if (!w.sub_b) colA_iter<LGM>(a, fM, buf, 0, 0, kRingGroupThreads);
-		else colB_iter<LGM>(a, fN, buf, w.local / w.ntiles, 0, 0, kRingGroupThreads);
+		else colB_iter<LGM>(a, fN, buf, (w.local / w.ntiles), w.col0 + 32 * (w.local % w.ntiles), w.col0, w.q % kColRingScratch, w.plane, 0, 0, kRingGroupThreads, []() {});
 		col_store<LGM>(a, w, buf);
 		a.done[(w.sub_b ? Q : 0) + w.q] += 1;
 	}

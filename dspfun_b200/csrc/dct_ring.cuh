@@ -192,6 +192,7 @@ DSP_DEV void ring_fwd_iter(const RingArgs &a, const RingFixed<LG> &f, C2<float> 
 			}
 		}
 	}
+	RING_PROXY_FENCE();
 	RING_SYNC(group);                                            // all slots read: the buffer may be refilled
 }
 
@@ -290,6 +291,7 @@ DSP_DEV void ring_inv_iter(const RingArgs &a, const RingFixed<LG> &f, C2<float> 
 			}
 		}
 	}
+	RING_PROXY_FENCE();
 	RING_SYNC(group);
 }
 

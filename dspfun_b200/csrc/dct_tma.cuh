@@ -106,6 +106,29 @@ DSP_DEV void tma_store4(const TmaDesc *map, const void *src, int c0, int c1, int
 	             "r"(c1), "r"(c2), "r"(c3)
 	             : "memory");
 }
+// L2 eviction-priority policies for the cache-hinted copies below
+DSP_DEV uint64_t l2_policy_evict_last() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+DSP_DEV uint64_t l2_policy_evict_first() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+DSP_DEV void tma_load4_hint(void *dst, const TmaDesc *map, int c0, int c1, int c2, int c3, uint64_t *bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(smem_u32(dst)),
+	             "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+	             : "memory");
+}
+DSP_DEV void tma_store4_hint(const TmaDesc *map, const void *src, int c0, int c1, int c2, int c3, uint64_t policy) {
+	asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+	             "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+	             : "memory");
+}
+// the 128-byte line at p (aligned) will not be read again before it is rewritten: the L2 may drop it without write-back
+DSP_DEV void discard_l2(const void *p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 DSP_DEV void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSP_DEV void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }    // sources of all groups read
 DSP_DEV void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // all groups complete
@@ -135,6 +158,20 @@ inline void tma_load3(void *dst, const TmaDesc *map, int c0, int c1, int c2, voi
 inline void tma_load4(void *dst, const TmaDesc *map, int c0, int c1, int c2, int c3, void *) { const int c[4] = {c0, c1, c2, c3}; tma_emu_copy(map, (float *)dst, c, true); }
 inline void tma_store3(const TmaDesc *map, const void *src, int c0, int c1, int c2) { const int c[4] = {c0, c1, c2, 0}; tma_emu_copy(map, (float *)src, c, false); }
 inline void tma_store4(const TmaDesc *map, const void *src, int c0, int c1, int c2, int c3) { const int c[4] = {c0, c1, c2, c3}; tma_emu_copy(map, (float *)src, c, false); }
+inline unsigned long long l2_policy_evict_last() { return 0; }
+inline unsigned long long l2_policy_evict_first() { return 0; }
+inline void tma_load4_hint(void *dst, const TmaDesc *map, int c0, int c1, int c2, int c3, void *bar, unsigned long long) { tma_load4(dst, map, c0, c1, c2, c3, bar); }
+inline void tma_store4_hint(const TmaDesc *map, const void *src, int c0, int c1, int c2, int c3, unsigned long long) { tma_store4(map, src, c0, c1, c2, c3); }
+#endif
+
+// Every thread that read or wrote a shared-memory buffer through the generic proxy runs this BEFORE the barrier after
+// which one thread hands the buffer to the copy engine (async proxy), for a refill or for a store: the barrier orders
+// the threads, the fence orders each thread's own accesses against the other proxy.  (A fence by the issuing thread
+// alone is not enough: measured as nondeterministic results of the column ring once the timing got tight.)
+#if DSP_GPU
+#define RING_PROXY_FENCE() fence_proxy_async()
+#else
+#define RING_PROXY_FENCE() ((void)0)
 #endif
 
 }  // namespace dsp

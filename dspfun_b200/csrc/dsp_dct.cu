@@ -529,7 +529,7 @@ static bool build_plan(dsp_dct_plan_s *P, int howmany, const int *inembed, int i
 					// ring sub-pass kernels (dct_colring.cuh): one launch walks all panels; three scratch panels in rotation
 					pp.rg_P = 0;
 					if (P->prec == 'f' && colring_supports(nn) && (A.ncols % 32) == 0 && (A.ax_is % 4) == 0 && (A.ax_os % 4) == 0 && !getenv("DSP_DCT_NO_COLRING")) {
-						const double mb = getenv("DSP_DCT_RING_PANEL_MB") ? atof(getenv("DSP_DCT_RING_PANEL_MB")) : 32.0;   // 512 items per segment at n = 8192: > 3 per CTA on 148 SMs
+						const double mb = getenv("DSP_DCT_RING_PANEL_MB") ? atof(getenv("DSP_DCT_RING_PANEL_MB")) : 24.0;   // measured best of 10 / 16 / 24 / 32 MB (profiles/r02_colring.md); >= one item per CTA per segment
 						long long rp = (long long)(mb * 1048576.0) / ((long long)nn * 4);
 						rp = (rp / 32) * 32;
 						if (rp < 32) rp = 32;
@@ -653,6 +653,14 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					e.args.twN = pp.ff.tw; e.args.omN = pp.ff.om; e.args.sigN = pp.ff.sig;
 					e.args.nplanes = np; e.args.ppp = ppp; e.args.P = pp.rg_P; e.args.ncols = c.ncols; e.args.reverse = 0;
 					e.args.done = P->d_ring_done;
+					e.args.scratch = (float *)P->d_split;
+					e.args.trace = nullptr;
+					e.args.flags = getenv("DSP_DCT_RING_NODISCARD") ? 1 : 0;
+					if (getenv("DSP_DCT_RING_TRACE")) {                       // debug: timeline of CTA 0 (leaked on purpose; read with cudaMemcpy by the tool)
+						void *tp = nullptr;
+						if (rt_malloc(&tp, 4 * 4096 * sizeof(long long), g_err)) { rt_zero(tp, 4 * 4096 * sizeof(long long), st, g_err); e.args.trace = (long long *)tp; fprintf(stderr, "[dsp_dct] ring trace buffer %p\n", tp); }
+					}
+					e.args.out = (float *)bout; e.args.ax_os = c.ax_os; e.args.plane_os = c.o.os[at];
 					if (ok) { if (pp.ring_maps.size() >= 64) pp.ring_maps.clear(); pp.ring_maps.push_back(e); rm = &pp.ring_maps.back(); }
 				}
 				if (ok) {

@@ -25,11 +25,11 @@ static bool colring_launch_t(const ColRingArgs &a, rt_stream st, std::string &er
 	const int Q = a.nplanes * a.ppp;
 	int minseg = 1 << 30;
 	for (int s = 0; s < 2 * Q; s++) { const int n = ColWork<LGM>::seg_items(a, s, Q); if (n < minseg) minseg = n; }
-	// The counters are free of cycles when every segment holds more than 3 items per CTA and B(q) does not follow A(q)
-	// directly (>= 2 panels): see colring_cta.
-	if (Q < 2 || minseg < 4) { err = "ring column pass needs at least two panels"; return false; }
+	// The counters are free of cycles when every segment holds at least one item of every CTA and B(q) does not follow
+	// A(q) directly (>= 2 panels): see colring_cta.
+	if (Q < 2 || minseg < 1) { err = "ring column pass needs at least two panels"; return false; }
 	const int sms = ring_sm_count();
-	int grid = (minseg - 1) / 3;
+	int grid = minseg;
 	if (grid > sms) grid = sms;
 #if DSP_GPU
 	const size_t smem = ColRingSmem<LGM>::kTotal;

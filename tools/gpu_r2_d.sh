@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_round2.py -x -q -k "ring_column" 2>&1 | tail -3
+for env in "DSP_DCT_RING_PANEL_MB=10" "DSP_DCT_RING_PANEL_MB=16" "DSP_DCT_RING_PANEL_MB=24" "DSP_DCT_RING_PANEL_MB=32"; do
+  echo "== plane8192 $env"
+  env $env timeout 300 python bench.py --workload plane8192 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roundtrip_rel_l2'], [ (k['plan'],k['kernel'],round(k['avg_ms'],4), round(k['achieved_gbs'])) for k in d['kernels']])"
+done
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:k_col_ring -s 3 -c 1 python bench.py --workload plane8192 --steps 1 --warmup 3 --no-cpu --no-e2e 2>&1 | grep -E "k_col_ring|gpu__time|dram__|hit_rate"
