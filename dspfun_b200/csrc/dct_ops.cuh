@@ -47,6 +47,8 @@ struct OpAny {
 	const void *aux_c;       // OP_SPEC: double[8] device scalars {scale_z[4], -, -, -, -};  OP_ISPEC: u8 signmap;  OP_SCAN_MASK: int32 index map
 	void *aux;               // OP_ACCUM_DC: double[4] accumulators;  OP_SPEC: double[4] DC out;  OP_SCAN_ACCUM: T sum buffer
 
+	int fast;                // OP_MOTION_COEFF: no threshold / preserve-dc / quantiser -> the OpMotionCoeff functor serves it
+	double nf[4], rnf[4];    // OP_MOTION_COEFF: 2 sqrt2 / sqrt2^k and its reciprocal, k = number of zero coordinates
 	// Not inlined on the GPU: the unrolled passes call it per element, and dozens of inlined copies of this switch
 	// overflow the instruction cache (measured: "no instruction" became the top stall of the fused kernels).
 	template <class T> DSP_OPANY_ATTR T operator()(T v, const Coord &c) const {
@@ -166,6 +168,53 @@ struct OpAny {
 		}
 		}
 	}
+};
+
+// ---- motion's two hot stages as small functors of their own: kernels instantiated for them carry a few dozen
+// instructions per element instead of OpAny's whole switch (ncu r02 on the 256-frame volume: the OpAny instantiation of
+// the temporal pass ran 5x the instructions of the plain one and stalled on instruction fetch).
+// OP_MOTION_COEFF without threshold / preserve-dc / quantiser (OpAny::fast): normalise, damp | boost, de-normalise.
+struct OpMotionCoeff {
+	enum { kNeedsCoord = 1 };
+	int a3[3], b3[3], e3[3];
+	int w, lo;                   // > 0: flat coordinates (see OpAny)
+	float m0, m1;                // damp (outside the band-pass box), boost (inside)
+	double nf0, nf1, nf2, nf3, rnf0, rnf1, rnf2, rnf3;
+	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+		typedef double I;
+		int z = c.i0, y = c.i1, x = c.i2;
+		if (w > 0) {
+			const int hw = lo + c.ch;
+			z = c.i2; y = hw / w; x = hw - y * w;
+		}
+		if (z >= a3[0] || y >= a3[1] || x >= a3[2]) return (T)0;                                     // motion.c:617
+		const int k = (x == 0) + (y == 0) + (z == 0);
+		const I nf = k == 0 ? nf0 : (k == 1 ? nf1 : (k == 2 ? nf2 : nf3)), rnf = k == 0 ? rnf0 : (k == 1 ? rnf1 : (k == 2 ? rnf2 : rnf3));
+		T f = (T)((I)v * nf);                                                                        // :644-647
+		const bool inside = z >= b3[0] && z < e3[0] && y >= b3[1] && y < e3[1] && x >= b3[2] && x < e3[2];
+		f = f * (T)(inside ? m1 : m0);                                                               // :683-719
+		return (T)((I)f * rnf);                                                                      // :748-751
+	}
+	static OpMotionCoeff from(const OpAny &o) {
+		OpMotionCoeff r;
+		for (int i = 0; i < 3; i++) { r.a3[i] = o.a3[i]; r.b3[i] = o.b3[i]; r.e3[i] = o.e3[i]; }
+		r.w = o.w; r.lo = o.lo; r.m0 = (float)o.m[0]; r.m1 = (float)o.m[1];
+		r.nf0 = o.nf[0]; r.nf1 = o.nf[1]; r.nf2 = o.nf[2]; r.nf3 = o.nf[3];
+		r.rnf0 = o.rnf[0]; r.rnf1 = o.rnf[1]; r.rnf2 = o.rnf[2]; r.rnf3 = o.rnf[3];
+		return r;
+	}
+};
+// OP_MOTION_STORE: scale, clamp, round to the 8-bit range (or float pels / 255)
+struct OpMotionStore {
+	enum { kNeedsCoord = 0 };
+	double scale;
+	int float_pixels;
+	template <class T> DSP_DEVM T operator()(T v, const Coord &) const {
+		const double pel = (double)v * scale;                                                        // motion.c:757,767
+		if (float_pixels) return (T)(pel / 255.0);                                                   // :773
+		return (T)(pel > 255.0 ? 255.0 : pel < 0.0 ? 0.0 : (double)lround(pel));                     // :776
+	}
+	static OpMotionStore from(const OpAny &o) { OpMotionStore r; r.scale = o.m[6]; r.float_pixels = o.flag2; return r; }
 };
 
 // Resolves spec's data-dependent range (spec/spec.c:92-117) once the row pass has accumulated the per-channel

@@ -1458,6 +1458,15 @@ int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsig
 	op.m[5] = 127.5 / (norm * norm * scalefactor);                                           // motion.c:736
 	op.flag = mp->preserve_dc;
 	op.aux = d_counter;
+	op.fast = (mp->threshold_max == 0.0 && mp->preserve_dc == 0 && mp->quant == 0.0) ? 1 : 0;
+	for (int k = 0; k < 4; k++) {
+		const double s2 = 1.41421356237309504880168872420969808;
+		double prod = 1.0;
+		for (int q = 0; q < k; q++) prod *= s2;                                              // the reference multiplies the three factors
+		op.nf[k] = (2 * s2) / prod;                                                          // motion.c:647
+		op.rnf[k] = 1.0 / op.nf[k];
+	}
+	if (getenv("DSP_DCT_NO_FAST_OPS")) op.fast = 0;
 	// flat_w > 0: the plan is the temporal pass of a slab-sharded volume over a [D][hw-slice] array -- the axis index is
 	// z and (y, x) come from the flattened column index: hw = flat_base + column, y = hw / flat_w, x = hw % flat_w
 	op.w = flat_w; op.lo = (int)flat_base;

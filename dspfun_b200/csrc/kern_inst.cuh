@@ -119,6 +119,25 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 		return false;
 	}
 #else
+	// motion's hot stages on their own small functors (dct_ops.cuh), float only
+	if constexpr (sizeof(KERN_T) == 4) if (fused && !getenv("DSP_DCT_NO_FAST_OPS")) {
+		const bool lplain = lop.kind == OP_NONE || lop.kind == OP_SCALE, splain = sop.kind == OP_NONE || sop.kind == OP_SCALE;
+		const bool fw = a.kind == DSP_KIND_REDFT10;
+#if KERN_FAST
+#define DSP_OPS_LAUNCH(L, S, l, s) (fw ? launch_t<KERN_T, KERN_ROW, 3, L, S>(a, f, l, s, grid, block, smem, st, err) : launch_t<KERN_T, KERN_ROW, 1, L, S>(a, f, l, s, grid, block, smem, st, err))
+#else
+#define DSP_OPS_LAUNCH(L, S, l, s) launch_t<KERN_T, KERN_ROW, 0, L, S>(a, f, l, s, grid, block, smem, st, err)
+#endif
+		(void)fw;
+#if !KERN_ROW
+		if (lop.kind == OP_MOTION_COEFF && lop.fast && splain) return DSP_OPS_LAUNCH(OpMotionCoeff, OpMul<KERN_T>, OpMotionCoeff::from(lop), sm);
+		if (sop.kind == OP_MOTION_COEFF && sop.fast && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpMotionCoeff, lm, OpMotionCoeff::from(sop));
+#else
+		if (sop.kind == OP_MOTION_STORE && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpMotionStore, lm, OpMotionStore::from(sop));
+#endif
+#undef DSP_OPS_LAUNCH
+		(void)lplain; (void)splain;
+	}
 #if KERN_FAST
 	// lean kernels with the length fixed at compile time for the common sizes (float only: FastFixed pads like float)
 	if (!fused && sizeof(KERN_T) == 4 && !getenv("DSP_DCT_NO_FIXED")) {

@@ -58,3 +58,33 @@ def test_unmodified_reference_tools_on_emulated_kernels(prec, preset, tmp_path):
 @pytest.mark.parametrize("preset", ["shift", "flat", "copy"])
 def test_unmodified_reference_tools_on_gpu(prec, preset, tmp_path):
     _run_chain("gpu", prec, preset, tmp_path)
+
+
+def _run_draw(kind, prec, tmp_path):
+    """applybasis/draw.c (call site P8, fftw_plan_r2r_2d REDFT01 x REDFT01 on a planar canvas): the unmodified tool's
+    canvas == DC/2 + sum of the requested cosine components, by the definition of REDFT01"""
+    out = str(tmp_path / "canvas.dspraw")
+    w, h = 96, 64
+    comps = [(3, 5, 0.25), (0, 7, 0.125), (10, 0, 0.2)]
+    args = [_tool("draw_%s_%s" % (kind, prec)), "-b", "%dx%d" % (w, h)]
+    for x, y, s in comps:
+        args += ["-f", "%dx%d:%g" % (x, y, s)]
+    subprocess.run(args + [out], check=True)
+    img, _ = dspraw.read(out)
+    coefs = np.zeros((h, w))
+    for x, y, s in comps:
+        coefs[y, x] = s / 4                                       # draw.c:69
+    coefs[0, 0] += 0.5                                             # draw.c:70
+    ref = od.dctn_def(coefs, [od.REDFT01, od.REDFT01])
+    assert od.rel_l2(img[:, :, 0], ref) < (1e-5 if prec == "f" else 1e-12)
+
+
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_unmodified_draw_on_emulated_kernels(prec, tmp_path):
+    _run_draw("emu", prec, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f", "d"])
+def test_unmodified_draw_on_gpu(prec, tmp_path):
+    _run_draw("gpu", prec, tmp_path)
