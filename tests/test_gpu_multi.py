@@ -69,3 +69,61 @@ def test_peer_fused_exchange_world2(shape):
     for rank, peer, nccl, same in res:
         assert max(peer) < 1e-5 and max(nccl) < 1e-5, (rank, peer, nccl)
         assert same, "peer-fused and NCCL exchanges must give identical coefficients"
+
+
+def _motion_worker(rank, world, port, dims, filt, mode, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dspfun_b200.dist3d import Dist3D, motion_params
+        D, H, W = dims
+        vol = np.random.default_rng(21).integers(96, 160, dims).astype(np.uint8)
+        d3 = Dist3D(D, H, W, prec="f", exchange=mode, motion=motion_params(dims, **filt))
+        Dl = D // world
+        pels = torch.from_numpy(vol[rank * Dl:(rank + 1) * Dl].copy()).cuda()
+        out = d3.process(pels)
+        out2 = d3.process(pels)                                   # symmetric buffers reused
+        torch.cuda.synchronize()
+        dist.barrier()
+        q.put((rank, d3.mode, out.cpu().numpy().copy(), bool(torch.equal(out, out2))))
+        d3.destroy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+@pytest.mark.parametrize("filt", [dict(), dict(damp=0.0, bandpass=((0, 0, 0), (8, 68, 120)))])
+def test_motion_volume_u8_world2(mode, filt):
+    """motion -b 0x0x0 on two GPUs, 8-bit pels in and out (fused pel load, coefficient stage on the temporal pass with flat
+    coordinates, pel store): no filter reproduces the source exactly; the low-pass box == the oracle's block loop"""
+    import torch
+    import torch.multiprocessing as mp
+    from oracle import pipelines as op
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dims = (16, 136, 240)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_motion_worker, args=(r, 2, port, dims, filt, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] == mode and r[3] for r in res)
+    got = np.concatenate([r[2] for r in res])
+    vol = np.random.default_rng(21).integers(96, 160, dims).astype(np.uint8)
+    if not filt:
+        assert np.array_equal(got, vol)
+        return
+    want, _, pel = op.motion_block(vol, dims, **filt)
+    diff = got.astype(np.int64) != want.astype(np.int64)
+    if diff.any():
+        assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
+        frac = np.abs(pel.astype(np.float64))
+        assert (np.abs(frac - np.floor(frac) - 0.5)[diff] < 2e-3).all()
