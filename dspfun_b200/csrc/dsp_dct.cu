@@ -1204,6 +1204,19 @@ int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *co
 	if (l.row || l.split || p->prec != 'f') { g_err = "segmented output needs a float plan whose last pass is a one-kernel strided-axis pass"; return 1; }
 	ColArgs &c = l.ca;
 	if (c.f.n != nseg * seg_rows) { g_err = "segments must tile the last axis exactly"; return 1; }
+	// the segmented store moves whole tiles: narrow the tile until it divides the columns (short axes get wide tiles,
+	// e.g. 256 columns at n = 32, which need not divide a slab's h*w / G columns)
+	if ((c.tc % 4) == 0 && (c.ncols % 4) == 0 && (c.ncols % c.tc) != 0) {
+		const size_t seqb = l.smem / (size_t)((c.tc + 1) / 2);
+		long long no = 1;
+		for (int k = 0; k < 4; k++) no *= c.o.cnt[k];
+		while (c.tc > 4 && (c.ncols % c.tc) != 0) c.tc /= 2;
+		c.ntiles = c.ncols / c.tc;
+		c.dtiles = mk_fd((uint32_t)c.ntiles);
+		l.grid = (int)((long long)c.ntiles * no);
+		l.smem = (size_t)(c.tc / 2) * seqb;
+		if (l.pf_dist >= l.grid) l.pf_dist = 0;
+	}
 	const int gpr = c.tc / 4;
 	if ((c.tc % 4) || (gpr & (gpr - 1)) || (l.block % gpr) || (c.ncols % c.tc) || !l.vec_in_layout || !l.vec_out_layout || c.f.dense || l.fused) {
 		g_err = "segmented output needs full, 16-byte aligned column tiles and no fused stage";
