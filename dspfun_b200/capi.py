@@ -53,7 +53,7 @@ class MotionParams(ctypes.Structure):
     _fields_ = [("block", ctypes.c_int * 3), ("scaled", ctypes.c_int * 3), ("float_pixels", ctypes.c_int),
                 ("damp", ctypes.c_double), ("boost", ctypes.c_double), ("bp_begin", ctypes.c_int * 3),
                 ("bp_end", ctypes.c_int * 3), ("threshold_min", ctypes.c_double), ("threshold_max", ctypes.c_double),
-                ("quant", ctypes.c_double), ("preserve_dc", ctypes.c_int)]
+                ("quant", ctypes.c_double), ("preserve_dc", ctypes.c_int), ("spec", ctypes.c_int), ("ispec", ctypes.c_int)]
 
 
 class ZoomParams(ctypes.Structure):

@@ -47,6 +47,7 @@ struct OpAny {
 	const void *aux_c;       // OP_SPEC: double[8] device scalars {scale_z[4], -, -, -, -};  OP_ISPEC: u8 signmap;  OP_SCAN_MASK: int32 index map
 	void *aux;               // OP_ACCUM_DC: double[4] accumulators;  OP_SPEC: double[4] DC out;  OP_SCAN_ACCUM: T sum buffer
 
+	int skipn, skipd;        // OP_MOTION_COEFF: skip the normalisation (motion --ispec input: motion.c:639) / the de-normalisation (--spec output: :746)
 	int fast;                // OP_MOTION_COEFF: no threshold / preserve-dc / quantiser -> the OpMotionCoeff functor serves it
 	double nf[4], rnf[4];    // OP_MOTION_COEFF: 2 sqrt2 / sqrt2^k and its reciprocal, k = number of zero coordinates
 	// Not inlined on the GPU: the unrolled passes call it per element, and dozens of inlined copies of this switch
@@ -127,7 +128,7 @@ struct OpAny {
 			}
 			if (z >= a3[0] || y >= a3[1] || x >= a3[2]) return (T)0;                                 // outside the active box: motion.c:617
 			const I nf = (2 * SQRT2) / ((x ? 1.0 : SQRT2) * (y ? 1.0 : SQRT2) * (z ? 1.0 : SQRT2));
-			T f = (T)((I)v * nf);                                                                    // :644-647
+			T f = skipn ? v : (T)((I)v * nf);                                                        // :644-647 (not with --ispec)
 			const T dc0 = f;
 			const bool inside = z >= b3[0] && z < e3[0] && y >= b3[1] && y < e3[1] && x >= b3[2] && x < e3[2];
 			if (!inside) { if (m[0] != 1.0) f = f * (T)m[0]; }                                       // :683-713
@@ -153,7 +154,7 @@ struct OpAny {
 #endif
 				}
 			}
-			return (T)((I)f / nf);                                                                   // :748-751
+			return skipd ? f : (T)((I)f / nf);                                                       // :748-751 (not with --spec)
 		}
 		case OP_MOTION_STORE: {
 			const I pel = (I)v * m[6];                                                               // :757,767
@@ -199,7 +200,7 @@ struct OpMotionCoeff {
 		OpMotionCoeff r;
 		for (int i = 0; i < 3; i++) { r.a3[i] = o.a3[i]; r.b3[i] = o.b3[i]; r.e3[i] = o.e3[i]; }
 		r.w = o.w; r.lo = o.lo; r.m0 = (float)o.m[0]; r.m1 = (float)o.m[1];
-		r.nf0 = o.nf[0]; r.nf1 = o.nf[1]; r.nf2 = o.nf[2]; r.nf3 = o.nf[3];
+		r.nf0 = o.skipn ? 1.0 : o.nf[0]; r.nf1 = o.skipn ? 1.0 : o.nf[1]; r.nf2 = o.skipn ? 1.0 : o.nf[2]; r.nf3 = o.skipn ? 1.0 : o.nf[3];   // (x 1.0 is exact)
 		r.rnf0 = o.rnf[0]; r.rnf1 = o.rnf[1]; r.rnf2 = o.rnf[2]; r.rnf3 = o.rnf[3];
 		return r;
 	}

@@ -1471,7 +1471,8 @@ int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsig
 	op.m[5] = 127.5 / (norm * norm * scalefactor);                                           // motion.c:736
 	op.flag = mp->preserve_dc;
 	op.aux = d_counter;
-	op.fast = (mp->threshold_max == 0.0 && mp->preserve_dc == 0 && mp->quant == 0.0) ? 1 : 0;
+	op.skipn = mp->ispec != 0; op.skipd = mp->spec != 0;
+	op.fast = (mp->threshold_max == 0.0 && mp->preserve_dc == 0 && mp->quant == 0.0 && !op.skipd) ? 1 : 0;
 	for (int k = 0; k < 4; k++) {
 		const double s2 = 1.41421356237309504880168872420969808;
 		double prod = 1.0;
@@ -1533,6 +1534,7 @@ struct dsp_motion_s {
 	void *d_coeffs;                 // T [minbuf]: zero outside the block box for the life of the session
 	void *d_in, *d_out;             // staging for the host entry
 	unsigned long long *d_counter;
+	MotionSpecArgs sp_in, sp_out;   // --ispec / --spec stages
 };
 
 static void motion_free(dsp_motion_s *m) {
@@ -1566,8 +1568,10 @@ dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp) {
 	bool ok = rt_init(g_err) && rt_malloc(&m->d_coeffs, m->coeff_bytes, g_err) && rt_zero(m->d_coeffs, m->coeff_bytes, 0, g_err) &&
 	          rt_malloc((void **)&m->d_counter, sizeof(unsigned long long), g_err) && rt_zero(m->d_counter, sizeof(unsigned long long), 0, g_err) &&
 	          rt_sync(0, g_err);
+	if (ok && (mp->spec < 0 || mp->spec > 4 || mp->ispec < 0 || mp->ispec > 4 || mp->ispec == DSP_MOTION_SPEC_ABS)) { g_err = "bad motion spectrogram type"; ok = false; }
 	if (ok) {
 		// motion.c:535-538 / :549-552: both plans address their box inside the same minbuf-sized buffer
+		// (a plan that --ispec / --spec replaces is still built: its coefficient stage descriptor is taken from it)
 		m->fwd = dsp_dct_plan_many(prec, 3, mp->block, 1, nullptr, m->minbuf, 1, 0, nullptr, m->minbuf, 1, 0, k10, 0);
 		m->inv = m->fwd ? dsp_dct_plan_many(prec, 3, mp->scaled, 1, nullptr, m->minbuf, 1, 0, nullptr, m->minbuf, 1, 0, k01, 0) : nullptr;
 		ok = m->fwd && m->inv;
@@ -1575,6 +1579,19 @@ dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp) {
 	if (ok)
 		ok = dsp_dct_fuse_pel_load(m->fwd, mp->float_pixels) == 0 &&
 		     dsp_dct_fuse_motion_coeff(m->inv, mp, m->d_counter, 0, 0) == 0 && dsp_dct_fuse_pel_store(m->inv, mp) == 0;
+	if (ok && (mp->spec || mp->ispec)) {
+		double sf, norm;
+		motion_constants(mp, sf, norm);
+		MotionSpecArgs a;
+		memset(&a, 0, sizeof(a));
+		a.md = m->minbuf[0]; a.mh = m->minbuf[1]; a.mw = m->minbuf[2];
+		a.float_pixels = mp->float_pixels;
+		a.norm = norm; a.sf = sf;
+		a.c = 127.5 / log1p((double)mp->scaled[2] * mp->scaled[1] * mp->scaled[0] * norm * 255 * 8);      // motion.c:568-569
+		a.coeff = m->inv->passes.front().lop;
+		m->sp_in = a; m->sp_in.type = mp->ispec; m->sp_in.bd = mp->block[0]; m->sp_in.bh = mp->block[1]; m->sp_in.bw = mp->block[2];
+		m->sp_out = a; m->sp_out.type = mp->spec; m->sp_out.bd = mp->scaled[0]; m->sp_out.bh = mp->scaled[1]; m->sp_out.bw = mp->scaled[2];
+	}
 	if (!ok) { motion_free(m); return nullptr; }
 	return m;
 }
@@ -1583,7 +1600,15 @@ int dsp_motion_block_dev(dsp_motion m, const void *d_pels_in, void *d_pels_out, 
 	g_err.clear();
 	if (!m || !d_pels_in || !d_pels_out) { g_err = "null motion session or buffer"; return 1; }
 	// forward: pels -> coefficients (block box of the zero-initialised buffer); inverse: coefficients -> pels
-	if (dsp_dct_execute_dev(m->fwd, (void *)d_pels_in, m->d_coeffs, stream) != 0) return 1;
+	if (m->mp.ispec) {
+		if (!launch_motion_ispec(m->prec, m->sp_in, d_pels_in, m->d_coeffs, (rt_stream)stream, g_err)) return 1;
+		g_launches++;
+	} else if (dsp_dct_execute_dev(m->fwd, (void *)d_pels_in, m->d_coeffs, stream) != 0) return 1;
+	if (m->mp.spec) {
+		if (!launch_motion_spec(m->prec, m->sp_out, m->d_coeffs, d_pels_out, (rt_stream)stream, g_err)) return 1;
+		g_launches++;
+		return 0;
+	}
 	return dsp_dct_execute_dev(m->inv, m->d_coeffs, d_pels_out, stream);
 }
 

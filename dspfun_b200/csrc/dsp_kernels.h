@@ -47,6 +47,20 @@ bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int 
                         unsigned long long *count, rt_stream st, std::string &err);
 bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err);
 
+// pointwise spectrogram stages of motion (kern_misc.cu)
+struct MotionSpecArgs {
+	int md, mh, mw;              // padded box (minbuf)
+	int bd, bh, bw;              // box the kernel covers: the block (ispec) or the scaled block (spec)
+	int type;                    // DSP_MOTION_SPEC_*
+	int float_pixels;
+	double norm, sf;             // motion.c:567, :566
+	double c;                    // shift: 127.5 / log1p(sw sh sd norm 255 8)  (:568-569)
+	OpAny coeff;                 // spec: the coefficient stages (OP_MOTION_COEFF with skipd), run here instead of in an inverse pass
+};
+
+bool launch_motion_ispec(char prec, const MotionSpecArgs &a, const void *pels, void *coeffs, rt_stream st, std::string &err);
+bool launch_motion_spec(char prec, const MotionSpecArgs &a, const void *coeffs, void *pels, rt_stream st, std::string &err);
+
 struct SplitArgs;
 bool launch_split_fft_f32(const SplitArgs &a, const FastDesc &fM, bool fused, const OpAny &lop, const OpAny &sop, int grid, size_t smem,
                           rt_stream st, std::string &err);

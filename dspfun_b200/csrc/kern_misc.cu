@@ -140,4 +140,109 @@ bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, l
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------ motion spectrograms
+// motion --ispec: the pels ARE a spectrogram; they become coefficients without a forward transform (motion.c:627-637).
+// motion --spec : the coefficients are written out as a spectrogram instead of being inverted (motion.c:755-776).
+// Both are pointwise over the block's padded box [md][mh][mw]; layouts and rounding points as in the reference.
+template <class T>
+DSP_DEV T motion_ispec_elem(const MotionSpecArgs &a, double pel) {
+	typedef double I;
+	switch (a.type) {
+	case 2: pel = copysign(expm1(fabs((pel - 127.5) / a.c)), pel - 127.5) / a.norm; break;            // shift  :628
+	case 3: pel = (pel - 127.5) * 2 / a.norm / a.norm; break;                                         // flat   :629
+	case 4: pel = pel / a.norm / a.norm; break;                                                       // copy   :630
+	default: break;
+	}
+	return (T)(I)pel;
+}
+
+template <class T>
+DSP_DEV double motion_spec_elem(const MotionSpecArgs &a, T coeff, double cabs) {
+	double pel = (double)coeff * a.sf * a.norm;                                                       // :757
+	switch (a.type) {
+	case 1: pel = cabs * log1p(fabs(pel)); break;                                                     // abs    :760
+	case 2: pel = a.c * copysign(log1p(fabs(pel)), pel) + 127.5; break;                               // shift  :761
+	case 3: pel = pel * a.norm / 2 + 127.5; break;                                                    // flat   :762
+	default: pel *= a.norm; break;                                                                    // copy   :764-765
+	}
+	return pel;
+}
+
+template <class T>
+DSP_DEV void motion_ispec_at(const MotionSpecArgs &a, const void *pels, T *coeffs, long long i) {
+	const long long row = i / a.mw;
+	const int x = (int)(i - row * a.mw), y = (int)(row % a.mh), z = (int)(row / a.mh);
+	if (z >= a.bd || y >= a.bh || x >= a.bw) { coeffs[i] = (T)0; return; }                            // :617 memset
+	const double pel = a.float_pixels ? (double)((const float *)pels)[i] * 255 : (double)((const unsigned char *)pels)[i];   // :621-624
+	coeffs[i] = motion_ispec_elem<T>(a, pel);
+}
+
+template <class T>
+DSP_DEV void motion_spec_at(const MotionSpecArgs &a, const T *coeffs, void *pels, long long i, double cabs) {
+	const long long row = i / a.mw;
+	const int x = (int)(i - row * a.mw), y = (int)(row % a.mh), z = (int)(row / a.mh);
+	if (z >= a.bd || y >= a.bh || x >= a.bw) return;                                                  // outside the scaled box: pels stay
+	const Coord c = {z, y, x, 0, 0};
+	const T f = a.coeff.template operator()<T>(coeffs[i], c);                                         // zero outside the active box, filters, quantiser
+	const double pel = motion_spec_elem<T>(a, f, cabs);
+	if (a.float_pixels) ((float *)pels)[i] = (float)(pel / 255);                                      // :773
+	else ((unsigned char *)pels)[i] = (unsigned char)(pel > 255.0 ? 255.0 : pel < 0.0 ? 0.0 : (double)lround(pel));   // :776
+}
+
+// c of --spec abs: 255 / log1p(|dc sf norm|), dc = the block's (normalised, unfiltered) DC coefficient (:649, :754)
+template <class T>
+DSP_DEV double motion_spec_cabs(const MotionSpecArgs &a, const T *coeffs) {
+	if (a.type != 1) return 0.0;
+	T dc = coeffs[0];
+	if (!a.coeff.skipn) dc = (T)((double)dc * a.coeff.nf[3]);                                         // :644-647 at x = y = z = 0
+	return 255.0 / log1p(fabs((double)dc * a.sf * a.norm));
+}
+
+#if DSP_GPU
+template <class T> __global__ void k_motion_ispec(MotionSpecArgs a, const void *pels, T *coeffs) {
+	const long long n = (long long)a.md * a.mh * a.mw;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) motion_ispec_at<T>(a, pels, coeffs, i);
+}
+template <class T> __global__ void k_motion_spec(MotionSpecArgs a, const T *coeffs, void *pels) {
+	const long long n = (long long)a.md * a.mh * a.mw;
+	const double cabs = motion_spec_cabs<T>(a, coeffs);
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) motion_spec_at<T>(a, coeffs, pels, i, cabs);
+}
+#endif
+
+bool launch_motion_ispec(char prec, const MotionSpecArgs &a, const void *pels, void *coeffs, rt_stream st, std::string &err) {
+	const long long n = (long long)a.md * a.mh * a.mw;
+#if DSP_GPU
+	long long g = (n + 255) / 256;
+	const int grid = (int)(g < 148 * 16 ? g : 148 * 16);
+	if (prec == 'f') k_motion_ispec<float><<<grid, 256, 0, st>>>(a, pels, (float *)coeffs);
+	else k_motion_ispec<double><<<grid, 256, 0, st>>>(a, pels, (double *)coeffs);
+	return rt_ok(cudaGetLastError(), err, "motion ispec launch");
+#else
+	(void)st; (void)err;
+	for (long long i = 0; i < n; i++) {
+		if (prec == 'f') motion_ispec_at<float>(a, pels, (float *)coeffs, i); else motion_ispec_at<double>(a, pels, (double *)coeffs, i);
+	}
+	return true;
+#endif
+}
+
+bool launch_motion_spec(char prec, const MotionSpecArgs &a, const void *coeffs, void *pels, rt_stream st, std::string &err) {
+	const long long n = (long long)a.md * a.mh * a.mw;
+#if DSP_GPU
+	long long g = (n + 255) / 256;
+	const int grid = (int)(g < 148 * 16 ? g : 148 * 16);
+	if (prec == 'f') k_motion_spec<float><<<grid, 256, 0, st>>>(a, (const float *)coeffs, pels);
+	else k_motion_spec<double><<<grid, 256, 0, st>>>(a, (const double *)coeffs, pels);
+	return rt_ok(cudaGetLastError(), err, "motion spec launch");
+#else
+	(void)st; (void)err;
+	const double cabs = prec == 'f' ? motion_spec_cabs<float>(a, (const float *)coeffs) : motion_spec_cabs<double>(a, (const double *)coeffs);
+	for (long long i = 0; i < n; i++) {
+		if (prec == 'f') motion_spec_at<float>(a, (const float *)coeffs, pels, i, cabs); else motion_spec_at<double>(a, (const double *)coeffs, pels, i, cabs);
+	}
+	return true;
+#endif
+}
+
 }  // namespace dsp

@@ -13,11 +13,17 @@ import numpy as np
 from . import capi
 
 PRESERVE_DC = {None: 0, "none": 0, "dc": 1, "grey": 2}
+SPEC = {None: 0, "none": 0, "abs": 1, "shift": 2, "flat": 3, "copy": 4}          # motion --spec / --ispec TYPE
 
 
 class Motion:
     def __init__(self, block, scaled=None, float_pixels=False, damp=1.0, boost=1.0, bandpass=None, threshold=(0.0, 0.0),
-                 quant=0.0, preserve_dc=None, prec="f", lib=None):
+                 quant=0.0, preserve_dc=None, spec=None, ispec=None, prec="f", lib=None, coeff_limit=0, expr=None, dither=False,
+                 linear=False):
+        if coeff_limit or expr or dither or linear:
+            # sequential / host-side stages of the reference (repeated qsort, FFmpeg's expression VM, Floyd-Steinberg error
+            # diffusion, libavutil transfer curves): not part of the GPU path, refused rather than silently ignored
+            raise capi.DspDctError("motion: --coeff-limit, --eval, --dither and --linear are not supported on the GPU path")
         self.lib = lib if lib is not None else capi.load()
         self.block = tuple(int(v) for v in block)
         self.scaled = tuple(int(v) for v in (scaled if scaled is not None else block))
@@ -33,6 +39,7 @@ class Motion:
         mp.threshold_min, mp.threshold_max = float(threshold[0]), float(threshold[1])
         mp.quant = float(quant)
         mp.preserve_dc = PRESERVE_DC[preserve_dc]
+        mp.spec, mp.ispec = SPEC[spec], SPEC[ispec]
         self.float_pixels = bool(float_pixels)
         self.coeffs_coded = 0
         self._h = self.lib.dsp_motion_create(prec.encode(), ctypes.byref(mp))

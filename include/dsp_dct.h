@@ -181,8 +181,10 @@ void dsp_scan_destroy(dsp_scan s);
  * same padded box, so scaled != block resamples by spectral zero-pad / crop.  Fused: 8-bit load in the first pass
  * of the forward transform; zero-pad/crop + normalise + band-pass + threshold + preserve-dc + quantise +
  * de-normalise in the first pass of the inverse; scale + clamp + lround + 8-bit store in its last pass.
- * Not covered (host-side / sequential in the reference): --coeff-limit, --eval, --dither, spectrogram in/out modes,
- * linear-light transfer curves.  All dims are (d, h, w). */
+ * Spectrogram output / input (--spec / --ispec) run as one pointwise kernel in place of the inverse / forward transform.
+ * Not covered, rejected by the host mirror (sequential or host-side in the reference): --coeff-limit (repeated qsort),
+ * --eval (FFmpeg expression VM), --dither (Floyd-Steinberg error diffusion), linear-light transfer curves (libavutil).
+ * All dims are (d, h, w). */
 typedef struct {
 	int block[3], scaled[3];
 	int float_pixels;             /* 0: 8-bit pels; 1: float32 pels in [0,1] (motion.c:621-624, 773) */
@@ -191,7 +193,12 @@ typedef struct {
 	double threshold_min, threshold_max;   /* as given on the command line; max == 0 = off */
 	double quant;                 /* 0 = off */
 	int preserve_dc;              /* 0 none, 1 dc, 2 grey */
+	int spec;                     /* --spec:  write the (filtered) coefficients out as a spectrogram instead of inverting them
+	                                 (motion.c:755-776): 0 none, 1 abs, 2 shift, 3 flat, 4 copy */
+	int ispec;                    /* --ispec: the pels are a spectrogram, no forward transform (motion.c:627-637):
+	                                 0 none, 2 shift, 3 flat, 4 copy */
 } dsp_motion_params;
+enum { DSP_MOTION_SPEC_NONE = 0, DSP_MOTION_SPEC_ABS = 1, DSP_MOTION_SPEC_SHIFT = 2, DSP_MOTION_SPEC_FLAT = 3, DSP_MOTION_SPEC_COPY = 4 };
 typedef struct dsp_motion_s *dsp_motion;
 dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp);
 

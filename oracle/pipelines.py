@@ -165,8 +165,9 @@ def scan_frames(pixels, index_map, step=1, nframes=None, fast=False):
 
 
 def motion_block(pels, block, scaled=None, damp=1.0, boost=1.0, bandpass=None, threshold=(0.0, 0.0), quant=0.0,
-                 preserve_dc=None, coeff=np.float32, intermediate=np.float64, fast=True):
-    """motion/motion.c:617-788 for one plane block with spec/ispec/linear/dither/coeff-limit/eval off.
+                 preserve_dc=None, coeff=np.float32, intermediate=np.float64, fast=True, spec=None, ispec=None):
+    """motion/motion.c:617-788 for one plane block with linear/dither/coeff-limit/eval off.
+    spec / ispec: None | "abs" (spec only) | "shift" | "flat" | "copy" (motion.c:627-637, 755-766).
     pels: staging block [minbuf.d][minbuf.h][minbuf.w], uint8 or float32.  Sizes are (d, h, w).
     Returns (processed block, coefficients coded)."""
     C, I = coeff, intermediate
@@ -185,12 +186,23 @@ def motion_block(pels, block, scaled=None, damp=1.0, boost=1.0, bandpass=None, t
     ssl = tuple(slice(0, v) for v in scaled)
     coeffs = np.zeros(minbuf, dtype=C)                                                        # :617
     src = pels[bsl].astype(I)
-    coeffs[bsl] = (src * 255 if float_pixels else src).astype(C)                              # :618-637
-    coeffs[bsl] = (odct.dctn_fast(coeffs[bsl], [odct.REDFT10] * 3) if fast else odct.dctn_def(coeffs[bsl], [odct.REDFT10] * 3)).astype(C)   # :641
+    pel_in = src * 255 if float_pixels else src                                               # :618-624
+    cshift = I(127.5) / np.log1p(I(scaled[0] * scaled[1] * scaled[2]) * norm * 255 * 8)       # :568-569 (c[i] and ic[i])
+    if ispec == "shift":
+        pel_in = np.copysign(np.expm1(np.abs((pel_in - I(127.5)) / cshift)), pel_in - I(127.5)) / norm      # :628
+    elif ispec == "flat":
+        pel_in = (pel_in - I(127.5)) * 2 / norm / norm                                        # :629
+    elif ispec == "copy":
+        pel_in = pel_in / norm / norm                                                         # :630
+    coeffs[bsl] = pel_in.astype(C)                                                            # :637
     z, y, x = np.meshgrid(*[np.arange(v) for v in active], indexing="ij")
     s2 = np.sqrt(I(2))
     nf = (2 * s2) / (np.where(x > 0, I(1), s2) * np.where(y > 0, I(1), s2) * np.where(z > 0, I(1), s2))
-    a = (coeffs[asl].astype(I) * nf).astype(C)                                                # :644-647
+    if not ispec:
+        coeffs[bsl] = (odct.dctn_fast(coeffs[bsl], [odct.REDFT10] * 3) if fast else odct.dctn_def(coeffs[bsl], [odct.REDFT10] * 3)).astype(C)   # :641
+        a = (coeffs[asl].astype(I) * nf).astype(C)                                            # :644-647
+    else:
+        a = coeffs[asl].copy()
     dc = a[0, 0, 0]                                                                           # :649
     bb, be = bandpass if bandpass is not None else ((0, 0, 0), active)
     inside = ((z >= bb[0]) & (z < be[0]) & (y >= bb[1]) & (y < be[1]) & (x >= bb[2]) & (x < be[2]))
@@ -212,9 +224,24 @@ def motion_block(pels, block, scaled=None, damp=1.0, boost=1.0, bandpass=None, t
     if quant:
         a = (np.round(a.astype(I) / quantizer) * quantizer).astype(C)                         # :740-744
         coded = int(np.count_nonzero(a))
-    coeffs[asl] = (a.astype(I) / nf).astype(C)                                                # :748-751
-    coeffs[ssl] = (odct.dctn_fast(coeffs[ssl], [odct.REDFT01] * 3) if fast else odct.dctn_def(coeffs[ssl], [odct.REDFT01] * 3)).astype(C)   # :753
-    pel = coeffs[ssl].astype(I) * sf * norm * norm                                            # :757,767
+    if not spec:
+        coeffs[asl] = (a.astype(I) / nf).astype(C)                                            # :748-751
+        coeffs[ssl] = (odct.dctn_fast(coeffs[ssl], [odct.REDFT01] * 3) if fast else odct.dctn_def(coeffs[ssl], [odct.REDFT01] * 3)).astype(C)   # :753
+        pel = coeffs[ssl].astype(I) * sf * norm * norm                                        # :757,767
+    else:
+        coeffs[asl] = a
+        if active != minbuf:                                                                  # (outside the active box the buffer is zero: :617)
+            keep = np.zeros(minbuf, dtype=bool); keep[asl] = True
+            coeffs[~keep] = 0
+        pel = coeffs[ssl].astype(I) * sf * norm                                               # :757
+        if spec == "abs":
+            pel = (255 / np.log1p(np.abs(I(dc) * sf * norm))) * np.log1p(np.abs(pel))         # :754, :760
+        elif spec == "shift":
+            pel = cshift * np.copysign(np.log1p(np.abs(pel)), pel) + I(127.5)                 # :761
+        elif spec == "flat":
+            pel = pel * norm / 2 + I(127.5)                                                   # :762
+        else:
+            pel = pel * norm                                                                  # :764-765
     out = pels.copy()
     if float_pixels:
         out[ssl] = (pel / 255).astype(np.float32)                                             # :773

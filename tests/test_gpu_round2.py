@@ -154,3 +154,13 @@ def test_ring_column_subpasses_batched_and_scaled(lib, small_panels):
     p.destroy()
     ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 2, axes=(1, 2)) * 0.25
     assert od.rel_l2(y, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- motion spectrograms
+@pytest.mark.parametrize("kw", [dict(spec="shift"), dict(spec="flat"), dict(spec="abs"), dict(spec="copy", quant=0.02),
+                                dict(ispec="shift"), dict(ispec="flat"), dict(ispec="copy"),
+                                dict(spec="shift", ispec="shift"), dict(spec="flat", boost=1.5, bandpass=((0, 1, 1), (4, 6, 6)))])
+def test_motion_spectrogram_modes(lib, kw):
+    cases.check_motion(lib, (4, 8, 8), **kw)
+    cases.check_motion(lib, (8, 30, 40), **kw)
+    cases.check_motion(lib, (4, 8, 12), float_pixels=True, **kw)
