@@ -218,6 +218,95 @@ struct OpMotionStore {
 	static OpMotionStore from(const OpAny &o) { OpMotionStore r; r.scale = o.m[6]; r.float_pixels = o.flag2; return r; }
 };
 
+// ---- spec / ispec stages as functors of their own (same arithmetic, same rounding points as the OpAny cases; the
+// kernels instantiated for them inline a few dozen instructions instead of calling the whole switch per element)
+struct OpAccumDc {               // store side of spec's row pass: sum the k = 0 outputs per channel (spec.c:92-117 resolved later)
+	enum { kNeedsCoord = 1 };
+	double *acc;
+	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+		if (c.i2 == 0) {
+#if DSP_GPU
+			atomicAdd(acc + c.ch, (double)v);
+#else
+			acc[c.ch] += (double)v;
+#endif
+		}
+		return v;
+	}
+	static OpAccumDc from(const OpAny &o) { OpAccumDc r; r.acc = (double *)o.aux; return r; }
+};
+struct OpSpecStore {             // store side of spec's column pass (spec.c:66-139)
+	enum { kNeedsCoord = 1 };
+	int scaletype, signtype, w, h;
+	double gain, rnorm, c254;
+	const double *scale_z;       // device: max[z] | ... | 1 / log1p(max[z]) at +8
+	double *dc_out;
+	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+		typedef double I;
+		const I SQRT2 = 1.41421356237309504880168872420969808;
+		const int y = c.i1, x = c.i2, ch = c.ch;
+		T f = v;
+		if (y == 0 && x == 0) dc_out[ch] = (double)f / ((double)w * (double)h * 4.0);            // spec.c:66-68
+		if (y == 0) f = (T)((I)f / SQRT2);                                                        // :70-71
+		if (x == 0) f = (T)((I)f / SQRT2);                                                        // :72-74
+		f = (T)((I)f * rnorm);                                                                    // :76-78
+		f = (T)((I)f * gain);                                                                     // :89-90
+		if (scaletype == 0) f = (T)(copysign(log1p(fabs((I)f)), (I)f) * DSP_LDG(scale_z + 8 + ch));   // :110-117
+		else f = (T)(f / (T)DSP_LDG(scale_z + ch));                                               // :118-121
+		if (signtype == 0) f = (T)fabs((I)f);                                                     // :126-128
+		else if (signtype == 1) f = (T)(((I)f * 0.5 + 0.5) * c254);                               // :130-132
+		else if (signtype == 2) { if (y != 0 || x != 0) f = signbit((I)f) ? (T)0 : (T)1; }         // :134-136
+		return f;
+	}
+	static OpSpecStore from(const OpAny &o) {
+		OpSpecStore r;
+		r.scaletype = o.scaletype; r.signtype = o.signtype; r.w = o.w; r.h = o.h;
+		r.gain = o.p[0]; r.rnorm = o.q[0]; r.c254 = o.q[1];
+		r.scale_z = (const double *)o.aux_c; r.dc_out = (double *)o.aux;
+		return r;
+	}
+};
+struct OpIspecLoad {             // load side of ispec's first pass (ispec.c:84-163)
+	enum { kNeedsCoord = 1 };
+	int scaletype, signtype, w, d, preserve;
+	double rgain, c255;
+	double q[4], dc[4];
+	const unsigned char *signmap;
+	template <class T> DSP_DEVM T operator()(T v, const Coord &c) const {
+		typedef double I;
+		const I SQRT2 = 1.41421356237309504880168872420969808;
+		const int y = c.i1, x = c.i2, ch = c.ch;
+		const bool pix0 = (y == 0 && x == 0);
+		const T qc = (T)(ch == 0 ? q[0] : (ch == 1 ? q[1] : (ch == 2 ? q[2] : q[3])));
+		T f = v;
+		if (signtype == 0) {                                                                      // ispec.c:87-98
+			if (signmap && !pix0) {
+				const int sm = (int)DSP_LDG(signmap + ((size_t)y * w + x) * d + ch) - 128;
+				f = (T)copysign((I)f, (I)sm);
+			}
+		} else if (signtype == 1) f = (T)(((I)f * c255 - 0.5) * 2);                               // :100-103
+		else if (signtype == 2) { if (!pix0) f = f * 2 - 1; }                                      // :104-107
+		if (scaletype == 0) {                                                                     // :136-143
+			const T prod = f * qc;
+			f = (T)copysign(expm1(fabs((I)prod)), (I)f);
+		} else f = f * qc;                                                                        // :144-147
+		f = (T)((I)f * rgain);                                                                    // :150-151
+		if (y == 0) f = (T)((I)f * SQRT2);                                                        // :153-154
+		if (x == 0) f = (T)((I)f * SQRT2);                                                        // :155-157
+		f = f / 2;                                                                                // :158-159
+		if (preserve && pix0) f = (T)(ch == 0 ? dc[0] : (ch == 1 ? dc[1] : (ch == 2 ? dc[2] : dc[3])));   // :161-163
+		return f;
+	}
+	static OpIspecLoad from(const OpAny &o) {
+		OpIspecLoad r;
+		r.scaletype = o.scaletype; r.signtype = o.signtype; r.w = o.w; r.d = o.d; r.preserve = o.flag;
+		r.rgain = o.p[2]; r.c255 = o.p[3];
+		for (int z = 0; z < 4; z++) { r.q[z] = o.q[z]; r.dc[z] = o.dc[z]; }
+		r.signmap = (const unsigned char *)o.aux_c;
+		return r;
+	}
+};
+
 // Resolves spec's data-dependent range (spec/spec.c:92-117) once the row pass has accumulated the per-channel
 // sums S[z] of its k = 0 outputs: Y[0,0,z] = 2 S[z].  Writes scale_z[ch] = log1p(max[ch]) or max[ch].
 template <class T>

@@ -132,8 +132,11 @@ bool KERN_LAUNCH(const KERN_ARGS &a, const FastDesc &f, bool fused, const OpAny 
 #if !KERN_ROW
 		if (lop.kind == OP_MOTION_COEFF && lop.fast && splain) return DSP_OPS_LAUNCH(OpMotionCoeff, OpMul<KERN_T>, OpMotionCoeff::from(lop), sm);
 		if (sop.kind == OP_MOTION_COEFF && sop.fast && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpMotionCoeff, lm, OpMotionCoeff::from(sop));
+		if (sop.kind == OP_SPEC && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpSpecStore, lm, OpSpecStore::from(sop));
+		if (lop.kind == OP_ISPEC && splain) return DSP_OPS_LAUNCH(OpIspecLoad, OpMul<KERN_T>, OpIspecLoad::from(lop), sm);
 #else
 		if (sop.kind == OP_MOTION_STORE && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpMotionStore, lm, OpMotionStore::from(sop));
+		if (sop.kind == OP_ACCUM_DC && lplain) return DSP_OPS_LAUNCH(OpMul<KERN_T>, OpAccumDc, lm, OpAccumDc::from(sop));
 #endif
 #undef DSP_OPS_LAUNCH
 		(void)lplain; (void)splain;

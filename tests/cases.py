@@ -267,7 +267,10 @@ def check_motion(lib, block, scaled=None, prec="f", float_pixels=False, seed=6, 
         assert np.abs(got[ssl].astype(np.int64) - want[ssl].astype(np.int64)).max() <= 1
         frac = np.abs(pel.astype(np.float64))
         dist = np.abs(frac - np.floor(frac) - 0.5)
-        assert (dist[diff] < (2e-3 if prec == "f" else 1e-8)).all(), dist[diff].max()
+        # a tie is "the reference's own unrounded pel within the float error of x.5": 2e-3 of a level for pels in 0..255,
+        # proportionally more when the unclamped values are far larger (a random block read as a spectrogram: --ispec)
+        tie = max(2e-3, 4e-7 * float(np.abs(pel).max())) if prec == "f" else 1e-8
+        assert (dist[diff] < tie).all(), (dist[diff].max(), tie)
     if filt.get("quant"):
         assert abs(coded - coded_ref) <= max(2, coded_ref // 500), (coded, coded_ref)
     return float(diff.mean())
