@@ -629,7 +629,10 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 		if (part) no = nc * pp.ch_inner;
 		int live = 0, at = 0;
 		for (int k = 0; k < 4; k++) if (c.o.cnt[k] > 1) { live++; at = k; }
-		if (fwd && f32 && !pp.fused && pp.rg_P > 0 && live <= 1 && P->d_ring_done) {
+		// the inverse on the ring is correct but measured SLOWER than the two-kernel DIT split (0.595 vs 0.497 ms per 2 planes
+		// of 8192^2: its sub-pass A'' forms every pre-twiddle pair twice and spills): opt-in, for experiments
+		static const bool inv_ring = getenv("DSP_DCT_COLRING_INV") != nullptr;
+		if ((fwd || (inv_ring && (c.ncols % 32) == 0)) && f32 && !pp.fused && pp.rg_P > 0 && live <= 1 && P->d_ring_done) {
 			// ring sub-pass kernels: ONE persistent launch walks every panel of every plane (dct_colring.cuh); the tensor maps
 			// depend on the pointers only and are cached in the plan
 			const int ppp = (c.ncols + pp.rg_P - 1) / pp.rg_P;
@@ -647,11 +650,11 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					PassPlan::RingMaps e;
 					memset(&e.args, 0, sizeof(e.args));
 					e.in = bin; e.out = bout; e.scratch = P->d_split; e.nplanes = np;
-					ok = colring_encode(e.args, c.f.n, (const float *)bin, c.ax_is, c.o.is[at], (float *)bout, c.ax_os, c.o.os[at], np, c.ncols,
+					ok = colring_encode(e.args, c.f.n, !fwd, (const float *)bin, c.ax_is, c.o.is[at], (float *)bout, c.ax_os, c.o.os[at], np, c.ncols,
 					                    (float *)P->d_split, pp.rg_P, g_err);
 					e.args.twM = pp.ffM.tw; e.args.sigM = pp.ffM.sig;
 					e.args.twN = pp.ff.tw; e.args.omN = pp.ff.om; e.args.sigN = pp.ff.sig;
-					e.args.nplanes = np; e.args.ppp = ppp; e.args.P = pp.rg_P; e.args.ncols = c.ncols; e.args.reverse = 0;
+					e.args.nplanes = np; e.args.ppp = ppp; e.args.P = pp.rg_P; e.args.ncols = c.ncols; e.args.reverse = fwd ? 0 : 1;
 					e.args.done = P->d_ring_done;
 					e.args.scratch = (float *)P->d_split;
 					e.args.trace = nullptr;
@@ -667,7 +670,7 @@ static bool run_pass(dsp_dct_plan_s *P, PassPlan &pp, const void *in, void *out,
 					ColRingArgs ra = rm->args;
 					ra.lscale = (float)(pp.lop.kind == OP_SCALE ? pp.lop.p[0] : 1.0); ra.sscale = (float)(pp.sop.kind == OP_SCALE ? pp.sop.p[0] : 1.0);
 					DSP_TRACE("split pass: ring sub-pass kernel n=%d planes %d panels/plane %d width %d", c.f.n, np, ppp, pp.rg_P);
-					ok = rt_zero(P->d_ring_done, sizeof(int) * 2 * (size_t)colring_max_panels(), st, g_err) && launch_col_ring_f32(ra, c.f.n, st, g_err);
+					ok = rt_zero(P->d_ring_done, sizeof(int) * 2 * (size_t)colring_max_panels(), st, g_err) && launch_col_ring_f32(ra, c.f.n, !fwd, st, g_err);
 					if (ok) g_launches++;
 				}
 			}

@@ -37,9 +37,9 @@ struct ColRingArgs;
 bool colring_supports(int n);
 int colring_max_panels();
 int colring_scratch_panels();
-bool colring_encode(ColRingArgs &a, int n, const float *in, long long ax_is, long long plane_is, float *out, long long ax_os, long long plane_os,
+bool colring_encode(ColRingArgs &a, int n, bool inverse, const float *in, long long ax_is, long long plane_is, float *out, long long ax_os, long long plane_os,
                     int nplanes, int ncols, float *scratch, int P, std::string &err);
-bool launch_col_ring_f32(const ColRingArgs &a, int n, rt_stream st, std::string &err);   // dct_colring.cuh
+bool launch_col_ring_f32(const ColRingArgs &a, int n, bool inverse, rt_stream st, std::string &err);   // dct_colring.cuh
 
 bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int row_bytes, rt_stream st, std::string &err);
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);

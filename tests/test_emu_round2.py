@@ -145,6 +145,21 @@ def test_ring_column_subpasses(lib, small_panels, kind, shape):
     cases.check_interleaved_2d(lib, "f", *shape, kind)
 
 
+@pytest.mark.parametrize("shape", [(4096, 160, 1), (8192, 96, 1), (4096, 32, 2)])
+def test_ring_column_inverse_opt_in(shape):
+    """the DCT-III ring sub-passes (DSP_DCT_COLRING_INV=1, opt-in): pre-twiddle pairs across the two sub-sequence boxes,
+    single sub-sequences 0 and 8, outer DIT butterflies with the un-permuting store -- emulated boxes, fresh process"""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from dspfun_b200 import REDFT01\nfrom tests import cases\nfrom tests.emu import emu\n"
+            "print(cases.check_interleaved_2d(emu.load(), 'f', %d, %d, %d, REDFT01))" % (os.getcwd(), *shape))
+    env = dict(os.environ, DSP_DCT_COLRING_INV="1", DSP_DCT_SPLIT_PANEL_MB="1", DSP_DCT_TRACE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ring sub-pass kernel" in r.stderr
+    assert float(r.stdout.strip().splitlines()[-1]) < 1e-5
+
+
 def test_ring_column_subpasses_batched_and_scaled(lib, small_panels):
     """outer (batch) offsets enter through the tensor maps' base pointers; fused store scale"""
     rng = np.random.default_rng(41)

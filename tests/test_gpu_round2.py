@@ -139,6 +139,20 @@ def test_ring_column_subpasses_small_panels(lib, small_panels, kind, shape):
     cases.check_interleaved_2d(lib, "f", *shape, kind)
 
 
+@pytest.mark.parametrize("shape", [(4096, 160, 1), (8192, 96, 1), (8192, 1024, 1)])
+def test_ring_column_inverse_opt_in(shape):
+    """the DCT-III ring sub-passes (DSP_DCT_COLRING_INV=1: correct, measured slower than the default two-kernel split, so
+    opt-in): a fresh process, because the switch is read once"""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from dspfun_b200 import capi, REDFT01\nfrom tests import cases\n"
+            "print(cases.check_interleaved_2d(capi.load(), 'f', %d, %d, %d, REDFT01))" % (os.getcwd(), *shape))
+    env = dict(os.environ, DSP_DCT_COLRING_INV="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert float(r.stdout.strip().splitlines()[-1]) < 1e-5
+
+
 @pytest.mark.parametrize("kind", [REDFT10, REDFT01])
 @pytest.mark.parametrize("shape", [(4096, 2048, 1), (8192, 1024, 1), (8192, 512, 3), (4096, 4096, 1)])
 def test_ring_column_subpasses(lib, kind, shape):
