@@ -28,6 +28,8 @@ SYMBOLS = [
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
     "dsp_block_store_u8",
+    "dsp_block_dct2d",
+    "dsp_block_dct2d_debug",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
     "dsp_dct_fuse_pel_load", "dsp_dct_fuse_motion_coeff", "dsp_dct_fuse_pel_store", "dsp_dct_is_emulation",
 ]
@@ -100,6 +102,10 @@ def bind(path):
     lib.dsp_block_quant.argtypes = [ctypes.c_char, vp, ci, ci, ci, ci, ci, ci, cd, vp, vp]
     lib.dsp_block_store_u8.restype = ci
     lib.dsp_block_store_u8.argtypes = [ctypes.c_char, vp, vp, ctypes.c_longlong, cd, vp]
+    lib.dsp_block_dct2d.restype = ci
+    lib.dsp_block_dct2d.argtypes = [ctypes.c_char, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, cd, vp]
+    lib.dsp_block_dct2d_debug.restype = ci
+    lib.dsp_block_dct2d_debug.argtypes = [vp, vp, ctypes.c_longlong, ci, ci, ci, ci, cd, vp, vp]
     lib.dsp_dct_set_output_segments.restype = ci
     lib.dsp_dct_set_output_segments.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.c_longlong, ctypes.c_longlong]
     lib.dsp_dct_fuse_spec.restype = ci

@@ -62,7 +62,9 @@ struct TmaView {
 };
 #if DSP_GPU
 typedef CUtensorMap TmaDesc;
-inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &err) {
+// swizzle128: the box lands with the 128-byte swizzle (16-byte chunk index ^= row % 8; box rows of exactly 128 bytes,
+// destination 1024-byte aligned), the layout the tensor core's SWIZZLE_128B operand descriptors read
+inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &err, bool swizzle128 = false) {
 	typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 	                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
 	                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -80,7 +82,7 @@ inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &err) {
 	cuuint32_t box[4], es[4];
 	for (int i = 0; i < v.rank; i++) { dims[i] = v.dims[i]; box[i] = v.box[i]; es[i] = 1; if (i) strides[i - 1] = v.strides[i]; }
 	const CUresult rc = fn(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)v.rank, v.base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                       swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (rc != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")"; return false; }
 	return true;
 }
@@ -134,7 +136,7 @@ DSP_DEV void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" 
 DSP_DEV void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // all groups complete
 #else
 typedef TmaView TmaDesc;
-inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &) { *d = v; return true; }
+inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &, bool = false) { *d = v; return true; }
 inline void tma_emu_copy(const TmaDesc *m, float *smem, const int *c, bool load) {
 	unsigned long long st[4] = {4, 0, 0, 0};
 	int cc[4] = {0, 0, 0, 0};

@@ -1264,6 +1264,20 @@ int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, l
 	return ok ? 0 : 1;
 }
 
+int dsp_block_dct2d_debug(const void *d_in, void *d_out, long long nplanes, int H, int W, int B, int kind, double scale, void *stream, float *d_debug) {
+	g_err.clear();
+	if (!d_in || !d_out || nplanes < 1 || H < 1 || W < 1) { g_err = "block DCT: bad arguments"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	const bool ok = launch_block_mm_f32((const float *)d_in, (float *)d_out, nplanes, H, W, B, kind, scale, (rt_stream)stream, g_err, d_debug);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
+}
+
+int dsp_block_dct2d(char prec, const void *d_in, void *d_out, long long nplanes, int H, int W, int B, int kind, double scale, void *stream) {
+	if (prec != 'f') { g_err = "block DCT by GEMM: float only (use the per-axis plans for double)"; return 1; }
+	return dsp_block_dct2d_debug(d_in, d_out, nplanes, H, W, B, kind, scale, stream, nullptr);
+}
+
 int dsp_dct_fuse_spec(dsp_dct_plan p, const dsp_spec_params *sp) {
 	g_err.clear();
 	if (!p || !sp) { g_err = "null plan or params"; return 1; }

@@ -47,6 +47,11 @@ bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int 
                         unsigned long long *count, rt_stream st, std::string &err);
 bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err);
 
+// 2-D block DCT of whole planes as tensor-core GEMMs (kern_block_mm.cu): tcgen05 / TMEM, 3 x TF32 split for float accuracy
+bool block_mm_supports(int B);
+bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, int W, int B, int kind, double scale, rt_stream st,
+                         std::string &err, float *dbg);
+
 // pointwise spectrogram stages of motion (kern_misc.cu)
 struct MotionSpecArgs {
 	int md, mh, mw;              // padded box (minbuf)

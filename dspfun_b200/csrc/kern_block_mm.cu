@@ -1,0 +1,413 @@
+// kern_block_mm.cu -- 2-D block DCT as two small GEMMs per tile on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// motion -b BxBx1 / -b BxBxD and applybasis' DCT bases transform every B x B block of a plane on its own
+// (/root/reference/motion/motion.c:613-641 with the README's 8x8x8 example motion/README.md:75-77;
+// /root/reference/applybasis/applybasis.c:410-448 is the same contraction written as an O(N^4) loop).  For B <= 64 the
+// FFT passes of the plan path move every sample through HBM once per axis; here a 128 x 128 tile of a plane makes ONE
+// round trip and both axes are contracted on chip:
+//
+//     stage 1 (along w):  D1[r][gB+n] = sum_k X[r][gB+k] M[n][k]      A = X tile, K-major, as the TMA left it (128-byte
+//                                                                     swizzle), B = the block matrix, D1 in TMEM
+//     stage 2 (along h):  D2[c][gB+n] = sum_k D1[gB+k][c] M[n][k]     A = D1 read back from TMEM and written to shared
+//                                                                     memory MN-major (a transposing store), D2 in TMEM
+//     epilogue:           out[gB+n][c] = D2[c][gB+n]                  lane = image column: 128-byte coalesced stores
+//
+// M is FFTW's unnormalised REDFT10 or REDFT01 matrix of size B (B = 8 uses a block-diagonal pair so that N = 16).
+// The tensor cores multiply in TF32; to keep float accuracy every operand is split x = hi + lo (hi = the top 19 bits,
+// lo = x - hi, exact) and each product is three MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM): the error is
+// ~2^-21 relative per product instead of 2^-11.
+//
+// One persistent CTA per SM, 256 threads.  Thread 0 issues the TMA loads (next tile's box lands while this one is
+// computed) and all MMAs; completion comes back through mbarriers (cp.async.bulk.tensor complete_tx, tcgen05.commit).
+#include "dsp_kernels.h"
+#include "dct_tma.cuh"
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace dsp {
+
+constexpr int kMmTile = 128;             // tile edge: M of both MMAs
+constexpr int kMmThreads = 256;
+constexpr int kMmBuf = kMmTile * kMmTile * 4;   // one operand buffer: 64 KB
+constexpr int kMmTmemCols = 256;         // D1 | D2
+
+struct BlockMmArgs {
+	TmaDesc in_map;          // [planes][H][W] floats, box {32, 128, 1}, 128-byte swizzle
+	const float *consts;     // hi | lo halves of the block matrix, each Be*Be floats in operand layout
+	float *out;
+	float *dbg;              // bring-up: D1 and D2 of tile 0 (2 x 128 x 128 floats) or null
+	int H, W, nplanes, Be;
+	int tiles_x, tiles_y;
+	long long ntiles;
+	float scale;
+	int variant;             // stage-2 operand layout: 0 K-major with the 128-byte swizzle, 1 / 2 MN-major unswizzled (bring-up)
+};
+
+static size_t block_mm_smem(int Be) { return 1024 + 3 * (size_t)kMmBuf + 8 * (size_t)Be * Be + 64; }
+
+// element (n, k) of an N x K operand stored K-major without swizzle: 8 x 16-byte core matrices, K chunks 128 bytes apart,
+// groups of 8 rows 32*K bytes apart (float index)
+static inline int const_slot(int n, int k, int K) { return (n >> 3) * (8 * K) + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
+
+#if DSP_GPU
+// ------------------------------------------------------------------------------------------------ tcgen05 wrappers
+// shared-memory operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start >> 4 [0,14), leading byte offset
+// >> 4 [16,30), stride byte offset >> 4 [32,46), version 1 [46,48), layout [61,64) (0 none, 2 = 128-byte swizzle)
+DSP_DEV uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+	return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+	       (1ull << 46) | ((uint64_t)layout << 61);
+}
+// instruction descriptor, kind::tf32 with fp32 accumulation: c_format F32 [4,6), a/b format TF32 [7,10) [10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N >> 3 [17,23), M >> 4 [24,29)
+DSP_DEV uint32_t umma_idesc(int M, int N, int a_mn, int b_mn) {
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+DSP_DEV void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+	    "}\n" ::"r"(d_tmem),
+	    "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+DSP_DEV void umma_commit(uint64_t *bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DSP_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DSP_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DSP_DEV void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// this warp's 32 lanes x 32 consecutive columns: v[i] = TMEM[lane][col + i]
+DSP_DEV void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+	      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+	      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+	      "=r"(v[31])
+	    : "r"(taddr)
+	    : "memory");
+}
+// mbarrier wait that gives up (trap: the launch fails instead of hanging the device) if the phase never completes
+DSP_DEV void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+	uint32_t ok = 0;
+	for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+		asm volatile(
+		    "{\n"
+		    ".reg .pred p;\n"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		    "selp.u32 %0, 1, 0, p;\n"
+		    "}\n"
+		    : "=r"(ok)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+		if (ok) return;
+	}
+	asm volatile("trap;");
+}
+DSP_DEV float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(kMmThreads, 1) k_block_mm(const __grid_constant__ BlockMmArgs a) {
+	extern __shared__ unsigned char mm_smem_raw[];
+	const uint32_t raw = smem_u32(mm_smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;              // the swizzled boxes need 1024-byte alignment
+	unsigned char *sm = mm_smem_raw + (base - raw);
+	const int Be = a.Be, nb = kMmTile / Be;
+	float *Chi = (float *)(sm + 3 * kMmBuf);
+	uint64_t *bars = (uint64_t *)(sm + 3 * kMmBuf + 8 * Be * Be);     // [0], [1]: tile landed in buffer 0 / 1; [2]: MMAs done
+	uint32_t *tslot = (uint32_t *)(bars + 3);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+	if (tid == 0) {
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		mbar_init(&bars[2], 1);
+		mbar_fence_init();
+	}
+	for (int i = tid; i < 2 * Be * Be / 4; i += kMmThreads) ((float4 *)Chi)[i] = __ldg((const float4 *)a.consts + i);
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"((uint32_t)kMmTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async();                                      // the constants are read by the tensor core (async proxy)
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = *(volatile uint32_t *)tslot;
+
+	const uint32_t c_hi = base + 3 * kMmBuf, c_lo = c_hi + 4 * Be * Be, s_lo = base + 2 * kMmBuf;
+	const uint32_t sbo_c = 32u * Be;
+	const uint32_t id1 = umma_idesc(kMmTile, Be, 0, 0), id2 = umma_idesc(kMmTile, Be, 1, 0);
+	const long long per_plane = (long long)a.tiles_x * a.tiles_y;
+
+	auto issue_load = [&](long long tile, int b) {
+		const int plane = (int)(tile / per_plane);
+		const int rem = (int)(tile - plane * per_plane);
+		const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+		mbar_expect_tx(&bars[b], kMmBuf);
+		for (int j = 0; j < 4; j++) tma_load3(sm + b * kMmBuf + j * (kMmBuf / 4), &a.in_map, tx * kMmTile + 32 * j, ty * kMmTile, plane, &bars[b]);
+	};
+
+	long long t = blockIdx.x;
+	uint32_t mph = 0;
+	if (tid == 0 && t < a.ntiles) issue_load(t, 0);
+	for (int it = 0; t < a.ntiles; t += gridDim.x, it++) {
+		const int b = it & 1;
+		const uint32_t s_hi = base + b * kMmBuf;
+		if (tid == 0 && t + gridDim.x < a.ntiles) issue_load(t + gridDim.x, b ^ 1);
+		const int plane = (int)(t / per_plane);
+		const int rem = (int)(t - plane * per_plane);
+		const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+		mbar_wait_bounded(&bars[b], (it >> 1) & 1);
+
+		// split the tile in place: hi stays where the TMA put it, lo goes to the same offset of the second buffer
+		{
+			float4 *X4 = (float4 *)(sm + b * kMmBuf), *S4 = (float4 *)(sm + 2 * kMmBuf);
+#pragma unroll 4
+			for (int i = 0; i < kMmBuf / 16 / kMmThreads; i++) {
+				const int f = tid + kMmThreads * i;
+				const float4 v = X4[f];
+				const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+				X4[f] = h;
+				S4[f] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+			}
+		}
+		fence_proxy_async();
+		__syncthreads();
+
+		if (tid == 0) {                                                    // stage 1: contract along w
+			tc_fence_after();
+			for (int g = 0; g < nb; g++) {
+				uint32_t acc = 0;
+				for (int term = 0; term < 3; term++) {
+					const uint32_t aop = term == 0 ? s_lo : s_hi, bop = term == 1 ? c_lo : c_hi;
+					for (int kk = 0; kk < Be / 8; kk++) {
+						const int c0 = g * Be + 8 * kk;
+						const uint64_t ad = umma_desc(aop + (uint32_t)(c0 >> 5) * (kMmBuf / 4) + (uint32_t)(c0 & 31) * 4, 16, 1024, 2);
+						const uint64_t bd = umma_desc(bop + (uint32_t)kk * 256, 128, sbo_c, 0);
+						umma_tf32(tmem + g * Be, ad, bd, id1, acc);
+						acc = 1;
+					}
+				}
+			}
+			umma_commit(&bars[2]);
+		}
+		mbar_wait_bounded(&bars[2], mph);
+		mph ^= 1;
+		tc_fence_after();
+
+		// D1 (lane = row) -> registers -> hi | lo -> the A operand of stage 2, A2[m = column][k = row], K-major in the
+		// same swizzled form the TMA gives stage 1: four boxes of 32 k, rows of 128 bytes, 16-byte chunk ^= m % 8.
+		// A warp (32 consecutive k, one m) stores one whole 128-byte row: no bank conflicts.
+		{
+			const int k = (warp & 3) * 32 + lane;
+			unsigned char *Thi = sm + b * kMmBuf, *Tlo = sm + 2 * kMmBuf;
+			const uint32_t koff = (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16;                  // MN-major variants
+			const uint32_t kbox = (uint32_t)(warp & 3) * (kMmBuf / 4), kch = (uint32_t)lane >> 2, kin = ((uint32_t)lane & 3) * 4;
+#pragma unroll 1
+			for (int u = 0; u < 2; u++) {
+				const int m0 = (warp >> 2) * 64 + u * 32;
+				uint32_t v[32];
+				tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + m0, v);
+				tmem_wait_ld();
+				if (a.dbg && blockIdx.x == 0 && it == 0)
+					for (int i = 0; i < 32; i++) a.dbg[k * kMmTile + m0 + i] = __uint_as_float(v[i]);
+				if (a.variant == 0) {
+#pragma unroll
+					for (int i = 0; i < 32; i++) {
+						const float x = __uint_as_float(v[i]), h = tf32_hi(x);
+						const uint32_t m = (uint32_t)(m0 + i);
+						const uint32_t off = kbox + m * 128 + ((kch ^ (m & 7)) << 4) + kin;
+						*(float *)(Thi + off) = h;
+						*(float *)(Tlo + off) = x - h;
+					}
+				} else {
+#pragma unroll
+					for (int g8 = 0; g8 < 8; g8++) {
+						const float x0 = __uint_as_float(v[4 * g8]), x1 = __uint_as_float(v[4 * g8 + 1]), x2 = __uint_as_float(v[4 * g8 + 2]),
+						            x3 = __uint_as_float(v[4 * g8 + 3]);
+						const float4 h = make_float4(tf32_hi(x0), tf32_hi(x1), tf32_hi(x2), tf32_hi(x3));
+						const uint32_t off = (uint32_t)((m0 >> 2) + g8) * 2048 + koff;
+						*(float4 *)(Thi + off) = h;
+						*(float4 *)(Tlo + off) = make_float4(x0 - h.x, x1 - h.y, x2 - h.z, x3 - h.w);
+					}
+				}
+			}
+		}
+		tc_fence_before();
+		fence_proxy_async();
+		__syncthreads();
+
+		if (tid == 0) {                                                    // stage 2: contract along h
+			tc_fence_after();
+			for (int g = 0; g < nb; g++) {
+				uint32_t acc = 0;
+				for (int term = 0; term < 3; term++) {
+					const uint32_t aop = term == 0 ? s_lo : s_hi, bop = term == 1 ? c_lo : c_hi;
+					for (int kk = 0; kk < Be / 8; kk++) {
+						const int k0 = g * Be + 8 * kk;
+						const uint64_t ad = a.variant == 0   ? umma_desc(aop + (uint32_t)(k0 >> 5) * (kMmBuf / 4) + (uint32_t)(k0 & 31) * 4, 16, 1024, 2)
+						                    : a.variant == 1 ? umma_desc(aop + (uint32_t)(k0 >> 3) * 128, 128, 2048, 0)
+						                                     : umma_desc(aop + (uint32_t)(k0 >> 3) * 128, 2048, 128, 0);
+						const uint64_t bd = umma_desc(bop + (uint32_t)kk * 256, 128, sbo_c, 0);
+						umma_tf32(tmem + kMmTile + g * Be, ad, bd, a.variant == 0 ? id1 : id2, acc);
+						acc = 1;
+					}
+				}
+			}
+			umma_commit(&bars[2]);
+		}
+		mbar_wait_bounded(&bars[2], mph);
+		mph ^= 1;
+		tc_fence_after();
+
+		// D2 (lane = image column, TMEM column = image row) -> global: a warp stores 128 contiguous bytes per row
+		{
+			const int m = (warp & 3) * 32 + lane;
+			const int col = tx * kMmTile + m;
+			float *op = a.out + ((long long)plane * a.H + (long long)ty * kMmTile) * a.W + col;
+#pragma unroll 1
+			for (int u = 0; u < 2; u++) {
+				const int r0 = (warp >> 2) * 64 + u * 32;
+				uint32_t v[32];
+				tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kMmTile + r0, v);
+				tmem_wait_ld();
+				if (a.dbg && blockIdx.x == 0 && it == 0)
+					for (int i = 0; i < 32; i++) a.dbg[kMmTile * kMmTile + (r0 + i) * kMmTile + m] = __uint_as_float(v[i]);
+				if (col < a.W) {
+#pragma unroll
+					for (int i = 0; i < 32; i++)
+						if (ty * kMmTile + r0 + i < a.H) op[(long long)(r0 + i) * a.W] = __uint_as_float(v[i]) * a.scale;
+				}
+			}
+		}
+		tc_fence_before();
+		__syncthreads();
+	}
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kMmTmemCols) : "memory");
+}
+#endif  // DSP_GPU
+
+// ------------------------------------------------------------------------------------------------ host side
+// FFTW's unnormalised matrices: REDFT10 Y[n] = 2 sum_k x[k] cos(pi (k + 1/2) n / B); REDFT01 Y[n] = x[0] + 2 sum_{k>=1} x[k] cos(pi (n + 1/2) k / B)
+static double block_matrix(int B, int kind, int n, int k) {
+	const double pi = 3.14159265358979323846264338327950288;
+	if (kind == DSP_KIND_REDFT10) return 2.0 * cos(pi * (k + 0.5) * n / B);
+	return k == 0 ? 1.0 : 2.0 * cos(pi * (n + 0.5) * k / B);
+}
+
+bool block_mm_supports(int B) { return B == 8 || B == 16 || B == 32 || B == 64; }
+
+#if DSP_GPU
+static float host_tf32_hi(float x) {
+	uint32_t u;
+	memcpy(&u, &x, 4);
+	u &= 0xFFFFE000u;
+	memcpy(&x, &u, 4);
+	return x;
+}
+static std::mutex g_mm_mu;
+static std::map<long long, float *> g_mm_consts;      // (device, B, kind) -> hi | lo operand images on the device
+
+static const float *block_mm_consts(int B, int kind, int Be, std::string &err) {
+	const long long key = ((long long)rt_device() << 16) | (B << 4) | kind;
+	std::lock_guard<std::mutex> lock(g_mm_mu);
+	auto it = g_mm_consts.find(key);
+	if (it != g_mm_consts.end()) return it->second;
+	std::vector<float> h(2 * (size_t)Be * Be, 0.0f);
+	for (int n = 0; n < Be; n++)
+		for (int k = 0; k < Be; k++) {
+			if (n / B != k / B) continue;                                  // B = 8: two blocks on the diagonal of a 16 x 16 matrix
+			const double c = block_matrix(B, kind, n % B, k % B);
+			const float hi = host_tf32_hi((float)c);
+			const float lo = host_tf32_hi((float)(c - (double)hi));
+			h[const_slot(n, k, Be)] = hi;
+			h[(size_t)Be * Be + const_slot(n, k, Be)] = lo;
+		}
+	float *d = nullptr;
+	if (!rt_ok(cudaMalloc(&d, h.size() * 4), err, "block matrix allocation")) return nullptr;
+	if (!rt_ok(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice), err, "block matrix upload")) { cudaFree(d); return nullptr; }
+	g_mm_consts[key] = d;
+	return d;
+}
+#endif
+
+// every B x B block of `nplanes` planes [H][W] (floats, W-contiguous): out = M X M^T per block, times `scale`.
+// in == out is allowed (each tile is read whole before it is written, tiles are disjoint).
+bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, int W, int B, int kind, double scale, rt_stream st,
+                         std::string &err, float *dbg) {
+	if (!block_mm_supports(B)) { err = "block DCT by GEMM: block size must be 8, 16, 32 or 64"; return false; }
+	if (H % B || W % B) { err = "block DCT by GEMM: the plane must be a whole number of blocks"; return false; }
+	if (kind != DSP_KIND_REDFT10 && kind != DSP_KIND_REDFT01) { err = "block DCT by GEMM: REDFT10 or REDFT01"; return false; }
+	if (nplanes < 1 || nplanes > 0x7fffffffLL) { err = "block DCT by GEMM: bad plane count"; return false; }
+#if DSP_GPU
+	if (((uintptr_t)in & 15) || ((uintptr_t)out & 3)) { err = "block DCT by GEMM: the input must be 16-byte aligned"; return false; }
+	const int Be = B < 16 ? 16 : B;
+	BlockMmArgs a;
+	memset(&a, 0, sizeof(a));
+	a.consts = block_mm_consts(B, kind, Be, err);
+	if (!a.consts) return false;
+	TmaView v;
+	memset(&v, 0, sizeof(v));
+	v.base = (void *)in; v.rank = 3;
+	v.dims[0] = (unsigned long long)W; v.dims[1] = (unsigned long long)H; v.dims[2] = (unsigned long long)nplanes;
+	v.strides[1] = (unsigned long long)W * 4; v.strides[2] = (unsigned long long)W * 4 * (unsigned long long)H;
+	v.box[0] = 32; v.box[1] = kMmTile; v.box[2] = 1;
+	if (!tma_encode(&a.in_map, v, err, true)) return false;
+	a.out = out; a.dbg = dbg; a.H = H; a.W = W; a.nplanes = (int)nplanes; a.Be = Be;
+	a.tiles_x = (W + kMmTile - 1) / kMmTile; a.tiles_y = (H + kMmTile - 1) / kMmTile;
+	a.ntiles = (long long)a.tiles_x * a.tiles_y * nplanes;
+	a.scale = (float)scale;
+	{ const char *e = getenv("DSP_BLOCKMM_VARIANT"); a.variant = e ? atoi(e) : 0; }
+	static int sm_count[64] = {0};
+	static unsigned long long attr_dev = 0;
+	const int dev = rt_device() & 63;
+	if (!sm_count[dev]) {
+		int s = 0;
+		if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || s < 1) s = 148;
+		sm_count[dev] = s;
+	}
+	if (!((attr_dev >> dev) & 1ull)) {
+		if (!rt_ok(cudaFuncSetAttribute(k_block_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_mm_smem(64)), err, "smem attribute")) return false;
+		attr_dev |= 1ull << dev;
+	}
+	const int grid = (int)(a.ntiles < sm_count[dev] ? a.ntiles : sm_count[dev]);
+	k_block_mm<<<grid, kMmThreads, block_mm_smem(Be), st>>>(a);
+	return rt_ok(cudaGetLastError(), err, "block DCT GEMM launch");
+#else
+	// emulation (tests/emu): the same contraction as plain loops in double; the tensor-core path itself only exists on the GPU
+	(void)st; (void)dbg;
+	std::vector<double> M((size_t)B * B), tmp((size_t)B * B);
+	for (int n = 0; n < B; n++)
+		for (int k = 0; k < B; k++) M[(size_t)n * B + k] = block_matrix(B, kind, n, k);
+	std::vector<float> blk((size_t)B * B);
+	for (long long p = 0; p < nplanes; p++)
+		for (int by = 0; by < H; by += B)
+			for (int bx = 0; bx < W; bx += B) {
+				const float *src = in + ((size_t)p * H + by) * W + bx;
+				float *dst = out + ((size_t)p * H + by) * W + bx;
+				for (int r = 0; r < B; r++)
+					for (int c = 0; c < B; c++) blk[(size_t)r * B + c] = src[(size_t)r * W + c];
+				for (int r = 0; r < B; r++)
+					for (int n = 0; n < B; n++) {
+						double s = 0;
+						for (int k = 0; k < B; k++) s += (double)blk[(size_t)r * B + k] * M[(size_t)n * B + k];
+						tmp[(size_t)r * B + n] = (double)(float)s;                 // D1 is held in fp32
+					}
+				for (int n = 0; n < B; n++)
+					for (int c = 0; c < B; c++) {
+						double s = 0;
+						for (int k = 0; k < B; k++) s += tmp[(size_t)k * B + c] * M[(size_t)n * B + k];
+						dst[(size_t)n * W + c] = (float)(s * (double)(float)scale);
+					}
+			}
+	return true;
+#endif
+}
+
+}  // namespace dsp

@@ -233,6 +233,20 @@ int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int 
                     unsigned long long *d_count, void *stream);
 int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream);
 
+/* ---- 2-D block DCT on the tensor cores: every B x B block (B = 8, 16, 32 or 64) of `nplanes` float planes [H][W]
+ * (device memory, W contiguous, H and W whole numbers of blocks, d_in 16-byte aligned; d_out may equal d_in) is
+ * replaced by its unnormalised FFTW transform along both axes, times `scale`: kind = DSP_DCT_REDFT10 or
+ * DSP_DCT_REDFT01, i.e. what fftw_plan_many_r2r(rank 2, {B, B}) computes per block in motion's block loop
+ * (motion/motion.c:559-564, :613-641, :753 with -b BxBx1, or the two spatial axes of -b BxBxD) and what applybasis'
+ * DCT contraction (applybasis/applybasis.c:410-448) evaluates with O(N^4) loops.  One pass over the planes: a
+ * 128 x 128 tile is contracted along w and then along h by tcgen05 MMAs (TF32 operands split hi + lo, three MMAs
+ * per product, fp32 accumulation in tensor memory), so the result carries float accuracy (~1e-6 relative).
+ * prec must be 'f'.  Other block sizes / double: use the per-axis plans (dspfun_b200/motion.py MotionTiled). */
+int dsp_block_dct2d(char prec, const void *d_in, void *d_out, long long nplanes, int H, int W, int B, int kind, double scale, void *stream);
+/* bring-up / test hook: as above for one launch, also copying the first tile's two accumulators ([2][128][128] floats:
+ * after the w contraction, after the h contraction transposed) to d_debug */
+int dsp_block_dct2d_debug(const void *d_in, void *d_out, long long nplanes, int H, int W, int B, int kind, double scale, void *stream, float *d_debug);
+
 /* ---- zoom: DCT-domain resampling of an RGB image (zoom/zoom.c:263-266 forward plan, :36-68 scaled basis,
  * :361-375 synthesis).  create: REDFT10 x REDFT10 of the [h][w][3] interleaved pixels, kept on the GPU.
  * frame: one output view.  Scale is num/den per axis; (vx, vy) the view offset in output samples; (vw, vh) the

@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Bring-up / measurement of the tensor-core block DCT (dsp_block_dct2d): stage-by-stage comparison of the first tile with
+numpy (float64), whole-output error for every block size and both kinds, ragged plane sizes, and timing."""
+import ctypes
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from dspfun_b200 import capi
+
+lib = capi.load()
+R10, R01 = capi.REDFT10, capi.REDFT01
+
+
+def matrix(B, kind):
+    n = np.arange(B)[:, None].astype(np.float64)
+    k = np.arange(B)[None, :].astype(np.float64)
+    if kind == R10:
+        return 2.0 * np.cos(np.pi * (k + 0.5) * n / B)
+    m = 2.0 * np.cos(np.pi * (n + 0.5) * k / B)
+    m[:, 0] = 1.0
+    return m
+
+
+def ref_blocks(x, B, kind):
+    P, H, W = x.shape
+    M = matrix(B, kind)
+    xb = x.astype(np.float64).reshape(P, H // B, B, W // B, B)
+    y = np.einsum("nr,pyrxc,mc->pynxm", M, xb, M)
+    return y.reshape(P, H, W)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run(x, B, kind, debug=False):
+    P, H, W = x.shape
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.zeros_like(d_in)
+    dbg = torch.zeros(2 * 128 * 128, dtype=torch.float32, device="cuda")
+    rc = lib.dsp_block_dct2d_debug(d_in.data_ptr(), d_out.data_ptr(), P, H, W, B, kind, 1.0, None, dbg.data_ptr() if debug else None)
+    if rc != 0:
+        raise RuntimeError(capi.last_error(lib))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy(), dbg.cpu().numpy().reshape(2, 128, 128)
+
+
+import os
+rng = np.random.default_rng(5)
+worst = 0.0
+for variant in (2, 1, 0):
+  os.environ["DSP_BLOCKMM_VARIANT"] = str(variant)
+  print("---- stage-2 operand variant", variant)
+  for B in (64, 32, 16, 8):
+    for kind in (R10, R01):
+          x = rng.standard_normal((2, 256, 384)).astype(np.float32)
+          try:
+              y, dbg = run(x, B, kind, debug=True)
+          except Exception as e:
+              print("B", B, "kind", kind, "FAILED", e)
+              continue
+          M = matrix(B, kind)
+          t = x[0, :128, :128].astype(np.float64)
+          d1 = np.einsum("rgk,nk->rgn", t.reshape(128, 128 // B, B), M).reshape(128, 128)         # [row][col-freq]
+          d2 = np.einsum("gkc,nk->gnc", d1.reshape(128 // B, B, 128), M).reshape(128, 128)         # [row-freq][col]
+          want = ref_blocks(x, B, kind)
+          e = rel(y, want)
+          worst = max(worst, e)
+          print("B %2d kind %d  stage1 %.3e  stage2 %.3e  out %.3e  max|d| %.3e" % (B, kind, rel(dbg[0], d1), rel(dbg[1], d2), e, np.abs(y - want).max()))
+          if e > 1e-4 and variant == 0:     # help the diagnosis: is it a permutation / a missing term?
+              print("   first row got ", y[0, 0, :8])
+              print("   first row want", want[0, 0, :8])
+              print("   dbg1 row0 got ", dbg[0, 0, :8])
+              print("   d1   row0 want", d1[0, :8])
+# ragged planes (H, W not multiples of 128), in place, many planes
+for (P, H, W, B) in ((3, 200, 328, 8), (1, 1080, 1920, 8), (5, 64, 64, 64), (2, 96, 160, 32), (1, 144, 16, 16)):
+    x = rng.standard_normal((P, H, W)).astype(np.float32)
+    for kind in (R10, R01):
+        try:
+            y, _ = run(x, B, kind)
+            e = rel(y, ref_blocks(x, B, kind))
+            worst = max(worst, e)
+            print("ragged", (P, H, W, B), "kind", kind, "out %.3e" % e)
+        except Exception as e:
+            print("ragged", (P, H, W, B), "FAILED", e)
+# in place + round trip
+x = rng.standard_normal((4, 512, 512)).astype(np.float32)
+d = torch.from_numpy(x).cuda()
+for B in (8, 64):
+    d.copy_(torch.from_numpy(x))
+    lib.dsp_block_dct2d(b"f", d.data_ptr(), d.data_ptr(), 4, 512, 512, B, R10, 1.0, None)
+    lib.dsp_block_dct2d(b"f", d.data_ptr(), d.data_ptr(), 4, 512, 512, B, R01, 1.0 / (4.0 * B * B), None)
+    torch.cuda.synchronize()
+    print("in-place round trip B", B, "%.3e" % rel(d.cpu().numpy(), x.astype(np.float64)))
+print("WORST", worst)
+
+# timing: 64 planes of 2048 x 2048 (1 GiB in + 1 GiB out per launch), inputs larger than L2
+P, H, W = 64, 2048, 2048
+a = torch.randn(P, H, W, device="cuda")
+o = torch.empty_like(a)
+for B in (8, 16, 32, 64):
+    for _ in range(3):
+        lib.dsp_block_dct2d(b"f", a.data_ptr(), o.data_ptr(), P, H, W, B, R10, 1.0, None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 10
+    for _ in range(n):
+        lib.dsp_block_dct2d(b"f", a.data_ptr(), o.data_ptr(), P, H, W, B, R10, 1.0, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print("time B %2d  %.3f ms  %.1f Gpixel/s  %.0f GB/s" % (B, ms, P * H * W / ms / 1e6, 2 * 4 * P * H * W / ms / 1e6))
