@@ -17,8 +17,10 @@
 // lo = x - hi, exact) and each product is three MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM): the error is
 // ~2^-21 relative per product instead of 2^-11.
 //
-// One persistent CTA per SM, 256 threads.  Thread 0 issues the TMA loads (next tile's box lands while this one is
-// computed) and all MMAs; completion comes back through mbarriers (cp.async.bulk.tensor complete_tx, tcgen05.commit).
+// One persistent CTA per SM, 384 threads: eight front warps (operand split, MMA issue by thread 0, the TMEM -> shared
+// hand-over between the stages) and four store warps that drain the finished accumulator of the previous tile while the
+// front works on the next one (D2 is double-buffered in TMEM).  Thread 0 also issues the TMA loads two tiles ahead;
+// completion comes back through mbarriers (cp.async.bulk.tensor complete_tx, tcgen05.commit).
 #include "dsp_kernels.h"
 #include "dct_tma.cuh"
 #include <math.h>
@@ -29,9 +31,11 @@
 namespace dsp {
 
 constexpr int kMmTile = 128;             // tile edge: M of both MMAs
-constexpr int kMmThreads = 256;
+constexpr int kMmFront = 256;           // warps 0-7: operand preparation, MMA issue, TMEM hand-over between the stages
+constexpr int kMmEpi = 128;             // warps 8-11: accumulator -> global stores of the previous tile
+constexpr int kMmThreads = kMmFront + kMmEpi;
 constexpr int kMmBuf = kMmTile * kMmTile * 4;   // one operand buffer: 64 KB
-constexpr int kMmTmemCols = 256;         // D1 | D2
+constexpr int kMmTmemCols = 512;         // D1 | D2[0] | D2[1] (384 columns used; allocations are powers of two)
 
 struct BlockMmArgs {
 	TmaDesc in_map;          // [planes][H][W] floats, box {32, 128, 1}, 128-byte swizzle
@@ -42,10 +46,9 @@ struct BlockMmArgs {
 	int tiles_x, tiles_y;
 	long long ntiles;
 	float scale;
-	int variant;             // stage-2 operand layout: 0 K-major with the 128-byte swizzle, 1 / 2 MN-major unswizzled (bring-up)
 };
 
-static size_t block_mm_smem(int Be) { return 1024 + 3 * (size_t)kMmBuf + 8 * (size_t)Be * Be + 64; }
+static size_t block_mm_smem(int Be) { return 1024 + 3 * (size_t)kMmBuf + 8 * (size_t)Be * Be + 128; }
 
 // element (n, k) of an N x K operand stored K-major without swizzle: 8 x 16-byte core matrices, K chunks 128 bytes apart,
 // groups of 8 rows 32*K bytes apart (float index)
@@ -112,21 +115,27 @@ DSP_DEV void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
 }
 DSP_DEV float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+DSP_DEV void mm_front_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMmFront) : "memory"); }
+DSP_DEV void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+// barriers: [0] [1] tile landed in buffer 0 / 1 (TMA bytes); [2] stage 1 done; [3] stage 2 done (operand buffers free);
+// [4] [5] accumulator D2[0] / D2[1] complete (tcgen05.commit); [6] [7] D2[0] / D2[1] drained by the four store warps
+template <int BE>
 __global__ void __launch_bounds__(kMmThreads, 1) k_block_mm(const __grid_constant__ BlockMmArgs a) {
 	extern __shared__ unsigned char mm_smem_raw[];
 	const uint32_t raw = smem_u32(mm_smem_raw);
 	const uint32_t base = (raw + 1023u) & ~1023u;              // the swizzled boxes need 1024-byte alignment
 	unsigned char *sm = mm_smem_raw + (base - raw);
-	const int Be = a.Be, nb = kMmTile / Be;
+	constexpr int Be = BE, nb = kMmTile / BE;
 	float *Chi = (float *)(sm + 3 * kMmBuf);
-	uint64_t *bars = (uint64_t *)(sm + 3 * kMmBuf + 8 * Be * Be);     // [0], [1]: tile landed in buffer 0 / 1; [2]: MMAs done
-	uint32_t *tslot = (uint32_t *)(bars + 3);
+	uint64_t *bars = (uint64_t *)(sm + 3 * kMmBuf + 8 * Be * Be);
+	uint32_t *tslot = (uint32_t *)(bars + 8);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
 	if (tid == 0) {
-		mbar_init(&bars[0], 1);
-		mbar_init(&bars[1], 1);
-		mbar_init(&bars[2], 1);
+		for (int i = 0; i < 6; i++) mbar_init(&bars[i], 1);
+		mbar_init(&bars[6], kMmEpi / 32);
+		mbar_init(&bars[7], kMmEpi / 32);
 		mbar_fence_init();
 	}
 	for (int i = tid; i < 2 * Be * Be / 4; i += kMmThreads) ((float4 *)Chi)[i] = __ldg((const float4 *)a.consts + i);
@@ -139,85 +148,91 @@ __global__ void __launch_bounds__(kMmThreads, 1) k_block_mm(const __grid_constan
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = *(volatile uint32_t *)tslot;
-
-	const uint32_t c_hi = base + 3 * kMmBuf, c_lo = c_hi + 4 * Be * Be, s_lo = base + 2 * kMmBuf;
-	const uint32_t sbo_c = 32u * Be;
-	const uint32_t id1 = umma_idesc(kMmTile, Be, 0, 0), id2 = umma_idesc(kMmTile, Be, 1, 0);
 	const long long per_plane = (long long)a.tiles_x * a.tiles_y;
+	const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;          // a warp reaches the TMEM lanes of its quarter
 
-	auto issue_load = [&](long long tile, int b) {
-		const int plane = (int)(tile / per_plane);
-		const int rem = (int)(tile - plane * per_plane);
-		const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-		mbar_expect_tx(&bars[b], kMmBuf);
-		for (int j = 0; j < 4; j++) tma_load3(sm + b * kMmBuf + j * (kMmBuf / 4), &a.in_map, tx * kMmTile + 32 * j, ty * kMmTile, plane, &bars[b]);
-	};
-
-	long long t = blockIdx.x;
-	uint32_t mph = 0;
-	if (tid == 0 && t < a.ntiles) issue_load(t, 0);
-	for (int it = 0; t < a.ntiles; t += gridDim.x, it++) {
-		const int b = it & 1;
-		const uint32_t s_hi = base + b * kMmBuf;
-		if (tid == 0 && t + gridDim.x < a.ntiles) issue_load(t + gridDim.x, b ^ 1);
-		const int plane = (int)(t / per_plane);
-		const int rem = (int)(t - plane * per_plane);
-		const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-		mbar_wait_bounded(&bars[b], (it >> 1) & 1);
-
-		// split the tile in place: hi stays where the TMA put it, lo goes to the same offset of the second buffer
-		{
-			float4 *X4 = (float4 *)(sm + b * kMmBuf), *S4 = (float4 *)(sm + 2 * kMmBuf);
-#pragma unroll 4
-			for (int i = 0; i < kMmBuf / 16 / kMmThreads; i++) {
-				const int f = tid + kMmThreads * i;
-				const float4 v = X4[f];
-				const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-				X4[f] = h;
-				S4[f] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-			}
-		}
-		fence_proxy_async();
-		__syncthreads();
-
-		if (tid == 0) {                                                    // stage 1: contract along w
-			tc_fence_after();
+	if (warp < kMmFront / 32) {
+		// ---------------------------------------------------------------- front: split, both MMA stages, the transposing hand-over
+		const uint32_t c_hi = base + 3 * kMmBuf, c_lo = c_hi + 4 * Be * Be, s_lo = base + 2 * kMmBuf;
+		const uint32_t sbo_c = 32u * Be;
+		const uint32_t id1 = umma_idesc(kMmTile, Be, 0, 0);
+		auto issue_load = [&](long long tile, int b) {
+			const int plane = (int)(tile / per_plane);
+			const int rem = (int)(tile - plane * per_plane);
+			const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+			mbar_expect_tx(&bars[b], kMmBuf);
+			for (int j = 0; j < 4; j++) tma_load3(sm + b * kMmBuf + j * (kMmBuf / 4), &a.in_map, tx * kMmTile + 32 * j, ty * kMmTile, plane, &bars[b]);
+		};
+		// One stage = for every group of Be columns of K: D[:, g Be ..] = A_lo B_hi + A_hi B_lo + A_hi B_hi over Be / 8 k-steps.
+		// Both stages read their A operand in the same form (K-major, 128-byte swizzle, four boxes of 32 k), so the issue
+		// loop is shared; it is fully unrolled with every operand offset a compile-time constant: one thread issues all
+		// 48 MMAs of a stage, and its instruction stream is on the stage's critical path.
+		const uint64_t bd_hi = umma_desc(c_hi, 128, sbo_c, 0), bd_lo = umma_desc(c_lo, 128, sbo_c, 0);
+		auto issue_stage = [&](uint32_t a_hi_addr, uint32_t d_tmem) {
+			const uint64_t ad_hi = umma_desc(a_hi_addr, 16, 1024, 2), ad_lo = umma_desc(s_lo, 16, 1024, 2);
+#pragma unroll
 			for (int g = 0; g < nb; g++) {
-				uint32_t acc = 0;
+#pragma unroll
 				for (int term = 0; term < 3; term++) {
-					const uint32_t aop = term == 0 ? s_lo : s_hi, bop = term == 1 ? c_lo : c_hi;
+#pragma unroll
 					for (int kk = 0; kk < Be / 8; kk++) {
 						const int c0 = g * Be + 8 * kk;
-						const uint64_t ad = umma_desc(aop + (uint32_t)(c0 >> 5) * (kMmBuf / 4) + (uint32_t)(c0 & 31) * 4, 16, 1024, 2);
-						const uint64_t bd = umma_desc(bop + (uint32_t)kk * 256, 128, sbo_c, 0);
-						umma_tf32(tmem + g * Be, ad, bd, id1, acc);
-						acc = 1;
+						const uint64_t aoff = (uint64_t)(((c0 >> 5) * (kMmBuf / 4) + (c0 & 31) * 4) >> 4), boff = (uint64_t)((kk * 256) >> 4);
+						umma_tf32(d_tmem + g * Be, (term == 0 ? ad_lo : ad_hi) + aoff, (term == 1 ? bd_lo : bd_hi) + boff, id1, (term | kk) != 0);
 					}
 				}
 			}
-			umma_commit(&bars[2]);
-		}
-		mbar_wait_bounded(&bars[2], mph);
-		mph ^= 1;
-		tc_fence_after();
+		};
 
-		// D1 (lane = row) -> registers -> hi | lo -> the A operand of stage 2, A2[m = column][k = row], K-major in the
-		// same swizzled form the TMA gives stage 1: four boxes of 32 k, rows of 128 bytes, 16-byte chunk ^= m % 8.
-		// A warp (32 consecutive k, one m) stores one whole 128-byte row: no bank conflicts.
-		{
-			const int k = (warp & 3) * 32 + lane;
-			unsigned char *Thi = sm + b * kMmBuf, *Tlo = sm + 2 * kMmBuf;
-			const uint32_t koff = (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16;                  // MN-major variants
-			const uint32_t kbox = (uint32_t)(warp & 3) * (kMmBuf / 4), kch = (uint32_t)lane >> 2, kin = ((uint32_t)lane & 3) * 4;
+		long long t = blockIdx.x;
+		uint32_t ph = 0;
+		if (tid == 0) {
+			if (t < a.ntiles) issue_load(t, 0);
+			if (t + gridDim.x < a.ntiles) issue_load(t + gridDim.x, 1);
+		}
+		for (int it = 0; t < a.ntiles; t += gridDim.x, it++) {
+			const int b = it & 1;
+			const uint32_t s_hi = base + b * kMmBuf;
+			mbar_wait_bounded(&bars[b], (it >> 1) & 1);
+
+			// split the tile in place: hi stays where the TMA put it, lo goes to the same offset of the second buffer
+			{
+				float4 *X4 = (float4 *)(sm + b * kMmBuf), *S4 = (float4 *)(sm + 2 * kMmBuf);
+#pragma unroll 4
+				for (int i = 0; i < kMmBuf / 16 / kMmFront; i++) {
+					const int f = tid + kMmFront * i;
+					const float4 v = X4[f];
+					const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+					X4[f] = h;
+					S4[f] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+				}
+			}
+			fence_proxy_async();
+			mm_front_sync();
+
+			if (tid == 0) {                                                    // stage 1: contract along w
+				tc_fence_after();
+				issue_stage(s_hi, tmem);
+				umma_commit(&bars[2]);
+			}
+			mbar_wait_bounded(&bars[2], ph);
+			tc_fence_after();
+
+			// D1 (lane = row) -> registers -> hi | lo -> the A operand of stage 2, A2[m = column][k = row], K-major in the
+			// same swizzled form the TMA gives stage 1: four boxes of 32 k, rows of 128 bytes, 16-byte chunk ^= m % 8.
+			// A warp (32 consecutive k, one m) stores one whole 128-byte row: no bank conflicts.
+			{
+				const int k = (warp & 3) * 32 + lane;
+				unsigned char *Thi = sm + b * kMmBuf, *Tlo = sm + 2 * kMmBuf;
+				const uint32_t kbox = (uint32_t)(warp & 3) * (kMmBuf / 4), kch = (uint32_t)lane >> 2, kin = ((uint32_t)lane & 3) * 4;
 #pragma unroll 1
-			for (int u = 0; u < 2; u++) {
-				const int m0 = (warp >> 2) * 64 + u * 32;
-				uint32_t v[32];
-				tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + m0, v);
-				tmem_wait_ld();
-				if (a.dbg && blockIdx.x == 0 && it == 0)
-					for (int i = 0; i < 32; i++) a.dbg[k * kMmTile + m0 + i] = __uint_as_float(v[i]);
-				if (a.variant == 0) {
+				for (int u = 0; u < 2; u++) {
+					const int m0 = (warp >> 2) * 64 + u * 32;
+					uint32_t v[32];
+					tmem_ld32(tmem + lane_base + m0, v);
+					tmem_wait_ld();
+					if (a.dbg && blockIdx.x == 0 && it == 0)
+						for (int i = 0; i < 32; i++) a.dbg[k * kMmTile + m0 + i] = __uint_as_float(v[i]);
 #pragma unroll
 					for (int i = 0; i < 32; i++) {
 						const float x = __uint_as_float(v[i]), h = tf32_hi(x);
@@ -226,69 +241,65 @@ __global__ void __launch_bounds__(kMmThreads, 1) k_block_mm(const __grid_constan
 						*(float *)(Thi + off) = h;
 						*(float *)(Tlo + off) = x - h;
 					}
-				} else {
-#pragma unroll
-					for (int g8 = 0; g8 < 8; g8++) {
-						const float x0 = __uint_as_float(v[4 * g8]), x1 = __uint_as_float(v[4 * g8 + 1]), x2 = __uint_as_float(v[4 * g8 + 2]),
-						            x3 = __uint_as_float(v[4 * g8 + 3]);
-						const float4 h = make_float4(tf32_hi(x0), tf32_hi(x1), tf32_hi(x2), tf32_hi(x3));
-						const uint32_t off = (uint32_t)((m0 >> 2) + g8) * 2048 + koff;
-						*(float4 *)(Thi + off) = h;
-						*(float4 *)(Tlo + off) = make_float4(x0 - h.x, x1 - h.y, x2 - h.z, x3 - h.w);
-					}
 				}
 			}
-		}
-		tc_fence_before();
-		fence_proxy_async();
-		__syncthreads();
+			tc_fence_before();
+			fence_proxy_async();
+			mm_front_sync();
 
-		if (tid == 0) {                                                    // stage 2: contract along h
-			tc_fence_after();
-			for (int g = 0; g < nb; g++) {
-				uint32_t acc = 0;
-				for (int term = 0; term < 3; term++) {
-					const uint32_t aop = term == 0 ? s_lo : s_hi, bop = term == 1 ? c_lo : c_hi;
-					for (int kk = 0; kk < Be / 8; kk++) {
-						const int k0 = g * Be + 8 * kk;
-						const uint64_t ad = a.variant == 0   ? umma_desc(aop + (uint32_t)(k0 >> 5) * (kMmBuf / 4) + (uint32_t)(k0 & 31) * 4, 16, 1024, 2)
-						                    : a.variant == 1 ? umma_desc(aop + (uint32_t)(k0 >> 3) * 128, 128, 2048, 0)
-						                                     : umma_desc(aop + (uint32_t)(k0 >> 3) * 128, 2048, 128, 0);
-						const uint64_t bd = umma_desc(bop + (uint32_t)kk * 256, 128, sbo_c, 0);
-						umma_tf32(tmem + kMmTile + g * Be, ad, bd, a.variant == 0 ? id1 : id2, acc);
-						acc = 1;
-					}
-				}
+			if (tid == 0) {                                                    // stage 2: contract along h, into D2[it & 1]
+				if (it >= 2) mbar_wait_bounded(&bars[6 + b], ((it >> 1) - 1) & 1);          // drained by the store warps (tile it - 2)
+				tc_fence_after();
+				issue_stage(s_hi, tmem + kMmTile * (1 + b));
+				umma_commit(&bars[4 + b]);
+				umma_commit(&bars[3]);
 			}
-			umma_commit(&bars[2]);
+			mbar_wait_bounded(&bars[3], ph);                                       // operand buffers free again
+			ph ^= 1;
+			if (tid == 0 && t + 2 * (long long)gridDim.x < a.ntiles) issue_load(t + 2 * (long long)gridDim.x, b);
 		}
-		mbar_wait_bounded(&bars[2], mph);
-		mph ^= 1;
-		tc_fence_after();
-
-		// D2 (lane = image column, TMEM column = image row) -> global: a warp stores 128 contiguous bytes per row
-		{
+	} else {
+		// ---------------------------------------------------------------- store warps: D2 (lane = image column, TMEM column =
+		// image row) -> global while the front works on the next tile; a warp stores 128 contiguous bytes per row
+		long long t = blockIdx.x;
+		for (int it = 0; t < a.ntiles; t += gridDim.x, it++) {
+			const int b = it & 1;
+			const int plane = (int)(t / per_plane);
+			const int rem = (int)(t - plane * per_plane);
+			const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
 			const int m = (warp & 3) * 32 + lane;
 			const int col = tx * kMmTile + m;
+			const int rows = a.H - ty * kMmTile;                                   // rows of this tile inside the plane (>= 128: all)
 			float *op = a.out + ((long long)plane * a.H + (long long)ty * kMmTile) * a.W + col;
+			mbar_wait_bounded(&bars[4 + b], (it >> 1) & 1);
+			tc_fence_after();
 #pragma unroll 1
-			for (int u = 0; u < 2; u++) {
-				const int r0 = (warp >> 2) * 64 + u * 32;
+			for (int u = 0; u < 4; u++) {
 				uint32_t v[32];
-				tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + kMmTile + r0, v);
+				tmem_ld32(tmem + lane_base + kMmTile * (1 + b) + 32 * u, v);
 				tmem_wait_ld();
 				if (a.dbg && blockIdx.x == 0 && it == 0)
-					for (int i = 0; i < 32; i++) a.dbg[kMmTile * kMmTile + (r0 + i) * kMmTile + m] = __uint_as_float(v[i]);
+					for (int i = 0; i < 32; i++) a.dbg[kMmTile * kMmTile + (32 * u + i) * kMmTile + m] = __uint_as_float(v[i]);
 				if (col < a.W) {
+					float *p = op;
+					if (32 * u + 32 <= rows) {
 #pragma unroll
-					for (int i = 0; i < 32; i++)
-						if (ty * kMmTile + r0 + i < a.H) op[(long long)(r0 + i) * a.W] = __uint_as_float(v[i]) * a.scale;
+						for (int i = 0; i < 32; i++, p += a.W) *p = __uint_as_float(v[i]) * a.scale;
+					} else {
+#pragma unroll
+						for (int i = 0; i < 32; i++, p += a.W)
+							if (32 * u + i < rows) *p = __uint_as_float(v[i]) * a.scale;
+					}
 				}
+				op += 32 * (long long)a.W;
 			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bars[6 + b]);
 		}
-		tc_fence_before();
-		__syncthreads();
 	}
+	tc_fence_before();
+	__syncthreads();
 	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kMmTmemCols) : "memory");
 }
 #endif  // DSP_GPU
@@ -363,7 +374,6 @@ bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, 
 	a.tiles_x = (W + kMmTile - 1) / kMmTile; a.tiles_y = (H + kMmTile - 1) / kMmTile;
 	a.ntiles = (long long)a.tiles_x * a.tiles_y * nplanes;
 	a.scale = (float)scale;
-	{ const char *e = getenv("DSP_BLOCKMM_VARIANT"); a.variant = e ? atoi(e) : 0; }
 	static int sm_count[64] = {0};
 	static unsigned long long attr_dev = 0;
 	const int dev = rt_device() & 63;
@@ -373,11 +383,16 @@ bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, 
 		sm_count[dev] = s;
 	}
 	if (!((attr_dev >> dev) & 1ull)) {
-		if (!rt_ok(cudaFuncSetAttribute(k_block_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_mm_smem(64)), err, "smem attribute")) return false;
+		if (!rt_ok(cudaFuncSetAttribute(k_block_mm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_mm_smem(16)), err, "smem attribute") ||
+		    !rt_ok(cudaFuncSetAttribute(k_block_mm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_mm_smem(32)), err, "smem attribute") ||
+		    !rt_ok(cudaFuncSetAttribute(k_block_mm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_mm_smem(64)), err, "smem attribute"))
+			return false;
 		attr_dev |= 1ull << dev;
 	}
 	const int grid = (int)(a.ntiles < sm_count[dev] ? a.ntiles : sm_count[dev]);
-	k_block_mm<<<grid, kMmThreads, block_mm_smem(Be), st>>>(a);
+	if (Be == 16) k_block_mm<16><<<grid, kMmThreads, block_mm_smem(16), st>>>(a);
+	else if (Be == 32) k_block_mm<32><<<grid, kMmThreads, block_mm_smem(32), st>>>(a);
+	else k_block_mm<64><<<grid, kMmThreads, block_mm_smem(64), st>>>(a);
 	return rt_ok(cudaGetLastError(), err, "block DCT GEMM launch");
 #else
 	// emulation (tests/emu): the same contraction as plain loops in double; the tensor-core path itself only exists on the GPU

@@ -51,7 +51,7 @@ def run(x, B, kind, debug=False):
 import os
 rng = np.random.default_rng(5)
 worst = 0.0
-for variant in (2, 1, 0):
+for variant in (0,):
   os.environ["DSP_BLOCKMM_VARIANT"] = str(variant)
   print("---- stage-2 operand variant", variant)
   for B in (64, 32, 16, 8):
