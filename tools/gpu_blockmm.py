@@ -52,8 +52,8 @@ import os
 rng = np.random.default_rng(5)
 worst = 0.0
 for variant in (0,):
-  os.environ["DSP_BLOCKMM_VARIANT"] = str(variant)
-  print("---- stage-2 operand variant", variant)
+  os.environ["DSP_BLOCKMM_RAWHI"] = str(variant)
+  print("---- raw hi operand", variant)
   for B in (64, 32, 16, 8):
     for kind in (R10, R01):
           x = rng.standard_normal((2, 256, 384)).astype(np.float32)
