@@ -11,6 +11,8 @@ The default invocation measures the three configurations BASELINE.json's north_s
             motion3d    C5  one 1920x1080x256 yuv420p 8-bit volume (Y + U + V), frame slabs over the ranks, 8-bit pels in
                             -> 3-D DCT -> coefficient stages -> inverse -> 8-bit pels out; exchange around the temporal
                             transform fused into the transform (peer stores over NVLink) or NCCL all-to-all
+            blocks      8f-3 every 8x8 block of 64 planes of 2048x2048 float32 per GPU, forward + inverse: the tensor-core
+                            GEMM kernel (tcgen05, 3 x TF32); weak scaling, no collective
 
 `--workload X` runs one workload alone (profiling); `--impl reference` runs the CPU arm (oracle port: scipy pocketfft
 on all host threads; FFTW is not in the image).
@@ -43,6 +45,7 @@ WORKLOADS = {
     "plane4096x3": (4096, 4096, 3, 2, "f", "weak"),
 }
 # BASELINE config 5: yuv420p, 8-bit: (name, D, H, W)
+BLOCKS = dict(planes=64, h=2048, w=2048, B=8)       # motion -b 8x8x1-style 2-D block DCT, per GPU
 MOTION_PLANES = (("Y", 256, 1080, 1920), ("U", 256, 540, 960), ("V", 256, 540, 960))
 
 
@@ -216,6 +219,25 @@ def cpu_roundtrip_3d(D, H, W, steps, warmup):
     return D * H * W / dt / 1e9, cores, dt
 
 
+def cpu_roundtrip_blocks(planes, h, w, B, steps, warmup):
+    """every B x B block of [planes][h][w]: 2-D DCT-II then DCT-III, scipy pocketfft over the in-block axes, all threads"""
+    cores = _cpu_threads()
+    import numpy as np
+    from oracle import dct as od
+    x = np.random.default_rng(0).random((planes, h // B, B, w // B, B)).astype(np.float32)
+
+    def one():
+        y = od.dctn_fast(x, [od.REDFT10] * 2, axes=(2, 4), workers=cores)
+        return od.dctn_fast(y, [od.REDFT01] * 2, axes=(2, 4), workers=cores)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return planes * h * w / dt / 1e9, cores, dt
+
+
 def cpu_sample_planes(h, w, d):
     """bounded CPU sample of a 2-D workload: about 2^24 samples per step"""
     return 1 if h * w * d >= (1 << 24) else max(1, (1 << 24) // (h * w * d))
@@ -270,9 +292,22 @@ def run_reference(args):
                                            "scipy pocketfft workers=%d (oracle port; FFTW is not in the image)" % (Ds, cores)},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
-    out = rec3d() if name == "motion3d" else rec2d(name)
+    def recblocks():
+        b = BLOCKS
+        n = 4
+        steps, warm = min(args.steps, 5), min(args.warmup, 1)
+        v, cores, dt = cpu_roundtrip_blocks(n, b["h"], b["w"], b["B"], steps, warm)
+        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": "blocks", **b},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "each step = %d of the %d planes, every %dx%d block forward+inverse, scipy pocketfft "
+                                           "workers=%d (oracle port)" % (n, b["planes"], b["B"], b["B"], cores)},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    out = rec3d() if name == "motion3d" else recblocks() if name == "blocks" else rec2d(name)
     if args.workload == "all":
-        out["records"] = {"batch1024": rec2d("batch1024"), "motion3d": rec3d()}
+        out["records"] = {"batch1024": rec2d("batch1024"), "motion3d": rec3d(), "blocks": recblocks()}
     print(json.dumps(out))
 
 
@@ -589,13 +624,102 @@ def bench_motion3d(ctx, args, want_cpu):
     return rec
 
 
+def bench_blocks(ctx, args, want_cpu):
+    """every 8 x 8 block of 64 planes of 2048 x 2048 floats per GPU, REDFT10 then REDFT01 (normalised), in place:
+    dsp_block_dct2d, the tcgen05 GEMM kernel (csrc/kern_block_mm.cu).  Independent planes: weak scaling, no collective."""
+    torch = ctx.torch
+    from dspfun_b200 import capi
+    lib = ctx.lib
+    b = BLOCKS
+    P, H, W, B = b["planes"], b["h"], b["w"], b["B"]
+    g = torch.Generator(device="cuda").manual_seed(11 + ctx.rank)
+    x = torch.rand(P, H, W, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def call(src, dst, kind, scale, bsize=B):
+        if lib.dsp_block_dct2d(b"f", src.data_ptr(), dst.data_ptr(), P, H, W, bsize, kind, scale, stream) != 0:
+            raise RuntimeError(capi.last_error(lib))
+
+    def step():
+        call(x, y, capi.REDFT10, 1.0)
+        call(y, y, capi.REDFT01, 1.0 / (4.0 * B * B))
+
+    sampler = ClockSampler(ctx.local)
+    ms, launches = ctx.timed(step, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    err = float((y - x).double().norm() / x.double().norm())
+    samples = P * H * W
+    value = samples * ctx.world * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    abytes = 16.0 * samples                       # per GPU and step: each transform reads and writes every float once
+    ach = abytes * args.steps / (ms * 1e-3) / 1e9
+    # the forward launch alone, per block size (CUDA events on the launching stream)
+    sizes = {}
+    for bs in (8, 16, 32, 64):
+        for _ in range(2):
+            call(x, y, capi.REDFT10, 1.0, bs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            call(x, y, capi.REDFT10, 1.0, bs)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 5
+        sizes[str(bs)] = {"ms": t, "gpixel_s": samples / t / 1e6, "achieved_gbs": 8.0 * samples / t / 1e6, "frac": 8.0 * samples / t / 1e6 / peak}
+    e2e = None
+    if not args.no_e2e:
+        n = 16
+        hin = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
+        hout = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
+        hin.copy_(x[:n])
+        ks = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            x[:n].copy_(hin, non_blocking=True)
+            if lib.dsp_block_dct2d(b"f", x.data_ptr(), y.data_ptr(), n, H, W, B, capi.REDFT10, 1.0, stream) != 0 or \
+               lib.dsp_block_dct2d(b"f", y.data_ptr(), y.data_ptr(), n, H, W, B, capi.REDFT01, 1.0 / (4.0 * B * B), stream) != 0:
+                raise RuntimeError(capi.last_error(lib))
+            hout.copy_(y[:n], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ks):
+            e2e_step()
+        ctx.barrier()
+        dt = ctx.max_over_ranks((time.perf_counter() - t0) / ks)
+        e2e = {"value": n * H * W * ctx.world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * H * W * 4, "d2h_bytes_per_step": n * H * W * 4,
+               "steps": ks, "ms_per_step": dt * 1e3, "sample": "%d of the rank's %d planes per step" % (n, P),
+               "path": "pinned host planes -> device -> dsp_block_dct2d forward + inverse -> pinned host planes"}
+    cpu = None
+    if ctx.rank == 0 and ctx.world == 1 and want_cpu:
+        v, cores, dt = cpu_roundtrip_blocks(4, H, W, B, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "4 of the %d planes, every %dx%d block forward+inverse, scipy pocketfft workers=%d (oracle port)" % (P, B, B, cores)}
+    rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accuracy)",
+           "data": "synthetic",
+           "config": {"workload": "blocks", **b, "planes_per_gpu": P,
+                      "l2_policy": "inputs larger than L2 (%.0f MB per GPU per step)" % (samples * 4 / 1e6),
+                      "parallelism": "independent planes per GPU, no collective"},
+           "roofline": {"bound": "hbm", "kernel": "k_block_mm<16>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_sample": 16,
+                        "note": "forward 4 B in + 4 B out, inverse the same; the tensor work (3 x TF32) is far below the tensor roofline"},
+           "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roundtrip_rel_l2": err,
+           "forward_by_block_size": sizes}
+    del x, y
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS) + ["motion3d"])
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS) + ["motion3d", "blocks"])
     ap.add_argument("--planes", type=int, default=0, help="planes/images per GPU (weak) or in total (strong); 0 = workload default")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -610,9 +734,10 @@ def main():
     if args.workload == "all":
         out = bench_planes(ctx, args, "plane8192", want_cpu)
         recs = {}
-        for nm in ("batch1024", "motion3d"):
+        for nm in ("batch1024", "motion3d", "blocks"):
             try:
-                recs[nm] = bench_planes(ctx, args, nm, want_cpu) if nm != "motion3d" else bench_motion3d(ctx, args, want_cpu)
+                recs[nm] = (bench_motion3d(ctx, args, want_cpu) if nm == "motion3d" else bench_blocks(ctx, args, want_cpu) if nm == "blocks"
+                            else bench_planes(ctx, args, nm, want_cpu))
             except Exception as e:                              # a failing sub-record must not take the headline with it
                 recs[nm] = {"error": repr(e)}
                 ctx.torch.cuda.synchronize()
@@ -620,6 +745,8 @@ def main():
         out["gpu_launches_total"] = out["gpu_launches"] + sum(r.get("gpu_launches", 0) for r in recs.values())
     elif args.workload == "motion3d":
         out = bench_motion3d(ctx, args, want_cpu)
+    elif args.workload == "blocks":
+        out = bench_blocks(ctx, args, want_cpu)
     else:
         out = bench_planes(ctx, args, args.workload, want_cpu)
     if ctx.rank == 0:

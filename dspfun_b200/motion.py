@@ -88,10 +88,14 @@ class MotionTiled:
     clamp / round / 8-bit store: motion.c:644-647, 740-751, 757-776) are one pass each (dsp_block_quant,
     dsp_block_store_u8), evaluated in double like the fused per-block path; filters other than --quant stay with
     `Motion` (block at a time).
+    Square spatial blocks of 8, 16, 32 or 64 (the README's 8x8x8 among them) skip the w and h plans: dsp_block_dct2d
+    contracts both spatial axes of every block in one pass over the volume on the tensor cores (tcgen05 MMAs, TF32
+    operands split hi + lo for float accuracy; csrc/kern_block_mm.cu), and only the d axis remains a plan.
+    `gemm=False` forces the three-plan path.
     Works on torch tensors: CUDA with the product library, CPU with the emulation library (tests).
     """
 
-    def __init__(self, dims, block, quant=0.0, float_pixels=False, lib=None):
+    def __init__(self, dims, block, quant=0.0, float_pixels=False, lib=None, gemm=True):
         import torch
         self.torch = torch
         self.lib = lib if lib is not None else capi.load()
@@ -107,8 +111,21 @@ class MotionTiled:
             return (Plan("f", [bw], [kind], (W // bw) * H * D, None, 1, bw, None, 1, bw, lib=self.lib),
                     Plan("f", [bh], [kind], W, None, W, 1, None, W, 1, (H // bh) * D, bh * W, bh * W, lib=self.lib),
                     Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib))
+        self.gemm = bool(gemm) and bh == bw and bw in (8, 16, 32, 64)
+        if self.gemm:
+            def plans(kind):                                  # the d axis only (none for depth-1 blocks)
+                if bd == 1:
+                    return ()
+                return (Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib),)
         self.fwd = plans(capi.REDFT10)
         self.inv = plans(capi.REDFT01)[::-1]
+
+    def _spatial(self, c, kind, stream):
+        D, H, W = self.dims
+        # depth-1 blocks have no d plan: FFTW's REDFT10 of length 1 doubles its sample (REDFT01 of length 1 copies it)
+        scale = 2.0 if (self.block[0] == 1 and kind == capi.REDFT10) else 1.0
+        if self.lib.dsp_block_dct2d(b"f", c.data_ptr(), c.data_ptr(), D, H, W, self.block[2], kind, scale, stream) != 0:
+            raise capi.DspDctError(capi.last_error(self.lib))
 
     def process(self, pels):
         """pels: [D][H][W] torch tensor, uint8 (or float32 in [0,1] with float_pixels).  Returns the processed volume."""
@@ -121,6 +138,8 @@ class MotionTiled:
             c = (pels.to(t.float64) * 255.0).to(t.float32).contiguous()                         # motion.c:618-637
         else:
             c = pels.to(t.float32).contiguous()                                                 # (8-bit values are exact)
+        if self.gemm:
+            self._spatial(c, capi.REDFT10, stream)
         for p in self.fwd:
             p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :641 for every block
         # normalise, quantise + count, de-normalise: one pass (dsp_block_quant, :644-647, :740-751)
@@ -130,6 +149,8 @@ class MotionTiled:
             raise capi.DspDctError(capi.last_error(self.lib))
         for p in self.inv:
             p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :753
+        if self.gemm:
+            self._spatial(c, capi.REDFT01, stream)
         scale = float((1.0 / np.sqrt(np.float64(bd * bh * bw * 8))) ** 2)                       # :757,767 (sf = 1)
         if self.quant:
             self.coeffs_coded += int(cnt.item())

@@ -299,7 +299,43 @@ def check_zoom(lib, prec, h, w, seed=8, **kw):
     return path, got, want
 
 
-def check_motion_tiled(lib, dims, block, quant=0.0, seed=12, device="cpu"):
+def block_dct2d_reference(x, B, kind):
+    """every B x B block of [P][H][W] through the oracle's 2-D transform, in double"""
+    P, H, W = x.shape
+    want = np.empty(x.shape, dtype=np.float64)
+    for p in range(P):
+        for y in range(0, H, B):
+            for xx in range(0, W, B):
+                want[p, y:y + B, xx:xx + B] = od.dctn_fast(x[p, y:y + B, xx:xx + B].astype(np.float64), [ORK[kind], ORK[kind]])
+    return want
+
+
+def check_block_dct2d(lib, shape, B, kind, tol, device="cpu", seed=17, in_place=False, scale=1.0):
+    """dsp_block_dct2d (tensor-core GEMM on the GPU, plain loops in the emulation build) == the oracle per block"""
+    import torch
+    P, H, W = shape
+    x = np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+    d_in = torch.from_numpy(x.copy()).to(device)
+    d_out = d_in if in_place else torch.full_like(d_in, np.nan)
+    stream = torch.cuda.current_stream().cuda_stream if device != "cpu" else None
+    rc = lib.dsp_block_dct2d(b"f", d_in.data_ptr(), d_out.data_ptr(), P, H, W, B, kind, scale, stream)
+    assert rc == 0, capi_last_error(lib)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    if not in_place:
+        assert np.array_equal(d_in.cpu().numpy(), x), "out-of-place call must leave the input alone"
+    err = od.rel_l2(got, block_dct2d_reference(x, B, kind) * scale)
+    assert err < tol, (shape, B, kind, err)
+    return err
+
+
+def capi_last_error(lib):
+    from dspfun_b200 import capi
+    return capi.last_error(lib)
+
+
+def check_motion_tiled(lib, dims, block, quant=0.0, seed=12, device="cpu", gemm=True):
     """MotionTiled (all blocks of a volume through three per-axis plans) == the reference block loop, block by block:
     8-bit output identical except where the reference's unrounded pel sits on a rounding tie; coded counts equal."""
     import torch
@@ -307,11 +343,11 @@ def check_motion_tiled(lib, dims, block, quant=0.0, seed=12, device="cpu"):
     D, H, W = dims
     bd, bh, bw = block
     v = np.random.default_rng(seed).integers(16, 236, dims).astype(np.uint8)
-    mt = MotionTiled(dims, block, quant=quant, lib=lib)
+    mt = MotionTiled(dims, block, quant=quant, lib=lib, gemm=gemm)
     out = mt.process(torch.from_numpy(v.copy()).to(device)).cpu().numpy()
     # sharding along d in whole blocks needs no exchange: the two halves processed separately give the same pels
     if (D // bd) % 2 == 0:
-        half = MotionTiled((D // 2, H, W), block, quant=quant, lib=lib)
+        half = MotionTiled((D // 2, H, W), block, quant=quant, lib=lib, gemm=gemm)
         lo = half.process(torch.from_numpy(v[:D // 2].copy()).to(device)).cpu().numpy()
         hi = half.process(torch.from_numpy(v[D // 2:].copy()).to(device)).cpu().numpy()
         half.destroy()

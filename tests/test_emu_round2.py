@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from dspfun_b200 import REDFT01, REDFT10, Plan
+from dspfun_b200 import REDFT01, REDFT10, Plan, capi
 from dspfun_b200 import spec as gspec
 from oracle import dct as od
 from oracle import pipelines as pl
@@ -169,3 +169,29 @@ def test_ring_column_subpasses_batched_and_scaled(lib, small_panels):
     p.destroy()
     ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 2, axes=(1, 2)) * 0.25
     assert od.rel_l2(y, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- block DCT by GEMM (host logic)
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("shape,B", [((2, 32, 48), 8), ((1, 64, 32), 16), ((3, 32, 96), 32), ((1, 128, 64), 64), ((1, 200, 328), 8)])
+def test_block_dct2d_matches_oracle_blocks(lib, kind, shape, B):
+    """the emulation build runs the same contraction as loops (the tcgen05 path itself is covered by tests/test_gpu_round2.py)"""
+    cases.check_block_dct2d(lib, shape, B, kind, 2e-6)
+    cases.check_block_dct2d(lib, shape, B, kind, 2e-6, in_place=True, scale=0.25)
+
+
+def test_block_dct2d_refuses_what_it_cannot_do(lib):
+    x = np.zeros((1, 48, 48), np.float32)
+    for args in ((b"f", 1, 48, 48, 12), (b"f", 1, 48, 40, 16), (b"d", 1, 48, 48, 8), (b"f", 0, 48, 48, 8)):
+        prec, P, H, W, B = args
+        assert lib.dsp_block_dct2d(prec, x.ctypes.data, x.ctypes.data, P, H, W, B, REDFT10, 1.0, None) != 0
+        assert capi.last_error(lib)
+    assert lib.dsp_block_dct2d(b"f", x.ctypes.data, x.ctypes.data, 1, 48, 48, 8, 3, 1.0, None) != 0      # not a DCT kind
+
+
+def test_motion_tiled_gemm_and_plan_paths_agree(lib):
+    """MotionTiled with the spatial axes on dsp_block_dct2d == the three-plan path == the reference block loop"""
+    cases.check_motion_tiled(lib, (16, 16, 24), (8, 8, 8), gemm=False)
+    cases.check_motion_tiled(lib, (16, 16, 24), (8, 8, 8), quant=0.05, gemm=False)
+    cases.check_motion_tiled(lib, (2, 32, 64), (1, 16, 16), quant=0.02)
+    cases.check_motion_tiled(lib, (2, 32, 64), (2, 32, 32))

@@ -178,3 +178,78 @@ def test_motion_spectrogram_modes(lib, kw):
     cases.check_motion(lib, (4, 8, 8), **kw)
     cases.check_motion(lib, (8, 30, 40), **kw)
     cases.check_motion(lib, (4, 8, 12), float_pixels=True, **kw)
+
+
+# ---------------------------------------------------------------------------------------------- block DCT on the tensor cores
+# float tolerance of the 3 x TF32 GEMM path: products carry ~2^-21 relative error (the FFT passes: ~1e-7); measured
+# 6e-7 (B = 8) .. 1e-6 (B = 64) relative L2 on normal data, asserted at 3e-6
+BLOCK_MM_TOL = 3e-6
+
+
+@pytest.mark.parametrize("kind", [REDFT10, REDFT01])
+@pytest.mark.parametrize("B", [8, 16, 32, 64])
+def test_block_dct2d_tensor_cores_vs_oracle(lib, kind, B):
+    """whole tiles, several tiles per CTA (more tiles than SMs), planes that are not multiples of the 128 x 128 tile"""
+    cases.check_block_dct2d(lib, (2, 256, 384), B, kind, BLOCK_MM_TOL, device="cuda")
+    cases.check_block_dct2d(lib, (3, 192, 320), B, kind, BLOCK_MM_TOL, device="cuda", in_place=True, scale=0.5)
+    cases.check_block_dct2d(lib, (1, 64, 64), B, kind, BLOCK_MM_TOL, device="cuda")
+
+
+def test_block_dct2d_ragged_and_many_tiles(lib):
+    cases.check_block_dct2d(lib, (1, 1080, 1920), 8, REDFT10, BLOCK_MM_TOL, device="cuda")        # C5's frame: 8.4 tiles high
+    cases.check_block_dct2d(lib, (1, 144, 16), 16, REDFT01, BLOCK_MM_TOL, device="cuda")
+    cases.check_block_dct2d(lib, (40, 256, 256), 32, REDFT10, BLOCK_MM_TOL, device="cuda")        # 160 tiles > 148 SMs: ring wrap
+    cases.check_block_dct2d(lib, (5, 1024, 640), 64, REDFT01, BLOCK_MM_TOL, device="cuda", in_place=True)
+
+
+def test_block_dct2d_equals_the_plan_path_and_round_trips(lib):
+    """the same blocks through two per-axis plans (FFT passes); forward then inverse / (4 B^2) returns the planes"""
+    import torch
+    P, H, W, B = 4, 512, 768, 16
+    x = torch.randn(P, H, W, device="cuda")
+    y = torch.empty_like(x)
+    assert lib.dsp_block_dct2d(b"f", x.data_ptr(), y.data_ptr(), P, H, W, B, REDFT10, 1.0, None) == 0
+    pw = Plan("f", [B], [REDFT10], (W // B) * H * P, None, 1, B, None, 1, B, lib=lib)
+    ph = Plan("f", [B], [REDFT10], W, None, W, 1, None, W, 1, (H // B) * P, B * W, B * W, lib=lib)
+    z = x.clone()
+    pw.execute_dev(z.data_ptr(), z.data_ptr(), None)
+    ph.execute_dev(z.data_ptr(), z.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert od.rel_l2(y.cpu().numpy(), z.cpu().numpy().astype(np.float64)) < BLOCK_MM_TOL
+    assert lib.dsp_block_dct2d(b"f", y.data_ptr(), y.data_ptr(), P, H, W, B, REDFT01, 1.0 / (4.0 * B * B), None) == 0
+    torch.cuda.synchronize()
+    assert od.rel_l2(y.cpu().numpy(), x.cpu().numpy().astype(np.float64)) < 2 * BLOCK_MM_TOL
+    pw.destroy()
+    ph.destroy()
+
+
+def test_block_dct2d_full_size_properties(lib):
+    """64 planes of 2048 x 2048 (1 GiB): linearity and the round trip, with sampled blocks against the oracle"""
+    import torch
+    P, H, W, B = 64, 2048, 2048, 8
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(P, H, W, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    assert lib.dsp_block_dct2d(b"f", x.data_ptr(), y.data_ptr(), P, H, W, B, REDFT10, 1.0, None) == 0
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(4)
+    for _ in range(32):
+        p, by, bx = int(rng.integers(P)), int(rng.integers(H // B)) * B, int(rng.integers(W // B)) * B
+        blk = x[p, by:by + B, bx:bx + B].cpu().numpy().astype(np.float64)
+        assert od.rel_l2(y[p, by:by + B, bx:bx + B].cpu().numpy(), od.dctn_fast(blk, [od.REDFT10, od.REDFT10])) < 2 * BLOCK_MM_TOL
+    # Parseval per plane for the orthogonalised transform: sum y^2 w = (2B)^2 sum x^2 with w = 1/2 on each zero index
+    w = torch.ones(B, device="cuda", dtype=torch.float64)
+    w[0] = 0.5
+    wy = (w.repeat(H // B)[:, None] * w.repeat(W // B)[None, :])
+    e_y = float((y[0].double() ** 2 * wy).sum())
+    e_x = float((x[0].double() ** 2).sum()) * (2.0 * B) ** 2
+    assert abs(e_y / e_x - 1.0) < 1e-5
+    assert lib.dsp_block_dct2d(b"f", y.data_ptr(), y.data_ptr(), P, H, W, B, REDFT01, 1.0 / (4.0 * B * B), None) == 0
+    torch.cuda.synchronize()
+    assert float((y - x).double().norm() / x.double().norm()) < 2 * BLOCK_MM_TOL
+
+
+def test_motion_tiled_on_the_gemm_path(lib):
+    cases.check_motion_tiled(lib, (16, 64, 96), (8, 8, 8), device="cuda", gemm=False)
+    cases.check_motion_tiled(lib, (4, 128, 256), (2, 32, 32), quant=0.02, device="cuda")
+    cases.check_motion_tiled(lib, (2, 128, 128), (1, 64, 64), device="cuda")
