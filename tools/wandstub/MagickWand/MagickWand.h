@@ -31,6 +31,8 @@ size_t MagickGetImageWidth(MagickWand *);
 size_t MagickGetImageHeight(MagickWand *);
 MagickBooleanType MagickTransformImageColorspace(MagickWand *, ColorspaceType);
 MagickBooleanType MagickSetImageColorspace(MagickWand *, ColorspaceType);
+ColorspaceType MagickGetImageColorspace(MagickWand *);      /* sRGB unless the file carries PROP colorspace RGB */
+size_t MagickGetImageDepth(MagickWand *);                   /* PROP depth N, default 8 */
 MagickBooleanType MagickExportImagePixels(MagickWand *, long x, long y, size_t w, size_t h, const char *map, StorageType, void *);
 MagickBooleanType MagickConstituteImage(MagickWand *, size_t w, size_t h, const char *map, StorageType, const void *);
 MagickBooleanType MagickSetImageProperty(MagickWand *, const char *, const char *);

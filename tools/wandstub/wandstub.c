@@ -31,6 +31,20 @@ size_t MagickGetImageHeight(MagickWand *w) { return w->h; }
 MagickBooleanType MagickTransformImageColorspace(MagickWand *w, ColorspaceType c) { (void)w; (void)c; return MagickTrue; }
 MagickBooleanType MagickSetImageColorspace(MagickWand *w, ColorspaceType c) { (void)w; (void)c; return MagickTrue; }
 
+static const char *wand_prop(MagickWand *w, const char *key) {
+	for (int i = 0; i < w->nprops; i++)
+		if (!strcmp(w->keys[i], key)) return w->vals[i];
+	return NULL;
+}
+ColorspaceType MagickGetImageColorspace(MagickWand *w) {
+	const char *v = wand_prop(w, "colorspace");
+	return v && !strcmp(v, "RGB") ? RGBColorspace : sRGBColorspace;
+}
+size_t MagickGetImageDepth(MagickWand *w) {
+	const char *v = wand_prop(w, "depth");
+	return v ? (size_t)strtoul(v, NULL, 10) : 8;
+}
+
 MagickBooleanType MagickReadImage(MagickWand *w, const char *path) {
 	FILE *f = fopen(path, "rb");
 	if (!f) { snprintf(w->err, sizeof w->err, "wandstub: cannot open %s", path); return MagickFalse; }
