@@ -1221,6 +1221,7 @@ int dsp_dct_set_output_segments(dsp_dct_plan p, int nseg, int seg_rows, void *co
 		if (l.pf_dist >= l.grid) l.pf_dist = 0;
 	}
 	const int gpr = c.tc / 4;
+	if (c.f.dense) { g_err = "segmented output: the last axis has a prime factor above 13 (dense transform), which has no segmented store"; return 1; }
 	if ((c.tc % 4) || (gpr & (gpr - 1)) || (l.block % gpr) || (c.ncols % c.tc) || !l.vec_in_layout || !l.vec_out_layout || c.f.dense || l.fused) {
 		g_err = "segmented output needs full, 16-byte aligned column tiles and no fused stage";
 		return 1;
