@@ -29,6 +29,7 @@ SYMBOLS = [
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
     "dsp_block_store_u8",
     "dsp_block_dct2d",
+    "dsp_motion_tiled_create", "dsp_motion_tiled_process_dev", "dsp_motion_tiled_destroy",
     "dsp_block_dct2d_debug",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
     "dsp_dct_fuse_pel_load", "dsp_dct_fuse_motion_coeff", "dsp_dct_fuse_pel_store", "dsp_dct_is_emulation",
@@ -102,6 +103,12 @@ def bind(path):
     lib.dsp_block_quant.argtypes = [ctypes.c_char, vp, ci, ci, ci, ci, ci, ci, cd, vp, vp]
     lib.dsp_block_store_u8.restype = ci
     lib.dsp_block_store_u8.argtypes = [ctypes.c_char, vp, vp, ctypes.c_longlong, cd, vp]
+    lib.dsp_motion_tiled_create.restype = vp
+    lib.dsp_motion_tiled_create.argtypes = [ci, ci, ci, ci, ci, ci, cd]
+    lib.dsp_motion_tiled_process_dev.restype = ci
+    lib.dsp_motion_tiled_process_dev.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_ulonglong), vp]
+    lib.dsp_motion_tiled_destroy.restype = None
+    lib.dsp_motion_tiled_destroy.argtypes = [vp]
     lib.dsp_block_dct2d.restype = ci
     lib.dsp_block_dct2d.argtypes = [ctypes.c_char, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, cd, vp]
     lib.dsp_block_dct2d_debug.restype = ci

@@ -10,6 +10,7 @@
 #include "dct_ring.cuh"
 #include "dct_colring.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -21,6 +22,8 @@
 #include <vector>
 #if !DSP_GPU
 #include <thread>
+#else
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges cost nothing unless a tool is attached
 #endif
 
 // The power-of-two fast path is built for float and double (the Makefile passes -DDSP_FAST_F64=1 and adds the
@@ -35,6 +38,9 @@ static thread_local std::string g_err;
 static std::mutex g_mu;
 static std::atomic<unsigned long long> g_launches(0);
 
+// DSP_DCT_NVTX=1 wraps every pass launch in an NVTX range ("dct pass <i> <row|col|split> n=<len>"), so that the passes
+// of a plan show up by name on an Nsight Systems / Nsight Compute timeline (tracing)
+static bool nvtx_on() { static int t = -1; if (t < 0) { const char *e = getenv("DSP_DCT_NVTX"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
 // DSP_DCT_TRACE=1 prints planner / launch steps to stderr
 static bool trace_on() { static int t = -1; if (t < 0) { const char *e = getenv("DSP_DCT_TRACE"); t = (e && *e && *e != '0') ? 1 : 0; } return t == 1; }
 #define DSP_TRACE(...) do { if (trace_on()) { fprintf(stderr, "[dsp_dct] " __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
@@ -807,7 +813,19 @@ static bool run_one(dsp_dct_plan_s *P, size_t i, void *d_in, void *d_out, rt_str
 		cudaEventRecord(e0, st);
 	}
 #endif
-	if (!run_pass(P, pp, in, out, st, c0, nc)) return false;
+#if DSP_GPU
+	const bool nv = nvtx_on();
+	if (nv) {
+		char name[96];
+		snprintf(name, sizeof name, "dct pass %zu %s n=%d", i, pp.row ? "row" : (pp.split ? "col-split" : "col"), pp.row ? pp.ra.f.n : pp.ca.f.n);
+		nvtxRangePushA(name);
+	}
+#endif
+	const bool launched = run_pass(P, pp, in, out, st, c0, nc);
+#if DSP_GPU
+	if (nv) nvtxRangePop();
+#endif
+	if (!launched) return false;
 #if DSP_GPU
 	if (prof) {
 		cudaEventRecord(e1, st);
@@ -1263,6 +1281,93 @@ int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, l
 	const bool ok = launch_block_store_u8(prec, d_coeffs, d_pels, n, scale, (rt_stream)stream, g_err);
 	if (ok) g_launches++;
 	return ok ? 0 : 1;
+}
+
+struct dsp_motion_tiled_s {
+	int D, H, W, bd, bh, bw;
+	double quant;
+	bool gemm;
+	std::vector<dsp_dct_plan> fwd, inv;      // per-axis plans in execution order
+	float *work;
+	unsigned long long *d_count;
+};
+
+void dsp_motion_tiled_destroy(dsp_motion_tiled t) {
+	if (!t) return;
+	for (dsp_dct_plan p : t->fwd) dsp_dct_destroy(p);
+	for (dsp_dct_plan p : t->inv) dsp_dct_destroy(p);
+	rt_free(t->work);
+	rt_free(t->d_count);
+	delete t;
+}
+
+dsp_motion_tiled dsp_motion_tiled_create(int D, int H, int W, int bd, int bh, int bw, double quant) {
+	g_err.clear();
+	if (D < 1 || H < 1 || W < 1 || bd < 1 || bh < 1 || bw < 1 || D % bd || H % bh || W % bw) {
+		g_err = "tiled motion: the volume must be a whole number of blocks (the reference pads the last block with zeros)";
+		return nullptr;
+	}
+	if (!rt_init(g_err)) return nullptr;
+	dsp_motion_tiled t = new dsp_motion_tiled_s();
+	t->D = D; t->H = H; t->W = W; t->bd = bd; t->bh = bh; t->bw = bw; t->quant = quant;
+	t->gemm = bh == bw && block_mm_supports(bw);
+	t->work = nullptr; t->d_count = nullptr;
+	const long long hw = (long long)H * W;
+	bool ok = true;
+	for (int dir = 0; dir < 2 && ok; dir++) {
+		const int kind = dir == 0 ? DSP_DCT_REDFT10 : DSP_DCT_REDFT01;
+		std::vector<dsp_dct_plan> &v = dir == 0 ? t->fwd : t->inv;
+		if (!t->gemm) {
+			// w: contiguous segments of bw; h: bh rows at stride W, W adjacent columns, one batch element per band of bh rows
+			v.push_back(dsp_dct_plan_many_batched('f', 1, &bw, (int)((W / bw) * (long long)H * D), nullptr, nullptr, 1, bw, nullptr, nullptr, 1, bw, &kind, 0, 1, 0, 0));
+			v.push_back(dsp_dct_plan_many_batched('f', 1, &bh, W, nullptr, nullptr, W, 1, nullptr, nullptr, W, 1, &kind, 0, (H / bh) * D, (ptrdiff_t)bh * W, (ptrdiff_t)bh * W));
+		}
+		if (bd > 1 || !t->gemm)    // d: bd frames at stride H W, H W adjacent columns, one batch element per slab of bd frames
+			v.push_back(dsp_dct_plan_many_batched('f', 1, &bd, (int)hw, nullptr, nullptr, (int)hw, 1, nullptr, nullptr, (int)hw, 1, &kind, 0, D / bd, (ptrdiff_t)bd * hw, (ptrdiff_t)bd * hw));
+		for (dsp_dct_plan p : v) ok = ok && p != nullptr;
+	}
+	if (ok) std::reverse(t->inv.begin(), t->inv.end());
+	const std::string keep = g_err;
+	if (ok) {
+		ok = rt_malloc((void **)&t->work, (size_t)D * hw * sizeof(float), g_err) && rt_malloc((void **)&t->d_count, sizeof(unsigned long long), g_err);
+	}
+	if (!ok) {
+		const std::string why = keep.empty() ? g_err : keep;
+		dsp_motion_tiled_destroy(t);
+		g_err = why.empty() ? "tiled motion: setup failed" : why;
+		return nullptr;
+	}
+	return t;
+}
+
+int dsp_motion_tiled_process_dev(dsp_motion_tiled t, const unsigned char *d_in, unsigned char *d_out, unsigned long long *coeffs_coded, void *stream) {
+	g_err.clear();
+	if (!t || !d_in || !d_out) { g_err = "tiled motion: null argument"; return 1; }
+	rt_stream st = (rt_stream)stream;
+	const long long n = (long long)t->D * t->H * t->W;
+	const double vol = (double)t->bd * t->bh * t->bw;
+	if (!launch_block_load_u8('f', d_in, t->work, n, st, g_err)) return 1;                      // motion.c:618-624
+	g_launches++;
+	if (t->gemm) {
+		// depth-1 blocks have no d plan: FFTW's REDFT10 of length 1 doubles its sample
+		if (dsp_block_dct2d('f', t->work, t->work, t->D, t->H, t->W, t->bw, DSP_DCT_REDFT10, t->bd == 1 ? 2.0 : 1.0, stream)) return 1;
+	}
+	for (dsp_dct_plan p : t->fwd)
+		if (dsp_dct_execute_dev(p, t->work, t->work, stream)) return 1;                              // :641 for every block
+	const double q = t->quant != 0.0 ? (double)(float)(t->quant * 8.0 * std::sqrt(vol)) : 0.0;    // :570
+	if (coeffs_coded && !rt_zero(t->d_count, sizeof(unsigned long long), st, g_err)) return 1;
+	if (dsp_block_quant('f', t->work, t->D, t->H, t->W, t->bd, t->bh, t->bw, q, coeffs_coded ? t->d_count : nullptr, stream)) return 1;   // :644-647, :740-751
+	for (dsp_dct_plan p : t->inv)
+		if (dsp_dct_execute_dev(p, t->work, t->work, stream)) return 1;                              // :753
+	if (t->gemm && dsp_block_dct2d('f', t->work, t->work, t->D, t->H, t->W, t->bw, DSP_DCT_REDFT01, 1.0, stream)) return 1;
+	const double norm = 1.0 / std::sqrt(vol * 8.0);
+	if (dsp_block_store_u8('f', t->work, d_out, n, norm * norm, stream)) return 1;               // :757-776 (sf = 1)
+	if (coeffs_coded) {
+		unsigned long long c = 0;
+		if (!rt_d2h(&c, t->d_count, sizeof c, st, g_err) || !rt_sync(st, g_err)) return 1;
+		if (t->quant != 0.0) *coeffs_coded += c;
+	}
+	return 0;
 }
 
 int dsp_block_dct2d_debug(const void *d_in, void *d_out, long long nplanes, int H, int W, int B, int kind, double scale, void *stream, float *d_debug) {

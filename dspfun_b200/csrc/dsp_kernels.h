@@ -46,6 +46,7 @@ bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *
 bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,
                         unsigned long long *count, rt_stream st, std::string &err);
 bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err);
+bool launch_block_load_u8(char prec, const unsigned char *pels, void *coeffs, long long n, rt_stream st, std::string &err);
 
 // 2-D block DCT of whole planes as tensor-core GEMMs (kern_block_mm.cu): tcgen05 / TMEM, 3 x TF32 split for float accuracy
 bool block_mm_supports(int B);

@@ -126,6 +126,28 @@ bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int 
 #endif
 }
 
+// 8-bit pels -> coefficients-to-be (motion.c:618-624 for 8-bit input: the value itself)
+#if DSP_GPU
+template <class T> __global__ void k_block_load_u8(const unsigned char *pels, T *c, long long n) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c[i] = (T)pels[i];
+}
+#endif
+bool launch_block_load_u8(char prec, const unsigned char *pels, void *coeffs, long long n, rt_stream st, std::string &err) {
+#if DSP_GPU
+	const int grid = 148 * 16;
+	if (prec == 'f') k_block_load_u8<float><<<grid, 256, 0, st>>>(pels, (float *)coeffs, n);
+	else k_block_load_u8<double><<<grid, 256, 0, st>>>(pels, (double *)coeffs, n);
+	return rt_ok(cudaGetLastError(), err, "block load launch");
+#else
+	(void)st; (void)err;
+	for (long long i = 0; i < n; i++) {
+		if (prec == 'f') ((float *)coeffs)[i] = (float)pels[i];
+		else ((double *)coeffs)[i] = (double)pels[i];
+	}
+	return true;
+#endif
+}
+
 bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err) {
 #if DSP_GPU
 	const int grid = 148 * 16;

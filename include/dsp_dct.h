@@ -233,6 +233,19 @@ int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int 
                     unsigned long long *d_count, void *stream);
 int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream);
 
+/* ---- the same block-tiled volume as ONE session behind the C ABI (what dspfun_b200/motion.py: MotionTiled does from
+ * Python): `motion -b BWxBHxBD [--quant q]` with block == scaled over a [D][H][W] plane of 8-bit pels in device memory
+ * (D, H, W whole numbers of blocks).  create builds the plans (square spatial blocks of 8 / 16 / 32 / 64 take
+ * dsp_block_dct2d for both spatial axes and keep a plan only for the d axis; other shapes use three per-axis plans) and a
+ * float work volume; process_dev enqueues pels -> block DCT-II -> normalise / quantise / de-normalise -> block DCT-III ->
+ * clamp, round, 8-bit pels on `stream` (d_pels_out may equal d_pels_in).  If coeffs_coded is not NULL the call
+ * synchronises the stream and adds the number of non-zero quantised coefficients (motion.c:740-744). */
+typedef struct dsp_motion_tiled_s *dsp_motion_tiled;
+dsp_motion_tiled dsp_motion_tiled_create(int D, int H, int W, int bd, int bh, int bw, double quant);
+int dsp_motion_tiled_process_dev(dsp_motion_tiled t, const unsigned char *d_pels_in, unsigned char *d_pels_out,
+                                 unsigned long long *coeffs_coded, void *stream);
+void dsp_motion_tiled_destroy(dsp_motion_tiled t);
+
 /* ---- 2-D block DCT on the tensor cores: every B x B block (B = 8, 16, 32 or 64) of `nplanes` float planes [H][W]
  * (device memory, W contiguous, H and W whole numbers of blocks, d_in 16-byte aligned; d_out may equal d_in) is
  * replaced by its unnormalised FFTW transform along both axes, times `scale`: kind = DSP_DCT_REDFT10 or

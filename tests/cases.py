@@ -330,6 +330,30 @@ def check_block_dct2d(lib, shape, B, kind, tol, device="cpu", seed=17, in_place=
     return err
 
 
+def check_motion_tiled_c_session(lib, dims, block, quant, device="cpu", seed=12):
+    """dsp_motion_tiled_* (the C-ABI session) == MotionTiled (the Python orchestration of the same calls), pels and counts"""
+    import ctypes
+    import torch
+    from dspfun_b200.motion import MotionTiled
+    v = torch.from_numpy(np.random.default_rng(seed).integers(16, 236, dims).astype(np.uint8)).to(device)
+    t = lib.dsp_motion_tiled_create(*dims, *block, float(quant))
+    assert t, capi_last_error(lib)
+    out = torch.empty_like(v)
+    cnt = ctypes.c_ulonglong(0)
+    stream = torch.cuda.current_stream().cuda_stream if device != "cpu" else None
+    assert lib.dsp_motion_tiled_process_dev(t, v.data_ptr(), out.data_ptr(), ctypes.byref(cnt), stream) == 0, capi_last_error(lib)
+    again = v.clone()                                             # in place, no count requested
+    assert lib.dsp_motion_tiled_process_dev(t, again.data_ptr(), again.data_ptr(), None, stream) == 0
+    if device != "cpu":
+        torch.cuda.synchronize()
+    lib.dsp_motion_tiled_destroy(t)
+    mt = MotionTiled(dims, block, quant=quant, lib=lib)
+    want = mt.process(v.clone())
+    assert torch.equal(out, want) and torch.equal(again, want)
+    assert cnt.value == mt.coeffs_coded
+    mt.destroy()
+
+
 def capi_last_error(lib):
     from dspfun_b200 import capi
     return capi.last_error(lib)

@@ -195,3 +195,11 @@ def test_motion_tiled_gemm_and_plan_paths_agree(lib):
     cases.check_motion_tiled(lib, (16, 16, 24), (8, 8, 8), quant=0.05, gemm=False)
     cases.check_motion_tiled(lib, (2, 32, 64), (1, 16, 16), quant=0.02)
     cases.check_motion_tiled(lib, (2, 32, 64), (2, 32, 32))
+
+
+def test_motion_tiled_c_session(lib):
+    """dsp_motion_tiled_create / process_dev / destroy: the block-tiled pipeline behind the C ABI (missing 5)"""
+    cases.check_motion_tiled_c_session(lib, (16, 16, 24), (8, 8, 8), 0.05)          # GEMM spatial axes + d plan
+    cases.check_motion_tiled_c_session(lib, (8, 32, 16), (4, 16, 8), 0.02)          # three per-axis plans
+    cases.check_motion_tiled_c_session(lib, (2, 24, 40), (1, 8, 8), 0.0)            # depth-1 blocks, no quantiser
+    assert not lib.dsp_motion_tiled_create(16, 16, 24, 8, 8, 7, 0.0) and capi.last_error(lib)

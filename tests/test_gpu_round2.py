@@ -253,3 +253,9 @@ def test_motion_tiled_on_the_gemm_path(lib):
     cases.check_motion_tiled(lib, (16, 64, 96), (8, 8, 8), device="cuda", gemm=False)
     cases.check_motion_tiled(lib, (4, 128, 256), (2, 32, 32), quant=0.02, device="cuda")
     cases.check_motion_tiled(lib, (2, 128, 128), (1, 64, 64), device="cuda")
+
+
+def test_motion_tiled_c_session_on_gpu(lib):
+    cases.check_motion_tiled_c_session(lib, (16, 128, 256), (8, 8, 8), 0.05, device="cuda")
+    cases.check_motion_tiled_c_session(lib, (8, 64, 96), (4, 16, 8), 0.02, device="cuda")
+    cases.check_motion_tiled_c_session(lib, (4, 128, 128), (1, 64, 64), 0.0, device="cuda")
