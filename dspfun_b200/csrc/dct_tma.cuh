@@ -87,6 +87,11 @@ inline bool tma_encode(TmaDesc *d, const TmaView &v, std::string &err, bool swiz
 	return true;
 }
 // box at coordinates (c0, c1, c2[, c3]) -> shared memory (128-byte aligned); completes on `bar` with the box's full byte count
+DSP_DEV void tma_load2(void *dst, const TmaDesc *map, int c0, int c1, uint64_t *bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+	             "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+	             : "memory");
+}
 DSP_DEV void tma_load3(void *dst, const TmaDesc *map, int c0, int c1, int c2, uint64_t *bar) {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
 	             "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))

@@ -1759,8 +1759,8 @@ struct dsp_zoom_s {
 	int h, w;
 	size_t es;
 	void *d_coeffs;                        // [h][w][3] REDFT10 x REDFT10 of the pixels
-	void *d_xb, *d_yb, *d_tmp, *d_out, *d_pad;
-	size_t xb_bytes, yb_bytes, tmp_bytes, out_bytes, pad_bytes;
+	void *d_xb, *d_yb, *d_tmp, *d_out, *d_pad, *d_cpl;
+	size_t xb_bytes, yb_bytes, tmp_bytes, out_bytes, pad_bytes, cpl_bytes;
 	int last_path;
 };
 
@@ -1775,7 +1775,7 @@ static bool zoom_reserve(void **p, size_t *have, size_t need) {
 
 static void zoom_free(dsp_zoom_s *z) {
 	if (!z) return;
-	rt_free(z->d_coeffs); rt_free(z->d_xb); rt_free(z->d_yb); rt_free(z->d_tmp); rt_free(z->d_out); rt_free(z->d_pad);
+	rt_free(z->d_coeffs); rt_free(z->d_xb); rt_free(z->d_yb); rt_free(z->d_tmp); rt_free(z->d_out); rt_free(z->d_pad); rt_free(z->d_cpl);
 	delete z;
 }
 
@@ -1873,6 +1873,31 @@ int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out) {
 		g_launches += 2;
 		z->last_path = 2;
 		return ok ? 0 : 1;
+	}
+
+	// ---- general path on the tensor cores (float): the two contractions per channel as 3 x TF32 GEMMs (kern_gemm_tc.cu):
+	//   tmpT[i][row] = sum_u xb[i][u] C[row][u][c]          (zoom.c:363-367, transposed so that it is K-major for the next product)
+	//   out[j][i][c] = sum_v yb[j][v] tmpT[i][v] / (W H)     (zoom.c:368-374)
+	if (z->prec == 'f' && gemm_tc_available()) {
+		const int cwp = (cw + 3) & ~3, chp = (ch + 3) & ~3;                  // leading dimensions: multiples of 16 bytes for the TMA
+		const size_t nxb = (size_t)vw * cwp, nyb = (size_t)vh * chp, ntm = (size_t)vw * chp, ncp = (size_t)ch * cwp;
+		if (!zoom_reserve(&z->d_xb, &z->xb_bytes, 2 * nxb * 4) || !zoom_reserve(&z->d_yb, &z->yb_bytes, 2 * nyb * 4) ||
+		    !zoom_reserve(&z->d_tmp, &z->tmp_bytes, 2 * ntm * 4) || !zoom_reserve(&z->d_cpl, &z->cpl_bytes, 2 * ncp * 4))
+			return 1;
+		float *xb = (float *)z->d_xb, *yb = (float *)z->d_yb, *tm = (float *)z->d_tmp, *cp = (float *)z->d_cpl;
+		if (!launch_zoom_basis('f', xb, vw, cwp, zp->basis, xn, xd, zp->vx, W, 0, g_err) || !launch_tf32_residual(xb, xb + nxb, (long long)nxb, 0, g_err) ||
+		    !launch_zoom_basis('f', yb, vh, chp, zp->basis, yn, yd, zp->vy, H, 0, g_err) || !launch_tf32_residual(yb, yb + nyb, (long long)nyb, 0, g_err))
+			return 1;
+		g_launches += 4;
+		for (int c = 0; c < 3; c++) {
+			if (!launch_planarize3((const float *)z->d_coeffs, ch, W, cw, c, cp, cp + ncp, cwp, 0, g_err) ||
+			    !launch_gemm_tf32x3(vw, ch, cw, xb, xb + nxb, cwp, cp, cp + ncp, cwp, tm, tm + ntm, chp, 1, 1.0, 0, g_err) ||
+			    !launch_gemm_tf32x3(vh, vw, ch, yb, yb + nyb, chp, tm, tm + ntm, chp, (float *)z->d_out + c, nullptr, (long long)vw * 3, 3, inv_wh, 0, g_err))
+				return 1;
+			g_launches += 3;
+		}
+		z->last_path = 3;
+		return (rt_d2h(out, z->d_out, (size_t)vh * vw * 3 * es, 0, g_err) && rt_sync(0, g_err)) ? 0 : 1;
 	}
 
 	// ---- general path: scaled bases (zoom.c:347-358) and the separable synthesis (zoom.c:361-375)

@@ -53,6 +53,13 @@ bool block_mm_supports(int B);
 bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, int W, int B, int kind, double scale, rt_stream st,
                          std::string &err, float *dbg);
 
+// dense float GEMM on the tensor cores, 3 x TF32 (kern_gemm_tc.cu): zoom's general synthesis path
+bool gemm_tc_available();
+bool launch_tf32_residual(const float *x, float *lo, long long n, rt_stream st, std::string &err);
+bool launch_planarize3(const float *src, int rows, int src_cols, int cols, int ch, float *dst, float *dst_lo, int ld, rt_stream st, std::string &err);
+bool launch_gemm_tf32x3(int M, int N, int K, const float *A, const float *A_lo, long long lda, const float *B, const float *B_lo, long long ldb,
+                        float *D, float *D_lo, long long dr, long long dc, double alpha, rt_stream st, std::string &err);
+
 // pointwise spectrogram stages of motion (kern_misc.cu)
 struct MotionSpecArgs {
 	int md, mh, mw;              // padded box (minbuf)

@@ -22,24 +22,42 @@ class Zoom:
         if not self._h:
             raise capi.DspDctError(capi.last_error(self.lib))
 
-    def frame(self, scale=1.0, basis="interpolated", pos=(0.0, 0.0), view=(0, 0), xscale=None, yscale=None):
-        """One output view [vh][vw][3].  scale / xscale / yscale: a number or a (num, den) pair (zoom -s / -x / -y)."""
+    def frame(self, scale=1.0, basis="interpolated", pos=(0.0, 0.0), view=(0, 0), xscale=None, yscale=None, pinned=False):
+        """One output view [vh][vw][3].  scale / xscale / yscale: a number or a (num, den) pair (zoom -s / -x / -y).
+        pinned=True returns a view of a page-locked buffer owned by this object (dsp_dct_alloc, what the tool's
+        fftw_alloc_real gives it through the shim): valid until the next pinned frame or destroy(), and copied out of the
+        GPU at PCIe speed instead of through pageable memory."""
         def frac(v):
             return (float(v[0]), float(v[1])) if isinstance(v, (tuple, list)) else (float(v), 1.0)
         xs, ys = frac(xscale if xscale is not None else scale), frac(yscale if yscale is not None else scale)
         zp = capi.ZoomParams(BASIS[basis], xs[0], xs[1], ys[0], ys[1], float(pos[0]), float(pos[1]), int(view[0]), int(view[1]))
         vw, vh = ctypes.c_int(0), ctypes.c_int(0)
         self.lib.dsp_zoom_view_size(self._h, ctypes.byref(zp), ctypes.byref(vw), ctypes.byref(vh))
-        out = np.empty((vh.value, vw.value, 3), self.dtype)
+        if pinned:
+            nbytes = vh.value * vw.value * 3 * np.dtype(self.dtype).itemsize
+            if getattr(self, "_pin_bytes", 0) < nbytes:
+                if getattr(self, "_pin", None):
+                    self.lib.dsp_dct_free(self._pin)
+                self._pin = self.lib.dsp_dct_alloc(nbytes)
+                if not self._pin:
+                    raise capi.DspDctError(capi.last_error(self.lib))
+                self._pin_bytes = nbytes
+            buf = (ctypes.c_char * nbytes).from_address(self._pin)
+            out = np.frombuffer(buf, dtype=self.dtype).reshape(vh.value, vw.value, 3)
+        else:
+            out = np.empty((vh.value, vw.value, 3), self.dtype)
         if self.lib.dsp_zoom_frame(self._h, ctypes.byref(zp), out.ctypes.data) != 0:
             raise capi.DspDctError(capi.last_error(self.lib))
-        self.last_path = {1: "inverse-dct", 2: "shifted-dct"}.get(self.lib.dsp_zoom_last_path(self._h), "dense")
+        self.last_path = {1: "inverse-dct", 2: "shifted-dct", 3: "dense-tensor-core"}.get(self.lib.dsp_zoom_last_path(self._h), "dense")
         return out
 
     def destroy(self):
         if getattr(self, "_h", None):
             self.lib.dsp_zoom_destroy(self._h)
             self._h = None
+        if getattr(self, "_pin", None):
+            self.lib.dsp_dct_free(self._pin)
+            self._pin, self._pin_bytes = None, 0
 
     def __del__(self):
         try:

@@ -279,7 +279,8 @@ dsp_zoom dsp_zoom_create(char prec, int h, int w, const void *pixels);
 int dsp_zoom_view_size(dsp_zoom z, const dsp_zoom_params *zp, int *vw, int *vh);
 int dsp_zoom_frame(dsp_zoom z, const dsp_zoom_params *zp, void *out);
 /* which path the last frame took: 1 = inverse-DCT fast path (native basis), 2 = four phase-shifted inverse DCTs
- * (interpolated basis with an integer scaled size, any offset), 0 = dense synthesis */
+ * (interpolated basis with an integer scaled size, any offset), 0 = dense synthesis (SIMT GEMM, FP64 accumulation),
+ * 3 = dense synthesis on the tensor cores (float sessions: two 3 x TF32 GEMMs per channel) */
 int dsp_zoom_last_path(dsp_zoom z);
 void dsp_zoom_destroy(dsp_zoom z);
 

@@ -259,3 +259,17 @@ def test_motion_tiled_c_session_on_gpu(lib):
     cases.check_motion_tiled_c_session(lib, (16, 128, 256), (8, 8, 8), 0.05, device="cuda")
     cases.check_motion_tiled_c_session(lib, (8, 64, 96), (4, 16, 8), 0.02, device="cuda")
     cases.check_motion_tiled_c_session(lib, (4, 128, 128), (1, 64, 64), 0.0, device="cuda")
+
+
+# ---------------------------------------------------------------------------------------------- zoom's dense path on the tensor cores
+@pytest.mark.parametrize("kw", [dict(scale=(3, 2)), dict(scale=(5, 3), basis="centered"), dict(scale=(7, 4), pos=(10.5, 3.25), view=(200, 150)),
+                                dict(xscale=(2, 1), yscale=(3, 2), basis="centered"), dict(scale=(2, 3))])
+def test_zoom_dense_path_tensor_core_gemm(lib, kw):
+    """k tails (cw, ch not multiples of 32), M / N tails (views not multiples of 128), several k blocks and tiles; against the
+    restated synthesis and against the SIMT GEMM of round 1 (DSP_ZOOM_NO_TC is read once per process, so that comparison
+    runs in the fullsize test below through a subprocess-free route: the double-precision session)"""
+    path, got, want = cases.check_zoom(lib, "f", 301, 421, **kw)
+    assert path == "dense-tensor-core"
+    path_d, got_d, _ = cases.check_zoom(lib, "d", 301, 421, **kw)
+    assert path_d == "dense"
+    assert od.rel_l2(got, got_d) < 1e-5                      # float bases and float coefficients against the double session
