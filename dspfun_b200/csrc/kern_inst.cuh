@@ -4,6 +4,14 @@
 #include <vector>
 #include <cstdlib>
 
+#ifndef KERN_GENERIC_MINB
+// generic (mixed-radix) float kernels are issue-latency bound (ncu r02: ~50 % issue utilisation at 16 warps per SM, top stall
+// "wait"), so the row kernels are built for 4 CTAs of 256 threads per SM (64 registers, ~100-300 B of spills): 1920-point
+// rows of the 256x1080x1920 volume 3.25 -> 2.37 ms forward, 3.67 -> 2.58 ms inverse (3 CTAs: 2.63 / 2.92, 5: 2.34 / 2.54).
+// Column kernels stay at 2: their 16-column tiles take 74 KB of shared memory, and neither a register cap (2.21 -> 2.40 ms
+// at n = 1080) nor 8-column tiles with 4 CTAs (2.39 ms) paid.
+#define KERN_GENERIC_MINB (KERN_ROW ? 4 : 2)
+#endif
 #ifndef KERN_ROW_MINB
 #define KERN_ROW_MINB 2
 #endif
@@ -67,7 +75,7 @@ DSP_DEV void cta_body(const KERN_ARGS &a, const FastDesc &f, const L &l, const S
 #if DSP_GPU
 // f32: two CTAs per SM (<= 128 registers); f64: one (the paired outer pass keeps 64 complex doubles live)
 template <class TT, int ROW, int FAST, class L, class S>
-__global__ void __launch_bounds__((KERN_FAST && !KERN_ROW) ? 2 * kThreads : kThreads, sizeof(KERN_T) != 4 ? 1 : (KERN_FAST ? (KERN_ROW ? KERN_ROW_MINB : 1) : 2))
+__global__ void __launch_bounds__((KERN_FAST && !KERN_ROW) ? 2 * kThreads : kThreads, sizeof(KERN_T) != 4 ? 1 : (KERN_FAST ? (KERN_ROW ? KERN_ROW_MINB : 1) : KERN_GENERIC_MINB))
 k_pass(const __grid_constant__ KERN_ARGS a, const __grid_constant__ FastDesc f, const __grid_constant__ L l,
        const __grid_constant__ S s) {
 	extern __shared__ __align__(16) unsigned char smem[];
