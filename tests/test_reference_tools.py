@@ -18,6 +18,9 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 
 def _tool(name):
     path = os.path.join(REF, name)
+    if not os.path.exists(path) and "_emu_" in name:
+        from tests.emu import emu
+        emu.load()                                  # the *_emu_* tools link tests/emu/libdspdct_emu.so: make sure it is there first
     if not os.path.exists(path):
         if os.path.exists("/root/reference/spec/spec.c"):
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "reftools"], check=True)
