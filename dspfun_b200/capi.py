@@ -28,7 +28,7 @@ SYMBOLS = [
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
     "dsp_block_store_u8",
-    "dsp_block_dct2d",
+    "dsp_block_dct2d", "dsp_dct_plan_with_ngpus", "dsp_dct_plan_ngpus",
     "dsp_motion_tiled_create", "dsp_motion_tiled_process_dev", "dsp_motion_tiled_destroy",
     "dsp_block_dct2d_debug",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
@@ -90,6 +90,10 @@ def bind(path):
     lib.dsp_dct_execute_dev.argtypes = [vp, vp, vp, vp]
     lib.dsp_dct_destroy.restype = None
     lib.dsp_dct_destroy.argtypes = [vp]
+    lib.dsp_dct_plan_with_ngpus.restype = None
+    lib.dsp_dct_plan_with_ngpus.argtypes = [ci]
+    lib.dsp_dct_plan_ngpus.restype = ci
+    lib.dsp_dct_plan_ngpus.argtypes = [vp]
     lib.dsp_dct_alloc.restype = vp
     lib.dsp_dct_alloc.argtypes = [ctypes.c_size_t]
     lib.dsp_dct_free.restype = None

@@ -274,6 +274,8 @@ struct PassPlan {
 	long long seg_os[4], seg_ax_os;
 };
 
+struct MultiGpu;
+
 }  // namespace dsp
 
 using namespace dsp;
@@ -327,6 +329,8 @@ struct dsp_dct_plan_s {
 #endif
 	std::vector<int> ev_pass;
 	std::vector<float> ev_frac;              // share of the pass each recorded launch covered (chunked schedule)
+	dsp::MultiGpu *mg;                       // rank-3 host-buffer plans over several GPUs of this process (dsp_dct_plan_with_ngpus)
+	bool mg_tried;
 };
 
 namespace dsp {
@@ -924,6 +928,7 @@ static dsp_dct_plan make_plan(char prec, int rank, const int *n, int howmany, vo
 	P->c_has_ie = inembed != nullptr; P->c_has_oe = onembed != nullptr;
 	for (int i = 0; i < 3; i++) { P->c_ie[i] = (inembed && i < rank) ? inembed[i] : 0; P->c_oe[i] = (onembed && i < rank) ? onembed[i] : 0; }
 	P->kids_failed = false;
+	P->mg = nullptr; P->mg_tried = false;
 	if (!build_plan(P, howmany, inembed, istride, idist, onembed, ostride, odist, nbatch, ibdist, obdist)) {
 		delete P;
 		return nullptr;
@@ -1026,7 +1031,163 @@ static bool chunkable(const dsp_dct_plan_s *P) {
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------ several GPUs, one process
+// fftw_plan_with_nthreads(n) (motion/motion.c:485-486, scan/scan.c:289-290) maps to dsp_dct_plan_with_ngpus(n): a rank-3
+// float plan over one contiguous [D][H][W] volume in HOST memory (motion -b 0x0x0: the whole clip is one block) is then
+// executed on G = min(n, visible GPUs) devices of this process, SURVEY 8e's slab decomposition behind the C ABI:
+//   forward  host slab g (frames [g D/G, (g+1) D/G)) -> GPU g -> REDFT10 over (h, w) per frame, its last pass storing rows
+//            [r H/G, (r+1) H/G) straight into GPU r's column buffer over NVLink (dsp_dct_set_output_segments: the exchange is
+//            fused into the transform) -> REDFT10 over d on every GPU's [D][H W / G] columns -> strided copy-out to the host
+//   inverse  the mirror image: column slices in, REDFT01 over d storing frames [r D/G, ..) into GPU r's slab, REDFT01 over
+//            (h, w), slabs out.
+// One exchange per transform (the host layout absorbs the other one).  Anything not eligible (double, embedded sub-boxes,
+// fused stages, sizes that do not divide, no peer access) stays on one GPU.
+static std::atomic<int> g_ngpus(1);
+
+struct MultiGpu {
+	int G, D, H, W, Dl;
+	long long Pl;
+	bool fwd;
+	std::vector<dsp_dct_plan> p2, pt;        // per device: frames plan, temporal plan
+	std::vector<float *> slab, cols;         // per device: [Dl][H][W], [D][Pl]
+};
+
+#if DSP_GPU
+static void mg_free(MultiGpu *m) {
+	if (!m) return;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	for (int g = 0; g < m->G; g++) {
+		cudaSetDevice(g);
+		if (g < (int)m->p2.size() && m->p2[g]) dsp_dct_destroy(m->p2[g]);
+		if (g < (int)m->pt.size() && m->pt[g]) dsp_dct_destroy(m->pt[g]);
+		if (g < (int)m->slab.size()) rt_free(m->slab[g]);
+		if (g < (int)m->cols.size()) rt_free(m->cols[g]);
+	}
+	cudaSetDevice(cur);
+	delete m;
+}
+
+static bool mg_eligible(const dsp_dct_plan_s *P, int &G) {
+	G = g_ngpus.load();
+	if (G < 2 || P->prec != 'f' || P->rank != 3 || P->d != 1 || P->c_howmany != 1 || P->c_nbatch != 1 || P->fuse_kind != 0) return false;
+	if (P->c_istride != 1 || P->c_ostride != 1 || P->out_has_gaps) return false;
+	for (int i = 0; i < 3; i++) {
+		if (P->kind[i] != P->kind[0]) return false;
+		if (P->c_has_ie && P->c_ie[i] != P->n[i]) return false;
+		if (P->c_has_oe && P->c_oe[i] != P->n[i]) return false;
+	}
+	if (P->passes.front().lop.kind != 0 || P->passes.back().sop.kind != 0) return false;      // plain scales stay on one GPU
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess) return false;
+	if (G > ndev) G = ndev;
+	while (G > 1 && (P->n[0] % G || P->n[1] % G)) G--;
+	if (G < 2) return false;
+	for (int a = 0; a < G; a++)
+		for (int b = 0; b < G; b++) {
+			int can = 0;
+			if (a != b && (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can)) return false;
+		}
+	return true;
+}
+
+static MultiGpu *mg_create(const dsp_dct_plan_s *P, int G) {
+	MultiGpu *m = new MultiGpu();
+	m->G = G; m->D = P->n[0]; m->H = P->n[1]; m->W = P->n[2]; m->Dl = m->D / G;
+	m->Pl = (long long)m->H * m->W / G;
+	m->fwd = P->kind[0] == DSP_DCT_REDFT10;
+	m->p2.assign(G, nullptr); m->pt.assign(G, nullptr); m->slab.assign(G, nullptr); m->cols.assign(G, nullptr);
+	const int hw[2] = {m->H, m->W}, kk[2] = {P->kind[0], P->kind[0]}, nd = m->D;
+	const long long fhw = (long long)m->H * m->W;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	bool ok = true;
+	for (int g = 0; g < G && ok; g++) {
+		cudaSetDevice(g);
+		for (int r = 0; r < G; r++)
+			if (r != g) {
+				const cudaError_t e = cudaDeviceEnablePeerAccess(r, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+				(void)cudaGetLastError();
+			}
+		ok = ok && rt_malloc((void **)&m->slab[g], (size_t)m->Dl * fhw * 4, g_err) && rt_malloc((void **)&m->cols[g], (size_t)m->D * m->Pl * 4, g_err);
+		if (!ok) break;
+		m->p2[g] = dsp_dct_plan_many_batched('f', 2, hw, 1, nullptr, nullptr, 1, 0, nullptr, nullptr, 1, 0, kk, 0, m->Dl, (ptrdiff_t)fhw, (ptrdiff_t)fhw);
+		m->pt[g] = dsp_dct_plan_many_batched('f', 1, &nd, (int)m->Pl, nullptr, nullptr, (int)m->Pl, 1, nullptr, nullptr, (int)m->Pl, 1, kk, 0, 1, 0, 0);
+		ok = m->p2[g] && m->pt[g];
+	}
+	// the pass in front of the exchange stores into every device's receive buffer
+	for (int g = 0; g < G && ok; g++) {
+		cudaSetDevice(g);
+		void *bases[8];
+		if (m->fwd) {
+			for (int r = 0; r < G; r++) bases[r] = m->cols[r] + (size_t)g * m->Dl * m->Pl;       // frame dl of GPU g -> cols[r][g Dl + dl][..]
+			ok = dsp_dct_set_output_segments(m->p2[g], G, m->H / G, bases, m->Pl, 0) == 0;
+		} else {
+			for (int r = 0; r < G; r++) bases[r] = m->slab[r] + (size_t)g * m->Pl;             // frame d of GPU r's slab, columns [g Pl, ..)
+			ok = dsp_dct_set_output_segments(m->pt[g], G, m->Dl, bases, 0, fhw) == 0;
+		}
+	}
+	cudaSetDevice(cur);
+	if (!ok) { const std::string why = g_err; mg_free(m); g_err = why; return nullptr; }
+	return m;
+}
+
+// host [D][H][W] in -> out (may be the same buffer); every device's work is enqueued from this thread and runs concurrently
+static bool mg_execute(MultiGpu *m, const float *in, float *out) {
+	const int G = m->G;
+	const long long fhw = (long long)m->H * m->W;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	bool ok = true;
+	auto sync_all = [&]() { for (int g = 0; g < G; g++) { cudaSetDevice(g); ok = rt_ok(cudaDeviceSynchronize(), g_err, "multi-GPU synchronize") && ok; } };
+	if (m->fwd) {
+		for (int g = 0; g < G && ok; g++) {
+			cudaSetDevice(g);
+			ok = rt_h2d(m->slab[g], in + (size_t)g * m->Dl * fhw, (size_t)m->Dl * fhw * 4, 0, g_err) &&
+			     dsp_dct_execute_dev(m->p2[g], m->slab[g], m->slab[g], nullptr) == 0;          // (its last pass stores into the peers' cols)
+		}
+		sync_all();                                                                          // the exchange is complete on every device
+		for (int g = 0; g < G && ok; g++) {
+			cudaSetDevice(g);
+			ok = dsp_dct_execute_dev(m->pt[g], m->cols[g], m->cols[g], nullptr) == 0 &&
+			     rt_ok(cudaMemcpy2DAsync(out + (size_t)g * m->Pl, (size_t)fhw * 4, m->cols[g], (size_t)m->Pl * 4, (size_t)m->Pl * 4, (size_t)m->D,
+			                             cudaMemcpyDeviceToHost, 0), g_err, "multi-GPU copy-out");
+		}
+		sync_all();
+	} else {
+		for (int g = 0; g < G && ok; g++) {
+			cudaSetDevice(g);
+			ok = rt_ok(cudaMemcpy2DAsync(m->cols[g], (size_t)m->Pl * 4, in + (size_t)g * m->Pl, (size_t)fhw * 4, (size_t)m->Pl * 4, (size_t)m->D,
+			                             cudaMemcpyHostToDevice, 0), g_err, "multi-GPU copy-in") &&
+			     dsp_dct_execute_dev(m->pt[g], m->cols[g], m->cols[g], nullptr) == 0;          // (stores into the peers' slabs)
+		}
+		sync_all();
+		for (int g = 0; g < G && ok; g++) {
+			cudaSetDevice(g);
+			ok = dsp_dct_execute_dev(m->p2[g], m->slab[g], m->slab[g], nullptr) == 0 &&
+			     rt_d2h(out + (size_t)g * m->Dl * fhw, m->slab[g], (size_t)m->Dl * fhw * 4, 0, g_err);
+		}
+		sync_all();
+	}
+	cudaSetDevice(cur);
+	return ok;
+}
+#endif
+
 static bool execute_host(dsp_dct_plan_s *P, void *in, void *out) {
+#if DSP_GPU
+	if (!P->mg_tried) {
+		P->mg_tried = true;
+		int G = 1;
+		if (mg_eligible(P, G)) {
+			P->mg = mg_create(P, G);
+			if (!P->mg) { DSP_TRACE("multi-GPU setup failed (%s): single GPU", g_err.c_str()); g_err.clear(); }
+			else DSP_TRACE("multi-GPU plan: %d devices, slabs of %d frames, %lld columns each", P->mg->G, P->mg->Dl, P->mg->Pl);
+		}
+	}
+	if (P->mg) return mg_execute(P->mg, (const float *)in, (float *)out);
+#endif
 	const bool inplace = in == out;
 	if (!ensure_staging(P, inplace)) return false;
 	void *din = P->d_in, *dout = inplace ? P->d_in : P->d_out;
@@ -1051,6 +1212,9 @@ static void destroy_plan(dsp_dct_plan_s *p) {
 #if DSP_GPU
 	for (size_t k = 0; k < p->kids.size(); k++) { cudaStreamSynchronize(p->kid_st[k]); destroy_plan(p->kids[k]); cudaStreamDestroy(p->kid_st[k]); }
 	if (p->aux_ok) for (int k = 0; k < p->naux; k++) cudaStreamSynchronize(p->aux[k]);
+#endif
+#if DSP_GPU
+	mg_free(p->mg);
 #endif
 	rt_free(p->d_in);
 	rt_free(p->d_out);
@@ -1124,6 +1288,16 @@ void dsp_dct_execute(dsp_dct_plan p) {
 void dsp_dct_destroy(dsp_dct_plan p) {
 	if (!p) return;
 	dsp::destroy_plan(p);
+}
+
+void dsp_dct_plan_with_ngpus(int n) { g_ngpus.store(n < 1 ? 1 : (n > 8 ? 8 : n)); }
+int dsp_dct_plan_ngpus(dsp_dct_plan p) {
+#if DSP_GPU
+	return (p && p->mg) ? p->mg->G : 1;
+#else
+	(void)p;
+	return 1;
+#endif
 }
 
 void *dsp_dct_alloc(size_t bytes) {

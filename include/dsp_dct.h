@@ -77,6 +77,17 @@ void dsp_dct_destroy(dsp_dct_plan p);
 
 /* Replace fftw(alloc_real) / fftw(free) (spec/spec.c:59,143, motion/motion.c:500,826): pinned host memory, so
  * dsp_dct_execute's staging copies run at full PCIe rate. */
+/* Replaces fftw(plan_with_nthreads)(n): motion/motion.c:485-486, scan/scan.c:289-290 (`--fftw-threads n`).  The knob the
+ * reference uses for CPU threads selects the number of GPUs of this process here: rank-3 float plans over one contiguous
+ * [D][H][W] volume (motion -b 0x0x0), executed with HOST buffers (dsp_dct_execute / dsp_dct_execute_host), created after the
+ * call run slab-sharded over min(n, visible GPUs) devices: frame slabs in, per-frame 2-D passes whose last pass stores
+ * straight into the other GPUs' column buffers over NVLink (the all-to-all of SURVEY 8e fused into the transform), temporal
+ * pass, strided copy-out -- one exchange per transform, no NCCL, no second process.  Everything else (rank 1 / 2, double,
+ * embedded sub-boxes, fused stages, D or H not divisible by the GPU count, no peer access) runs on one GPU as before.
+ * dsp_dct_plan_ngpus reports how many GPUs the plan's last host execution used. */
+void dsp_dct_plan_with_ngpus(int n);
+int dsp_dct_plan_ngpus(dsp_dct_plan p);
+
 void *dsp_dct_alloc(size_t bytes);
 void dsp_dct_free(void *p);
 

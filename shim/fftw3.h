@@ -68,7 +68,7 @@ static inline dsp_dct_plan dsp_shim_checked(dsp_dct_plan p) {
 	static inline void PFX##_free(void *p) { dsp_dct_free(p); }                                                        \
 	static inline void PFX##_cleanup(void) { dsp_dct_cleanup(); }                                                      \
 	static inline int PFX##_init_threads(void) { return 1; }             /* non-zero = success */                      \
-	static inline void PFX##_plan_with_nthreads(int nthreads) { (void)nthreads; }                                      \
+	static inline void PFX##_plan_with_nthreads(int nthreads) { dsp_dct_plan_with_ngpus(nthreads); }                                      \
 	static inline void PFX##_cleanup_threads(void) {}                                                                  \
 	static inline int PFX##_import_wisdom_from_filename(const char *f) { (void)f; return 0; }  /* 0 = nothing read */  \
 	static inline int PFX##_export_wisdom_to_filename(const char *f) { (void)f; return 0; }

@@ -136,3 +136,85 @@ def test_motion_volume_u8_world2(mode, filt):
         assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
         frac = np.abs(pel.astype(np.float64))
         assert (np.abs(frac - np.floor(frac) - 0.5)[diff] < 2e-3).all()
+
+
+# ---------------------------------------------------------------------------------------------- several GPUs behind the C ABI
+def _single_process_multi_gpu(q):
+    """runs in a fresh process: dsp_dct_plan_with_ngpus is process-wide"""
+    try:
+        import ctypes
+        from dspfun_b200 import Plan, REDFT01, REDFT10, capi
+        from oracle import dct as od
+        lib = capi.load()
+        out = []
+        for (D, H, W) in ((16, 24, 32), (32, 120, 240), (8, 1080, 1920)):
+            x = np.random.default_rng(4).random((D, H, W)).astype(np.float32)
+            res = {}
+            for ng in (1, 2):
+                lib.dsp_dct_plan_with_ngpus(ng)
+                fwd = Plan("f", [D, H, W], [REDFT10] * 3)
+                inv = Plan("f", [D, H, W], [REDFT01] * 3)
+                y = fwd.execute_host(x.copy())
+                z = inv.execute_host(y.copy())
+                res[ng] = (y, z, lib.dsp_dct_plan_ngpus(fwd._h), lib.dsp_dct_plan_ngpus(inv._h))
+                fwd.destroy(); inv.destroy()
+            ref = od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 3) if D * H * W < 1 << 21 else None
+            out.append(dict(shape=(D, H, W), ngpus=res[2][2:], single=res[1][2:],
+                            same_fwd=bool(np.array_equal(res[1][0], res[2][0])), same_inv=bool(np.array_equal(res[1][1], res[2][1])),
+                            err_fwd=float(od.rel_l2(res[2][0], ref)) if ref is not None else float(od.rel_l2(res[2][0], res[1][0].astype(np.float64))),
+                            err_rt=float(od.rel_l2(res[2][1] / (8.0 * D * H * W), x.astype(np.float64)))))
+        # not eligible: an odd frame count stays on one GPU and still works
+        lib.dsp_dct_plan_with_ngpus(2)
+        p = Plan("f", [5, 8, 16], [REDFT10] * 3)
+        x = np.random.default_rng(5).random((5, 8, 16)).astype(np.float32)
+        y = p.execute_host(x.copy())
+        out.append(dict(shape=(5, 8, 16), ngpus=(lib.dsp_dct_plan_ngpus(p._h),), err_fwd=float(od.rel_l2(y, od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 3)))))
+        p.destroy()
+        q.put(out)
+    except Exception as e:
+        q.put(repr(e))
+        raise
+
+
+def test_rank3_host_plans_over_two_gpus_in_one_process():
+    """fftw_plan_with_nthreads(2) -> dsp_dct_plan_with_ngpus(2): motion's whole-clip rank-3 plan, host buffers, slab-sharded
+    over two GPUs of ONE process with the exchange fused into the transform (peer stores): same coefficients as one GPU"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_single_process_multi_gpu, args=(q,))
+    p.start()
+    res = q.get(timeout=300)
+    p.join(timeout=60)
+    assert not isinstance(res, str), res
+    for r in res[:-1]:
+        assert r["ngpus"] == (2, 2) and r["single"] == (1, 1), r
+        assert r["err_fwd"] < 1e-5 and r["err_rt"] < 1e-5, r
+        assert r["same_fwd"] and r["same_inv"], r                 # the same kernels on the same lines: identical bits
+    assert res[-1]["ngpus"] == (1,) and res[-1]["err_fwd"] < 1e-5
+
+
+def test_unmodified_motion_tool_over_two_gpus(tmp_path):
+    """the reference's motion.c, unmodified, `--fftw-threads 2 -b 0x0x0`: its rank-3 FFTW plans run on two GPUs through the shim"""
+    import subprocess
+    import torch
+    from tests import dspraw
+    from tests.test_reference_tools import _tool
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    D, H, W = 8, 64, 96
+    vol = np.random.default_rng(6).integers(0, 256, (D, H, W)).astype(np.uint8)
+    src = str(tmp_path / "in.dspv")
+    dspraw.write_video(src, "gray", W, H, [[vol[z]] for z in range(D)])
+    outs = {}
+    for ng in (1, 2):
+        dst = str(tmp_path / ("out%d.dspv" % ng))
+        env = dict(os.environ, DSP_DCT_TRACE="1")
+        r = subprocess.run([_tool("motion_gpu_f"), "-Q", "--fftw-threads", str(ng), "-b", "%dx%dx%d" % (W, H, D), "-q", "0.02", src, dst],
+                           check=True, env=env, capture_output=True, text=True)
+        assert ("multi-GPU plan: 2 devices" in r.stderr) == (ng == 2), r.stderr[-2000:]
+        outs[ng] = np.stack([f[0] for f in dspraw.read_video(dst)[3]])
+    assert np.array_equal(outs[1], outs[2])
