@@ -667,6 +667,37 @@ def bench_blocks(ctx, args, want_cpu):
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 5
         sizes[str(bs)] = {"ms": t, "gpixel_s": samples / t / 1e6, "achieved_gbs": 8.0 * samples / t / 1e6, "frac": 8.0 * samples / t / 1e6 / peak}
+    # the README's `motion -b 8x8x8 --quant` over a 256 x 1080 x 1920 8-bit volume (motion/README.md:75-77), all blocks at once
+    # through the C session dsp_motion_tiled_*: 8-bit pels -> block DCT-II (tensor-core GEMM over (h, w) + an 8-point pass
+    # over d) -> normalise / quantise / de-normalise -> inverse -> 8-bit pels
+    tiled = None
+    try:
+        del y
+        torch.cuda.empty_cache()
+        vd, vh, vw = 256, 1080, 1920
+        pels = torch.randint(16, 236, (vd, vh, vw), device="cuda", dtype=torch.uint8, generator=g)
+        outp = torch.empty_like(pels)
+        sess = lib.dsp_motion_tiled_create(vd, vh, vw, 8, 8, 8, 1.0)
+        if not sess:
+            raise RuntimeError(capi.last_error(lib))
+        for _ in range(2):
+            if lib.dsp_motion_tiled_process_dev(sess, pels.data_ptr(), outp.data_ptr(), None, stream) != 0:
+                raise RuntimeError(capi.last_error(lib))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.dsp_motion_tiled_process_dev(sess, pels.data_ptr(), outp.data_ptr(), None, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 5
+        lib.dsp_motion_tiled_destroy(sess)
+        tiled = {"volume": [vd, vh, vw], "block": [8, 8, 8], "quant": 1.0, "ms": t, "gpixel_s": vd * vh * vw / t / 1e6,
+                 "max_abs_pel_change": int((outp.to(torch.int16) - pels.to(torch.int16)).abs().max().item())}
+        del pels, outp
+        torch.cuda.empty_cache()
+    except Exception as e:
+        tiled = {"error": repr(e)}
+    y = torch.empty_like(x)
     e2e = None
     if not args.no_e2e:
         n = 16
@@ -707,7 +738,7 @@ def bench_blocks(ctx, args, want_cpu):
                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_sample": 16,
                         "note": "forward 4 B in + 4 B out, inverse the same; the tensor work (3 x TF32) is far below the tensor roofline"},
            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roundtrip_rel_l2": err,
-           "forward_by_block_size": sizes}
+           "forward_by_block_size": sizes, "motion_tiled_8x8x8_quant": tiled}
     del x, y
     torch.cuda.empty_cache()
     return rec
