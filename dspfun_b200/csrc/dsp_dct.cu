@@ -1448,6 +1448,15 @@ int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int 
 	return ok ? 0 : 1;
 }
 
+int dsp_block_dquant(void *d_coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer, unsigned long long *d_count, void *stream) {
+	g_err.clear();
+	if (!d_coeffs || D < 1 || H < 1 || W < 1 || bh < 1 || bw < 1 || !block_dquant_supports(bd) || D % bd) { g_err = "block d-axis + quantiser: bad arguments (depth 2, 4, 8 or 16 dividing D)"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	const bool ok = launch_block_dquant((float *)d_coeffs, D, H, W, bd, bh, bw, quantizer, d_count, (rt_stream)stream, g_err);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
+}
+
 int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream) {
 	g_err.clear();
 	if ((prec != 'f' && prec != 'd') || !d_coeffs || !d_pels || n < 1) { g_err = "block store: bad arguments"; return 1; }
@@ -1496,7 +1505,7 @@ dsp_motion_tiled dsp_motion_tiled_create(int D, int H, int W, int bd, int bh, in
 			v.push_back(dsp_dct_plan_many_batched('f', 1, &bw, (int)((W / bw) * (long long)H * D), nullptr, nullptr, 1, bw, nullptr, nullptr, 1, bw, &kind, 0, 1, 0, 0));
 			v.push_back(dsp_dct_plan_many_batched('f', 1, &bh, W, nullptr, nullptr, W, 1, nullptr, nullptr, W, 1, &kind, 0, (H / bh) * D, (ptrdiff_t)bh * W, (ptrdiff_t)bh * W));
 		}
-		if (bd > 1 || !t->gemm)    // d: bd frames at stride H W, H W adjacent columns, one batch element per slab of bd frames
+		if ((bd > 1 && !(t->gemm && block_dquant_supports(bd))) || !t->gemm)    // d: bd frames at stride H W, H W adjacent columns, one batch element per slab of bd frames
 			v.push_back(dsp_dct_plan_many_batched('f', 1, &bd, (int)hw, nullptr, nullptr, (int)hw, 1, nullptr, nullptr, (int)hw, 1, &kind, 0, D / bd, (ptrdiff_t)bd * hw, (ptrdiff_t)bd * hw));
 		for (dsp_dct_plan p : v) ok = ok && p != nullptr;
 	}
@@ -1530,11 +1539,15 @@ int dsp_motion_tiled_process_dev(dsp_motion_tiled t, const unsigned char *d_in, 
 		if (dsp_dct_execute_dev(p, t->work, t->work, stream)) return 1;                              // :641 for every block
 	const double q = t->quant != 0.0 ? (double)(float)(t->quant * 8.0 * std::sqrt(vol)) : 0.0;    // :570
 	if (coeffs_coded && !rt_zero(t->d_count, sizeof(unsigned long long), st, g_err)) return 1;
-	if (dsp_block_quant('f', t->work, t->D, t->H, t->W, t->bd, t->bh, t->bw, q, coeffs_coded ? t->d_count : nullptr, stream)) return 1;   // :644-647, :740-751
+	if (t->gemm && block_dquant_supports(t->bd)) {          // d forward + coefficient stage + d inverse in one pass (no d plans were made)
+		if (dsp_block_dquant(t->work, t->D, t->H, t->W, t->bd, t->bh, t->bw, q, coeffs_coded ? t->d_count : nullptr, stream)) return 1;
+	} else if (dsp_block_quant('f', t->work, t->D, t->H, t->W, t->bd, t->bh, t->bw, q, coeffs_coded ? t->d_count : nullptr, stream)) return 1;   // :644-647, :740-751
 	for (dsp_dct_plan p : t->inv)
 		if (dsp_dct_execute_dev(p, t->work, t->work, stream)) return 1;                              // :753
 	if (t->gemm && dsp_block_dct2d('f', t->work, t->work, t->D, t->H, t->W, t->bw, DSP_DCT_REDFT01, 1.0, stream)) return 1;
 	const double norm = 1.0 / std::sqrt(vol * 8.0);
+	// (a fused 8-bit store in the GEMM kernel's epilogue was tried: the double-precision clamp / lround on the four store
+	// warps made them the bottleneck, 7.6 -> 9.0 ms for the 256 x 1080 x 1920 volume; the separate sweep stays)
 	if (dsp_block_store_u8('f', t->work, d_out, n, norm * norm, stream)) return 1;               // :757-776 (sf = 1)
 	if (coeffs_coded) {
 		unsigned long long c = 0;

@@ -45,6 +45,9 @@ bool launch_l2_prefetch(const void *base, long long pitch_bytes, int nrows, int 
 bool launch_spec_resolve(char prec, const OpAny &op, const double *acc, double *scale_z, rt_stream st, std::string &err);
 bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,
                         unsigned long long *count, rt_stream st, std::string &err);
+bool block_dquant_supports(int bd);
+bool launch_block_dquant(float *coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer, unsigned long long *count, rt_stream st,
+                         std::string &err);
 bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, long long n, double scale, rt_stream st, std::string &err);
 bool launch_block_load_u8(char prec, const unsigned char *pels, void *coeffs, long long n, rt_stream st, std::string &err);
 

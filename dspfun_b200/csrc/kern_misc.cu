@@ -60,6 +60,7 @@ struct BlockQuantArgs {
 	long long n;                 // D * H * W
 	int H, W, bd, bh, bw;
 	double nf[4];                // 2 sqrt2 / sqrt2^k for k = number of zero in-block indices
+	double rnf[4], rquant;       // reciprocals (dsp_block_dquant)
 	double quantizer;            // 0 = no quantisation (the normalise / de-normalise rounding still applies)
 	unsigned long long *count;   // device counter of non-zero quantised coefficients (may be null)
 };
@@ -103,6 +104,110 @@ template <class T> __global__ void k_block_store_u8(const T *c, unsigned char *p
 		pels[i] = block_store_elem<T>(c[i], scale);
 }
 #endif
+
+// ------------------------------------------------------------------------------------------------ d axis + quantiser in one pass
+// The blocks of a tiled volume are independent along d as well: once the two spatial axes are done (dsp_block_dct2d), one
+// thread per pixel and group of BD frames holds the BD samples in registers, applies REDFT10 along d (a BD x BD matrix
+// product with FFTW's unnormalised cosines), the coefficient stage above on the now complete 3-D coefficients, and REDFT01
+// along d -- three sweeps over the volume (d forward, quantise, d inverse = 24 B per sample) become one (8 B per sample).
+// Accesses are coalesced along (h, w).
+template <int BD>
+DSP_DEV int block_dquant_pixel(const BlockQuantArgs &a, float *c, long long hw, long long plane, long long zg, const float *m10, const float *m01) {
+	const long long row = hw / a.W;
+	const int x = (int)(hw - row * a.W), y = (int)row;
+	const int kxy = ((x % a.bw) == 0) + ((y % a.bh) == 0);
+	float v[BD], t[BD];
+	float *p = c + zg * BD * plane + hw;
+#pragma unroll
+	for (int z = 0; z < BD; z++) v[z] = p[z * plane];
+	int nz = 0;
+#pragma unroll
+	for (int k = 0; k < BD; k++) {                                   // REDFT10 along d, then motion.c:644-647, 740-751
+		float s = 0.0f;
+#pragma unroll
+		for (int z = 0; z < BD; z++) s = fmaf(m10[k * BD + z], v[z], s);
+		// (the two divisions of the reference are multiplications by reciprocals prepared once, as in the spec store stage:
+		// the double result differs by at most one ulp, which the cast to float absorbs)
+		const double nf = a.nf[kxy + (k == 0)], rnf = a.rnf[kxy + (k == 0)];
+		float f = (float)((double)s * nf);
+		if (a.quantizer != 0.0) {
+			f = (float)(round((double)f * a.rquant) * a.quantizer);
+			nz += f != 0.0f;
+		}
+		t[k] = (float)((double)f * rnf);
+	}
+#pragma unroll
+	for (int z = 0; z < BD; z++) {                                   // REDFT01 along d
+		float s = 0.0f;
+#pragma unroll
+		for (int k = 0; k < BD; k++) s = fmaf(m01[z * BD + k], t[k], s);
+		p[z * plane] = s;
+	}
+	return nz;
+}
+#if DSP_GPU
+template <int BD> __global__ void __launch_bounds__(256) k_block_dquant(BlockQuantArgs a, float *c, long long plane, long long groups) {
+	__shared__ float m10[BD * BD], m01[BD * BD];
+	const double PI = 3.14159265358979323846264338327950288;
+	for (int i = threadIdx.x; i < BD * BD; i += blockDim.x) {
+		const int r = i / BD, q = i - r * BD;
+		m10[i] = (float)(2.0 * cos(PI * (q + 0.5) * r / BD));                       // Y[r] = 2 sum_q x[q] cos(pi (q + 1/2) r / BD)
+		m01[i] = q == 0 ? 1.0f : (float)(2.0 * cos(PI * (r + 0.5) * q / BD));       // y[r] = x[0] + 2 sum_{q>=1} x[q] cos(pi (r + 1/2) q / BD)
+	}
+	__syncthreads();
+	unsigned long long local = 0;
+	const long long total = plane * groups;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const long long zg = i / plane, hw = i - zg * plane;
+		local += (unsigned long long)block_dquant_pixel<BD>(a, c, hw, plane, zg, m10, m01);
+	}
+	if (a.count) {
+		for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+		if ((threadIdx.x & 31) == 0 && local) atomicAdd(a.count, local);
+	}
+}
+#endif
+template <int BD>
+static bool block_dquant_t(const BlockQuantArgs &a, float *c, long long plane, long long groups, rt_stream st, std::string &err) {
+#if DSP_GPU
+	k_block_dquant<BD><<<148 * 8, 256, 0, st>>>(a, c, plane, groups);
+	return rt_ok(cudaGetLastError(), err, "block d-axis + quantiser launch");
+#else
+	(void)st; (void)err;
+	const double PI = 3.14159265358979323846264338327950288;
+	float m10[BD * BD], m01[BD * BD];
+	for (int i = 0; i < BD * BD; i++) {
+		const int r = i / BD, q = i - r * BD;
+		m10[i] = (float)(2.0 * cos(PI * (q + 0.5) * r / BD));
+		m01[i] = q == 0 ? 1.0f : (float)(2.0 * cos(PI * (r + 0.5) * q / BD));
+	}
+	unsigned long long total = 0;
+	for (long long zg = 0; zg < groups; zg++)
+		for (long long hw = 0; hw < plane; hw++) total += (unsigned long long)block_dquant_pixel<BD>(a, c, hw, plane, zg, m10, m01);
+	if (a.count) *a.count += total;
+	return true;
+#endif
+}
+bool block_dquant_supports(int bd) { return bd == 2 || bd == 4 || bd == 8 || bd == 16; }
+bool launch_block_dquant(float *coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer, unsigned long long *count, rt_stream st,
+                         std::string &err) {
+	BlockQuantArgs a;
+	a.n = (long long)D * H * W; a.H = H; a.W = W; a.bd = bd; a.bh = bh; a.bw = bw; a.quantizer = quantizer; a.count = count;
+	const long double s2 = 1.41421356237309504880168872420969808L;
+	long double den = 1.0L;
+	for (int k = 0; k < 4; k++) { a.nf[k] = (double)((2.0L * s2) / den); a.rnf[k] = (double)(den / (2.0L * s2)); den *= s2; }
+	a.rquant = quantizer != 0.0 ? 1.0 / quantizer : 0.0;
+	const long long plane = (long long)H * W, groups = D / bd;
+	switch (bd) {
+	case 2: return block_dquant_t<2>(a, coeffs, plane, groups, st, err);
+	case 4: return block_dquant_t<4>(a, coeffs, plane, groups, st, err);
+	case 8: return block_dquant_t<8>(a, coeffs, plane, groups, st, err);
+	case 16: return block_dquant_t<16>(a, coeffs, plane, groups, st, err);
+	default: break;
+	}
+	err = "block d-axis + quantiser: depth must be 2, 4, 8 or 16";
+	return false;
+}
 
 bool launch_block_quant(char prec, void *coeffs, long long n, int H, int W, int bd, int bh, int bw, double quantizer,
                         unsigned long long *count, rt_stream st, std::string &err) {

@@ -112,9 +112,10 @@ class MotionTiled:
                     Plan("f", [bh], [kind], W, None, W, 1, None, W, 1, (H // bh) * D, bh * W, bh * W, lib=self.lib),
                     Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib))
         self.gemm = bool(gemm) and bh == bw and bw in (8, 16, 32, 64)
+        self.dquant = self.gemm and bd in (2, 4, 8, 16)       # d forward + coefficient stage + d inverse in one pass (dsp_block_dquant)
         if self.gemm:
-            def plans(kind):                                  # the d axis only (none for depth-1 blocks)
-                if bd == 1:
+            def plans(kind):                                  # the d axis only (none for depth-1 blocks or with dsp_block_dquant)
+                if bd == 1 or self.dquant:
                     return ()
                 return (Plan("f", [bd], [kind], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=self.lib),)
         self.fwd = plans(capi.REDFT10)
@@ -145,7 +146,11 @@ class MotionTiled:
         # normalise, quantise + count, de-normalise: one pass (dsp_block_quant, :644-647, :740-751)
         q = float(np.float32(self.quant * 8.0 * np.sqrt(np.float64(bd * bh * bw)))) if self.quant else 0.0   # :570
         cnt = t.zeros(1, dtype=t.int64, device=c.device)
-        if self.lib.dsp_block_quant(b"f", c.data_ptr(), D, H, W, bd, bh, bw, q, cnt.data_ptr(), stream) != 0:
+        if self.dquant:
+            rc = self.lib.dsp_block_dquant(c.data_ptr(), D, H, W, bd, bh, bw, q, cnt.data_ptr(), stream)
+        else:
+            rc = self.lib.dsp_block_quant(b"f", c.data_ptr(), D, H, W, bd, bh, bw, q, cnt.data_ptr(), stream)
+        if rc != 0:
             raise capi.DspDctError(capi.last_error(self.lib))
         for p in self.inv:
             p.execute_dev(c.data_ptr(), c.data_ptr(), stream)                                   # :753

@@ -243,6 +243,10 @@ void dsp_motion_destroy(dsp_motion m);
 int dsp_block_quant(char prec, void *d_coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer,
                     unsigned long long *d_count, void *stream);
 int dsp_block_store_u8(char prec, const void *d_coeffs, unsigned char *d_pels, long long n, double scale, void *stream);
+/*   dsp_block_dquant   : float volumes, block depth bd = 2, 4, 8 or 16, to be called between the spatial transforms: in ONE
+ *                        pass per pixel and group of bd frames: REDFT10 along d, the stage of dsp_block_quant on the now
+ *                        complete 3-D coefficients, REDFT01 along d (replaces d-plan + dsp_block_quant + inverse d-plan). */
+int dsp_block_dquant(void *d_coeffs, int D, int H, int W, int bd, int bh, int bw, double quantizer, unsigned long long *d_count, void *stream);
 
 /* ---- the same block-tiled volume as ONE session behind the C ABI (what dspfun_b200/motion.py: MotionTiled does from
  * Python): `motion -b BWxBHxBD [--quant q]` with block == scaled over a [D][H][W] plane of 8-bit pels in device memory
