@@ -1757,27 +1757,23 @@ static void motion_constants(const dsp_motion_params *mp, double &scalefactor, d
 	norm = 1.0 / sqrt(sw * sh * sd * 8.0);                                                   // motion.c:567
 }
 
-int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsigned long long *d_counter, int flat_w,
-                              long long flat_base) {
-	g_err.clear();
-	if (!p || !mp) { g_err = "null plan or params"; return 1; }
-	if (p->fuse_kind && p->fuse_kind != 4) { g_err = "plan already carries a fused stage"; return 1; }
+// the coefficient stage of motion's block loop (motion.c:617, 644-751) as one pointwise map
+static bool motion_coeff_op(const dsp_motion_params *mp, char prec, unsigned long long *d_counter, int flat_w, long long flat_base, OpAny &op) {
 	double scalefactor, norm;
 	motion_constants(mp, scalefactor, norm);
 	const double sw = mp->scaled[2], sh = mp->scaled[1], sd = mp->scaled[0];
-	OpAny op;
 	memset(&op, 0, sizeof(op));
 	op.kind = OP_MOTION_COEFF;
 	for (int i = 0; i < 3; i++) {
 		const int active = mp->block[i] < mp->scaled[i] ? mp->block[i] : mp->scaled[i];      // motion.c:494-496
-		if (mp->bp_begin[i] < 0 || mp->bp_end[i] > active || mp->bp_begin[i] > mp->bp_end[i]) { g_err = "band-pass box outside the active box"; return 1; }
+		if (mp->bp_begin[i] < 0 || mp->bp_end[i] > active || mp->bp_begin[i] > mp->bp_end[i]) { g_err = "band-pass box outside the active box"; return false; }
 		op.a3[i] = active; op.b3[i] = mp->bp_begin[i]; op.e3[i] = mp->bp_end[i];
 	}
 	op.m[0] = mp->damp; op.m[1] = mp->boost;
 	op.m[2] = mp->threshold_min * 255.0 / norm / norm; op.m[3] = mp->threshold_max * 255.0 / norm / norm;   // motion.c:571-572
-	if (p->prec == 'f') { op.m[2] = (double)(float)op.m[2]; op.m[3] = (double)(float)op.m[3]; }
+	if (prec == 'f') { op.m[2] = (double)(float)op.m[2]; op.m[3] = (double)(float)op.m[3]; }
 	op.m[4] = mp->quant * 8.0 * sqrt(sw * sh * sd);                                          // motion.c:570
-	if (p->prec == 'f') op.m[4] = (double)(float)op.m[4];
+	if (prec == 'f') op.m[4] = (double)(float)op.m[4];
 	op.m[5] = 127.5 / (norm * norm * scalefactor);                                           // motion.c:736
 	op.flag = mp->preserve_dc;
 	op.aux = d_counter;
@@ -1794,6 +1790,16 @@ int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsig
 	// flat_w > 0: the plan is the temporal pass of a slab-sharded volume over a [D][hw-slice] array -- the axis index is
 	// z and (y, x) come from the flattened column index: hw = flat_base + column, y = hw / flat_w, x = hw % flat_w
 	op.w = flat_w; op.lo = (int)flat_base;
+	return true;
+}
+
+int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsigned long long *d_counter, int flat_w,
+                              long long flat_base) {
+	g_err.clear();
+	if (!p || !mp) { g_err = "null plan or params"; return 1; }
+	if (p->fuse_kind && p->fuse_kind != 4) { g_err = "plan already carries a fused stage"; return 1; }
+	OpAny op;
+	if (!motion_coeff_op(mp, p->prec, d_counter, flat_w, flat_base, op)) return 1;
 	if (flat_w > 0 && (p->rank != 1 || p->passes.size() != 1 || p->passes[0].row)) {
 		g_err = "flat coefficient coordinates need the rank-1 strided-axis plan of a [D][h*w slice] array";
 		return 1;
@@ -1808,6 +1814,19 @@ int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsig
 	}
 	p->fuse_kind = 4;
 	return 0;
+}
+
+int dsp_motion_coeff_stage(char prec, const dsp_motion_params *mp, void *d_coeffs, unsigned long long *d_counter, void *stream) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || !mp || !d_coeffs) { g_err = "coefficient stage: bad arguments"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	OpAny op;
+	if (!motion_coeff_op(mp, prec, d_counter, 0, 0, op)) return 1;
+	int mb[3];
+	for (int i = 0; i < 3; i++) mb[i] = mp->block[i] > mp->scaled[i] ? mp->block[i] : mp->scaled[i];      // minbuf, motion.c:491-493
+	const bool ok = launch_motion_coeff(prec, op, d_coeffs, mb[0], mb[1], mb[2], (rt_stream)stream, g_err);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
 }
 
 int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp) {

@@ -74,6 +74,7 @@ struct MotionSpecArgs {
 	OpAny coeff;                 // spec: the coefficient stages (OP_MOTION_COEFF with skipd), run here instead of in an inverse pass
 };
 
+bool launch_motion_coeff(char prec, const OpAny &op, void *coeffs, int D, int H, int W, rt_stream st, std::string &err);
 bool launch_motion_ispec(char prec, const MotionSpecArgs &a, const void *pels, void *coeffs, rt_stream st, std::string &err);
 bool launch_motion_spec(char prec, const MotionSpecArgs &a, const void *coeffs, void *pels, rt_stream st, std::string &err);
 

@@ -267,6 +267,55 @@ bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, l
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------ motion coefficient stage, standalone
+// The same pointwise map the plans can carry in a pass (OP_MOTION_COEFF), as one lean sweep over a [D][H][W] volume of
+// coefficients.  Fused into the temporal pass of the 256 x 1080 x 1920 volume it costs 2.4 ms on top of the plain pass (the
+// coordinate-carrying tile moves of the transform kernels are slow); this sweep moves 8 B per sample at stream speed.
+template <class T, class Op>
+DSP_DEV void motion_coeff_elem(const Op &op, T *c, uint32_t i, uint32_t W, uint32_t H, const FastDiv &dW, const FastDiv &dH) {
+	const uint32_t row = fd_div(i, dW), x = i - row * W;
+	const uint32_t z = fd_div(row, dH), y = row - z * H;
+	Coord cc = {0, 0, 0, 0, 0};
+	cc.i0 = (int)z; cc.i1 = (int)y; cc.i2 = (int)x;
+	c[i] = op(c[i], cc);
+}
+#if DSP_GPU
+template <class T, class Op>
+__global__ void __launch_bounds__(256) k_motion_coeff(const __grid_constant__ Op op, T *c, uint32_t n, uint32_t W, uint32_t H, FastDiv dW, FastDiv dH) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) motion_coeff_elem<T, Op>(op, c, i, W, H, dW, dH);
+}
+#endif
+static FastDiv misc_mk_fd(uint32_t d) {           // same scheme as the planner's (fd_div: n < 2^31)
+	FastDiv f;
+	f.d = d ? d : 1;
+	if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
+	uint32_t k = 0;
+	while ((1ull << k) < f.d) k++;
+	const uint32_t p = 31 + k;
+	f.mul = (uint32_t)(((1ull << p) + f.d - 1) / f.d);
+	f.shr = p - 32;
+	return f;
+}
+template <class T>
+static bool motion_coeff_t(const OpAny &op, T *c, int D, int H, int W, const FastDiv &dW, const FastDiv &dH, rt_stream st, std::string &err) {
+	const long long n = (long long)D * H * W;
+	if (n >= (1ll << 31)) { err = "coefficient stage: volume too large for one sweep"; return false; }
+#if DSP_GPU
+	const int grid = 148 * 16;
+	if (op.fast) k_motion_coeff<T, OpMotionCoeff><<<grid, 256, 0, st>>>(OpMotionCoeff::from(op), c, (uint32_t)n, (uint32_t)W, (uint32_t)H, dW, dH);
+	else k_motion_coeff<T, OpAny><<<grid, 256, 0, st>>>(op, c, (uint32_t)n, (uint32_t)W, (uint32_t)H, dW, dH);
+	return rt_ok(cudaGetLastError(), err, "motion coefficient stage launch");
+#else
+	(void)st;
+	for (long long i = 0; i < n; i++) motion_coeff_elem<T, OpAny>(op, c, (uint32_t)i, (uint32_t)W, (uint32_t)H, dW, dH);
+	return true;
+#endif
+}
+bool launch_motion_coeff(char prec, const OpAny &op, void *coeffs, int D, int H, int W, rt_stream st, std::string &err) {
+	const FastDiv dW = misc_mk_fd((uint32_t)W), dH = misc_mk_fd((uint32_t)H);
+	return prec == 'f' ? motion_coeff_t<float>(op, (float *)coeffs, D, H, W, dW, dH, st, err) : motion_coeff_t<double>(op, (double *)coeffs, D, H, W, dW, dH, st, err);
+}
+
 // ------------------------------------------------------------------------------------------------ motion spectrograms
 // motion --ispec: the pels ARE a spectrogram; they become coefficients without a forward transform (motion.c:627-637).
 // motion --spec : the coefficients are written out as a spectrogram instead of being inverted (motion.c:755-776).

@@ -226,6 +226,10 @@ dsp_motion dsp_motion_create(char prec, const dsp_motion_params *mp);
 int dsp_dct_fuse_pel_load(dsp_dct_plan p, int float_pixels);
 int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsigned long long *d_counter, int flat_w,
                               long long flat_base);
+/* The same coefficient stage as ONE sweep over a contiguous device volume of coefficients [minbuf.d][minbuf.h][minbuf.w]
+ * (block == scaled: the whole volume), in place, for callers that run plain plans around it.  Measured on the
+ * 256 x 1080 x 1920 volume the separate sweep is cheaper than carrying the stage in the temporal pass. */
+int dsp_motion_coeff_stage(char prec, const dsp_motion_params *mp, void *d_coeffs, unsigned long long *d_counter, void *stream);
 int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp);
 /* host staging buffers (pels_out may equal pels_in); *coeffs_coded += non-zero coefficients after --quant */
 int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned long long *coeffs_coded);
