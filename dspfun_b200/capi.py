@@ -28,7 +28,7 @@ SYMBOLS = [
     "dsp_scan_create", "dsp_scan_frame", "dsp_scan_coeffs", "dsp_scan_sum", "dsp_scan_destroy",
     "dsp_motion_create", "dsp_motion_block", "dsp_motion_block_dev", "dsp_motion_destroy", "dsp_block_quant",
     "dsp_block_store_u8",
-    "dsp_motion_coeff_stage", "dsp_block_dquant", "dsp_block_dct2d", "dsp_dct_plan_with_ngpus", "dsp_dct_plan_ngpus",
+    "dsp_motion_coeff_stage", "dsp_motion_coeff_stage_flat", "dsp_block_dquant", "dsp_block_dct2d", "dsp_dct_plan_with_ngpus", "dsp_dct_plan_ngpus",
     "dsp_motion_tiled_create", "dsp_motion_tiled_process_dev", "dsp_motion_tiled_destroy",
     "dsp_block_dct2d_debug",
     "dsp_zoom_create", "dsp_zoom_view_size", "dsp_zoom_frame", "dsp_zoom_last_path", "dsp_zoom_destroy",
@@ -115,6 +115,8 @@ def bind(path):
     lib.dsp_motion_tiled_destroy.argtypes = [vp]
     lib.dsp_motion_coeff_stage.restype = ci
     lib.dsp_motion_coeff_stage.argtypes = [ctypes.c_char, ctypes.POINTER(MotionParams), vp, vp, vp]
+    lib.dsp_motion_coeff_stage_flat.restype = ci
+    lib.dsp_motion_coeff_stage_flat.argtypes = [ctypes.c_char, ctypes.POINTER(MotionParams), vp, ci, ctypes.c_longlong, ci, ctypes.c_longlong, vp, vp]
     lib.dsp_block_dquant.restype = ci
     lib.dsp_block_dquant.argtypes = [vp, ci, ci, ci, ci, ci, ci, cd, vp, vp]
     lib.dsp_block_dct2d.restype = ci

@@ -1829,6 +1829,18 @@ int dsp_motion_coeff_stage(char prec, const dsp_motion_params *mp, void *d_coeff
 	return ok ? 0 : 1;
 }
 
+int dsp_motion_coeff_stage_flat(char prec, const dsp_motion_params *mp, void *d_coeffs, int D, long long ncols, int flat_w, long long flat_base,
+                                unsigned long long *d_counter, void *stream) {
+	g_err.clear();
+	if ((prec != 'f' && prec != 'd') || !mp || !d_coeffs || D < 1 || ncols < 1 || ncols > 0x7fffffffLL || flat_w < 1 || flat_base < 0) { g_err = "coefficient stage: bad arguments"; return 1; }
+	if (!rt_init(g_err)) return 1;
+	OpAny op;
+	if (!motion_coeff_op(mp, prec, d_counter, flat_w, flat_base, op)) return 1;
+	const bool ok = launch_motion_coeff(prec, op, d_coeffs, D, 0, (int)ncols, (rt_stream)stream, g_err);
+	if (ok) g_launches++;
+	return ok ? 0 : 1;
+}
+
 int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp) {
 	g_err.clear();
 	if (!p || !mp) { g_err = "null plan or params"; return 1; }

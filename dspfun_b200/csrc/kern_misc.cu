@@ -271,12 +271,17 @@ bool launch_block_store_u8(char prec, const void *coeffs, unsigned char *pels, l
 // The same pointwise map the plans can carry in a pass (OP_MOTION_COEFF), as one lean sweep over a [D][H][W] volume of
 // coefficients.  Fused into the temporal pass of the 256 x 1080 x 1920 volume it costs 2.4 ms on top of the plain pass (the
 // coordinate-carrying tile moves of the transform kernels are slow); this sweep moves 8 B per sample at stream speed.
+// H > 0: a [D][H][W] volume, coordinates (z, y, x).  H == 0: a [D][W] array whose W columns are a slice of the flattened
+// (y, x) positions (the temporal layout of a slab-sharded volume): the stage decodes (y, x) from op.lo + column itself.
 template <class T, class Op>
 DSP_DEV void motion_coeff_elem(const Op &op, T *c, uint32_t i, uint32_t W, uint32_t H, const FastDiv &dW, const FastDiv &dH) {
 	const uint32_t row = fd_div(i, dW), x = i - row * W;
-	const uint32_t z = fd_div(row, dH), y = row - z * H;
 	Coord cc = {0, 0, 0, 0, 0};
-	cc.i0 = (int)z; cc.i1 = (int)y; cc.i2 = (int)x;
+	if (H == 0) { cc.ch = (int)x; cc.i2 = (int)row; }
+	else {
+		const uint32_t z = fd_div(row, dH), y = row - z * H;
+		cc.i0 = (int)z; cc.i1 = (int)y; cc.i2 = (int)x;
+	}
 	c[i] = op(c[i], cc);
 }
 #if DSP_GPU
@@ -298,7 +303,7 @@ static FastDiv misc_mk_fd(uint32_t d) {           // same scheme as the planner'
 }
 template <class T>
 static bool motion_coeff_t(const OpAny &op, T *c, int D, int H, int W, const FastDiv &dW, const FastDiv &dH, rt_stream st, std::string &err) {
-	const long long n = (long long)D * H * W;
+	const long long n = (long long)D * (H > 0 ? H : 1) * W;
 	if (n >= (1ll << 31)) { err = "coefficient stage: volume too large for one sweep"; return false; }
 #if DSP_GPU
 	const int grid = 148 * 16;
@@ -312,7 +317,7 @@ static bool motion_coeff_t(const OpAny &op, T *c, int D, int H, int W, const Fas
 #endif
 }
 bool launch_motion_coeff(char prec, const OpAny &op, void *coeffs, int D, int H, int W, rt_stream st, std::string &err) {
-	const FastDiv dW = misc_mk_fd((uint32_t)W), dH = misc_mk_fd((uint32_t)H);
+	const FastDiv dW = misc_mk_fd((uint32_t)W), dH = misc_mk_fd((uint32_t)(H > 0 ? H : 1));
 	return prec == 'f' ? motion_coeff_t<float>(op, (float *)coeffs, D, H, W, dW, dH, st, err) : motion_coeff_t<double>(op, (double *)coeffs, D, H, W, dW, dH, st, err);
 }
 

@@ -19,8 +19,10 @@ Two exchange modes:
     [D][HW/G] array; inverse, the temporal pass writes frames [g D/G, (g+1) D/G) into rank g's slab.  No pack kernel,
     no separate collective: one device-side barrier before and after.  Needs H % G == 0, float, CUDA tensors.
 """
-import numpy as np
 import ctypes
+import os
+
+import numpy as np
 
 import torch
 import torch.distributed as dist
@@ -83,8 +85,12 @@ class Dist3D:
                 self.fwd3.fuse_pel_load(bool(motion.float_pixels))
                 self.inv3.fuse_pel_store(motion)
             else:
+                # (the coefficient stages run as a sweep over this rank's [D][Pl] coefficients with flat (y, x) coordinates,
+                # dsp_motion_coeff_stage_flat in process(); set DSP_DIST_FUSE_COEFF=1 to carry them in the temporal pass's store)
                 self.fwd2.fuse_pel_load(bool(motion.float_pixels))
-                self.fwdt.fuse_motion_coeff(motion, None, W, self.rank * self.Pl)    # coefficient stages: temporal pass's store
+                self.fuse_coeff = bool(os.environ.get("DSP_DIST_FUSE_COEFF"))
+                if self.fuse_coeff:
+                    self.fwdt.fuse_motion_coeff(motion, None, W, self.rank * self.Pl)
                 self.inv2.fuse_pel_store(motion)
         self.a2a_bytes = 0
         self.mode = "nccl"
@@ -167,6 +173,10 @@ class Dist3D:
             self.inv3.execute_dev(_ptr(work), _ptr(out), st)
             return out
         coeffs = self._forward_from(pels, work, st)
+        if not self.fuse_coeff:
+            if self.lib.dsp_motion_coeff_stage_flat(self.prec.encode(), ctypes.byref(self.motion), _ptr(coeffs), self.D, self.Pl, self.W,
+                                                    self.rank * self.Pl, None, st) != 0:
+                raise capi.DspDctError(capi.last_error(self.lib))
         slab = self._inverse_to_slab(coeffs, st)
         self.inv2.execute_dev(_ptr(slab), _ptr(out), st)
         return out

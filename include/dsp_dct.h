@@ -230,6 +230,10 @@ int dsp_dct_fuse_motion_coeff(dsp_dct_plan p, const dsp_motion_params *mp, unsig
  * (block == scaled: the whole volume), in place, for callers that run plain plans around it.  Measured on the
  * 256 x 1080 x 1920 volume the separate sweep is cheaper than carrying the stage in the temporal pass. */
 int dsp_motion_coeff_stage(char prec, const dsp_motion_params *mp, void *d_coeffs, unsigned long long *d_counter, void *stream);
+/* The same over the temporal layout of a slab-sharded volume: a [D][ncols] array whose columns are the flattened (y, x)
+ * positions flat_base .. flat_base + ncols of frames of width flat_w (the coordinates dsp_dct_fuse_motion_coeff's flat mode uses). */
+int dsp_motion_coeff_stage_flat(char prec, const dsp_motion_params *mp, void *d_coeffs, int D, long long ncols, int flat_w, long long flat_base,
+                                unsigned long long *d_counter, void *stream);
 int dsp_dct_fuse_pel_store(dsp_dct_plan p, const dsp_motion_params *mp);
 /* host staging buffers (pels_out may equal pels_in); *coeffs_coded += non-zero coefficients after --quant */
 int dsp_motion_block(dsp_motion m, const void *pels_in, void *pels_out, unsigned long long *coeffs_coded);
