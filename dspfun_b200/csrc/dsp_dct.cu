@@ -1320,6 +1320,7 @@ void dsp_dct_cleanup(void) {
 		delete t;
 	}
 	g_tables.clear();
+	block_mm_cleanup();
 }
 
 const char *dsp_dct_last_error(void) { return g_err.c_str(); }

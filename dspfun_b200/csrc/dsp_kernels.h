@@ -53,6 +53,7 @@ bool launch_block_load_u8(char prec, const unsigned char *pels, void *coeffs, lo
 
 // 2-D block DCT of whole planes as tensor-core GEMMs (kern_block_mm.cu): tcgen05 / TMEM, 3 x TF32 split for float accuracy
 bool block_mm_supports(int B);
+void block_mm_cleanup();
 bool launch_block_mm_f32(const float *in, float *out, long long nplanes, int H, int W, int B, int kind, double scale, rt_stream st,
                          std::string &err, float *dbg);
 

@@ -338,6 +338,9 @@ static double block_matrix(int B, int kind, int n, int k) {
 
 bool block_mm_supports(int B) { return B == 8 || B == 16 || B == 32 || B == 64; }
 
+// releases the cached block matrices (dsp_dct_cleanup)
+void block_mm_cleanup();
+
 #if DSP_GPU
 static float host_tf32_hi(float x) {
 	uint32_t u;
@@ -370,6 +373,20 @@ static const float *block_mm_consts(int B, int kind, int Be, std::string &err) {
 	g_mm_consts[key] = d;
 	return d;
 }
+void block_mm_cleanup() {
+	std::lock_guard<std::mutex> lock(g_mm_mu);
+	int cur = 0;
+	cudaGetDevice(&cur);
+	for (auto &kv : g_mm_consts) {
+		cudaSetDevice((int)(kv.first >> 16));
+		cudaDeviceSynchronize();                     // a launch that still reads the matrix finishes first
+		cudaFree(kv.second);
+	}
+	cudaSetDevice(cur);
+	g_mm_consts.clear();
+}
+#else
+void block_mm_cleanup() {}
 #endif
 
 // every B x B block of `nplanes` planes [H][W] (floats, W-contiguous): out = M X M^T per block, times `scale`.
