@@ -2,8 +2,8 @@
 // (zoom/zoom.c:361-375) as two dense contractions per channel:  out = Yb * C * Xb^T / (W H).
 //
 // This is the reference's O(N^3) loop restated as GEMMs.  Products of coeff-precision values are accumulated in
-// double (the reference accumulates in `intermediate`), on the FP32/FP64 pipes: a first, correctness-oriented
-// version -- a split-precision tensor-core path is the planned replacement.
+// double (the reference accumulates in `intermediate`), on the FP32/FP64 pipes.  Float sessions take the split-precision
+// tensor-core GEMM of kern_gemm_tc.cu instead (dsp_zoom_frame); this one serves double and is the float fallback.
 #include "dsp_kernels.h"
 #include <math.h>
 #include <vector>
