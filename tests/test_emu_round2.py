@@ -203,3 +203,71 @@ def test_motion_tiled_c_session(lib):
     cases.check_motion_tiled_c_session(lib, (8, 32, 16), (4, 16, 8), 0.02)          # three per-axis plans
     cases.check_motion_tiled_c_session(lib, (2, 24, 40), (1, 8, 8), 0.0)            # depth-1 blocks, no quantiser
     assert not lib.dsp_motion_tiled_create(16, 16, 24, 8, 8, 7, 0.0) and capi.last_error(lib)
+
+
+# ---------------------------------------------------------------------------------------------- motion coefficient stage as a sweep
+@pytest.mark.parametrize("kw", [dict(), dict(damp=0.25, boost=1.5, bandpass=((0, 1, 1), (3, 6, 9))), dict(quant=0.05),
+                                dict(threshold=(0.001, 0.4), preserve_dc="dc", damp=0.0, bandpass=((1, 0, 2), (4, 8, 12)))])
+def test_motion_coeff_stage_sweep_equals_the_fused_pass(lib, kw):
+    """dsp_motion_coeff_stage (one sweep over the volume) and dsp_motion_coeff_stage_flat (the [D][h*w] layout of the sharded
+    path) apply exactly the map dsp_dct_fuse_motion_coeff carries in a pass: same coefficients in, same bits out"""
+    import ctypes
+    from dspfun_b200.dist3d import motion_params
+    D, H, W = 4, 8, 12
+    kw = dict(kw)
+    if "preserve_dc" in kw:
+        kw["preserve_dc"] = {"dc": 1, "grey": 2}[kw["preserve_dc"]]
+    mp = motion_params((D, H, W), **kw)
+    c = (np.random.default_rng(2).standard_normal((D, H, W)) * 50).astype(np.float32)
+    fused = Plan("f", [D, H, W], [REDFT01] * 3, lib=lib).fuse_motion_coeff(mp)
+    want = fused.execute_host(c.copy())
+    fused.destroy()
+    plain = Plan("f", [D, H, W], [REDFT01] * 3, lib=lib)
+    a = c.copy()
+    assert lib.dsp_motion_coeff_stage(b"f", ctypes.byref(mp), a.ctypes.data, None, None) == 0, capi.last_error(lib)
+    b = c.copy().reshape(D, H * W)
+    assert lib.dsp_motion_coeff_stage_flat(b"f", ctypes.byref(mp), b.ctypes.data, D, H * W, W, 0, None, None) == 0, capi.last_error(lib)
+    assert np.array_equal(a.reshape(D, H * W), b)
+    # a slice of the columns with its base, as a rank of the sharded path sees it
+    half = np.ascontiguousarray(c.reshape(D, H * W)[:, H * W // 2:])
+    assert lib.dsp_motion_coeff_stage_flat(b"f", ctypes.byref(mp), half.ctypes.data, D, H * W // 2, W, H * W // 2, None, None) == 0
+    assert np.array_equal(half, b[:, H * W // 2:])
+    got = plain.execute_host(a)
+    plain.destroy()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bd", [2, 4, 8, 16])
+def test_block_dquant_equals_the_three_sweeps(lib, bd):
+    """dsp_block_dquant (d forward + quantiser stage + d inverse per pixel, in registers) against the d plan, dsp_block_quant
+    and the inverse d plan; the direct 8-point sums and the FFT passes round differently, so the comparison is to float accuracy"""
+    import ctypes
+    D, H, W, bh, bw = 2 * bd, 8, 16, 8, 8
+    c = (np.random.default_rng(3).standard_normal((D, H, W)) * 200).astype(np.float32)
+    q = float(np.float32(0.05 * 8.0 * np.sqrt(bd * bh * bw)))
+    a = c.copy()
+    cnt_a = ctypes.c_ulonglong(0)
+    assert lib.dsp_block_dquant(a.ctypes.data, D, H, W, bd, bh, bw, q, ctypes.byref(cnt_a), None) == 0, capi.last_error(lib)
+    b = c.copy()
+    cnt_b = ctypes.c_ulonglong(0)
+    fwd = Plan("f", [bd], [REDFT10], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=lib)
+    inv = Plan("f", [bd], [REDFT01], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=lib)
+    fwd.execute_host(b)
+    assert lib.dsp_block_quant(b"f", b.ctypes.data, D, H, W, bd, bh, bw, q, ctypes.byref(cnt_b), None) == 0
+    inv.execute_host(b)
+    fwd.destroy(); inv.destroy()
+    assert od.rel_l2(a, b.astype(np.float64)) < 2e-6
+    assert abs(int(cnt_a.value) - int(cnt_b.value)) <= max(2, int(cnt_b.value) // 1000)          # a coefficient on a quantiser tie may flip
+    assert lib.dsp_block_dquant(a.ctypes.data, D, H, W, 3, bh, bw, q, None, None) != 0           # unsupported depth: refused
+
+
+def test_gpu_count_knob_is_inert_without_gpus(lib):
+    """dsp_dct_plan_with_ngpus on the emulation build: accepted, plans stay on one (emulated) device"""
+    lib.dsp_dct_plan_with_ngpus(4)
+    p = Plan("f", [4, 8, 8], [REDFT10] * 3, lib=lib)
+    x = np.random.default_rng(1).random((4, 8, 8)).astype(np.float32)
+    y = p.execute_host(x.copy())
+    assert lib.dsp_dct_plan_ngpus(p._h) == 1
+    assert od.rel_l2(y, od.dctn_fast(x.astype(np.float64), [od.REDFT10] * 3)) < 1e-5
+    p.destroy()
+    lib.dsp_dct_plan_with_ngpus(1)
