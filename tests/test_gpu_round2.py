@@ -273,3 +273,58 @@ def test_zoom_dense_path_tensor_core_gemm(lib, kw):
     path_d, got_d, _ = cases.check_zoom(lib, "d", 301, 421, **kw)
     assert path_d == "dense"
     assert od.rel_l2(got, got_d) < 1e-5                      # float bases and float coefficients against the double session
+
+
+# ---------------------------------------------------------------------------------------------- sweeps added at the end of round 2
+@pytest.mark.parametrize("kw", [dict(), dict(damp=0.25, boost=1.5, bandpass=((0, 1, 1), (12, 60, 100))), dict(quant=0.05),
+                                dict(threshold=(0.001, 0.4), preserve_dc=1, damp=0.0, bandpass=((1, 0, 2), (16, 64, 128)))])
+def test_motion_coeff_stage_sweep_equals_the_fused_pass_on_gpu(lib, kw):
+    import ctypes
+    import torch
+    from dspfun_b200.dist3d import motion_params
+    D, H, W = 16, 72, 160
+    mp = motion_params((D, H, W), **kw)
+    c = (torch.randn(D, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) * 50).contiguous()
+    fused = Plan("f", [D, H, W], [REDFT01] * 3, lib=lib).fuse_motion_coeff(mp)
+    want = c.clone()
+    fused.execute_dev(want.data_ptr(), want.data_ptr(), None)
+    a = c.clone()
+    assert lib.dsp_motion_coeff_stage(b"f", ctypes.byref(mp), a.data_ptr(), None, None) == 0, capi.last_error(lib)
+    b = c.clone()
+    assert lib.dsp_motion_coeff_stage_flat(b"f", ctypes.byref(mp), b.data_ptr(), D, H * W, W, 0, None, None) == 0, capi.last_error(lib)
+    assert torch.equal(a, b)
+    plain = Plan("f", [D, H, W], [REDFT01] * 3, lib=lib)
+    plain.execute_dev(a.data_ptr(), a.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert torch.equal(a, want)
+    fused.destroy(); plain.destroy()
+
+
+@pytest.mark.parametrize("bd", [2, 4, 8, 16])
+def test_block_dquant_equals_the_three_sweeps_on_gpu(lib, bd):
+    import torch
+    D, H, W, bh, bw = 4 * bd, 64, 128, 8, 8
+    c = (torch.randn(D, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 200).contiguous()
+    q = float(np.float32(0.05 * 8.0 * np.sqrt(bd * bh * bw)))
+    a, b = c.clone(), c.clone()
+    ca = torch.zeros(1, dtype=torch.int64, device="cuda")
+    cb = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.dsp_block_dquant(a.data_ptr(), D, H, W, bd, bh, bw, q, ca.data_ptr(), None) == 0, capi.last_error(lib)
+    fwd = Plan("f", [bd], [REDFT10], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=lib)
+    inv = Plan("f", [bd], [REDFT01], H * W, None, H * W, 1, None, H * W, 1, D // bd, bd * H * W, bd * H * W, lib=lib)
+    fwd.execute_dev(b.data_ptr(), b.data_ptr(), None)
+    assert lib.dsp_block_quant(b"f", b.data_ptr(), D, H, W, bd, bh, bw, q, cb.data_ptr(), None) == 0
+    inv.execute_dev(b.data_ptr(), b.data_ptr(), None)
+    torch.cuda.synchronize()
+    # a coefficient that sits on a quantiser tie may round the other way (the direct sums and the FFT passes differ in the last
+    # bits): a handful of full quantiser steps in 10^5 coefficients, hence the looser bound with the quantiser on
+    assert od.rel_l2(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < 2e-4
+    assert abs(int(ca.item()) - int(cb.item())) <= max(2, int(cb.item()) // 1000)
+    a, b = c.clone(), c.clone()                                           # quantiser off: float accuracy
+    assert lib.dsp_block_dquant(a.data_ptr(), D, H, W, bd, bh, bw, 0.0, None, None) == 0
+    fwd.execute_dev(b.data_ptr(), b.data_ptr(), None)
+    assert lib.dsp_block_quant(b"f", b.data_ptr(), D, H, W, bd, bh, bw, 0.0, None, None) == 0
+    inv.execute_dev(b.data_ptr(), b.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert od.rel_l2(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < 2e-6
+    fwd.destroy(); inv.destroy()
