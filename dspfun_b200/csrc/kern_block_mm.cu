@@ -8,19 +8,21 @@
 //
 //     stage 1 (along w):  D1[r][gB+n] = sum_k X[r][gB+k] M[n][k]      A = X tile, K-major, as the TMA left it (128-byte
 //                                                                     swizzle), B = the block matrix, D1 in TMEM
-//     stage 2 (along h):  D2[c][gB+n] = sum_k D1[gB+k][c] M[n][k]     A = D1 read back from TMEM and written to shared
-//                                                                     memory MN-major (a transposing store), D2 in TMEM
+//     stage 2 (along h):  D2[c][gB+n] = sum_k D1[gB+k][c] M[n][k]     A = D1 read back from TMEM and stored transposed into
+//                                                                     shared memory, K-major in the same swizzled form;
+//                                                                     D2 in TMEM
 //     epilogue:           out[gB+n][c] = D2[c][gB+n]                  lane = image column: 128-byte coalesced stores
 //
 // M is FFTW's unnormalised REDFT10 or REDFT01 matrix of size B (B = 8 uses a block-diagonal pair so that N = 16).
 // The tensor cores multiply in TF32; to keep float accuracy every operand is split x = hi + lo (hi = the top 19 bits,
-// lo = x - hi, exact) and each product is three MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM): the error is
-// ~2^-21 relative per product instead of 2^-11.
+// which is what the MMA reads of an fp32 word, lo = x - hi, exact) and each product is three TF32 products with fp32
+// accumulation in TMEM, issued as two MMA sequences: A_hi [M_hi | M_lo] (one operand of width 2B) and A_lo M_hi onto the
+// small half; whoever reads the accumulator adds the halves.  The error is ~2^-21 relative per product instead of 2^-11.
 //
-// One persistent CTA per SM, 384 threads: eight front warps (operand split, MMA issue by thread 0, the TMEM -> shared
+// One persistent CTA per SM, 384 threads: eight front warps (lo operand, MMA issue by thread 0, the TMEM -> shared
 // hand-over between the stages) and four store warps that drain the finished accumulator of the previous tile while the
-// front works on the next one (D2 is double-buffered in TMEM).  Thread 0 also issues the TMA loads two tiles ahead;
-// completion comes back through mbarriers (cp.async.bulk.tensor complete_tx, tcgen05.commit).
+// front works on the next one.  Thread 0 also issues the TMA loads two tiles ahead; completion comes back through
+// mbarriers (cp.async.bulk.tensor complete_tx, tcgen05.commit).  DESIGN.md 4b has the measurements.
 #include "dsp_kernels.h"
 #include "dct_tma.cuh"
 #include <math.h>
