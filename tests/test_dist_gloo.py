@@ -128,8 +128,10 @@ def _pel_diff_ok(got, want, pel):
     return float(diff.mean())
 
 
-def _motion_worker(rank, world, port, dims, filt, q):
+def _motion_worker(rank, world, port, dims, filt, q, fuse=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if fuse:
+        os.environ["DSP_DIST_FUSE_COEFF"] = "1"        # the stage carried in the temporal pass's store instead of its own sweep
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from dspfun_b200.dist3d import Dist3D, motion_params
@@ -170,6 +172,28 @@ def test_motion_volume_u8_world2(filt):
     _pel_diff_ok(got, want, pel)
     if not filt:
         assert np.array_equal(got, vol)          # no filter: the round trip reproduces the 8-bit source
+
+
+def test_motion_volume_u8_world2_stage_carried_in_the_pass():
+    """DSP_DIST_FUSE_COEFF=1: the coefficient stage rides in the store of the forward temporal pass (flat coordinates) -- the
+    variant the sweep replaced; same pels"""
+    from oracle import pipelines as op
+    dims = (8, 12, 16)
+    filt = dict(boost=1.5, bandpass=((1, 2, 2), (6, 10, 12)), preserve_dc="dc")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_motion_worker, args=(r, 2, port, dims, filt, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.concatenate([r[1] for r in res])
+    vol = np.random.default_rng(21).integers(16, 236, dims).astype(np.uint8)
+    want, _, pel = op.motion_block(vol, dims, **filt)
+    _pel_diff_ok(got, want, pel)
 
 
 def test_motion_volume_single_rank_matches_session():
